@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the ensemble-HMC leapfrog hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c5|c5l4|c1]
+
+Workload at every N: BASELINE config 2 -- 100-D correlated Gaussian (dense precision
+Lambda = A A^T / D + I), ensemble of 2^20 particles, L = 50 leapfrog steps per HMC
+iteration, float32, Philox in-kernel RNG, synthetic data.  A "step" is ONE HMC
+iteration of the whole ensemble (momentum refresh + L leapfrog steps + Metropolis),
+i.e. P*L particle-leapfrog-steps in one fused kernel launch.  The 2^20 particles are
+sharded over the N ranks (strong scaling, no data-path collective).
+
+value  : particle-leapfrog-steps/s with the ensemble resident in HBM (device path).
+e2e    : the same metric through the public drop-in API on HOST buffers
+         (HMC.step on a host-backed Ensemble -> ehmc_hmc_iter host path): every step
+         copies q from pinned host memory, runs the kernel and copies q (+accept) back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KB = 1.380649e-23
+SEED = 20221018
+
+CONFIGS = {
+    # name: D, P, L, h, description
+    "c2": dict(D=100, P=1 << 20, L=50, h=0.05, desc="config2: 100-D dense-precision Gaussian, P=2^20, L=50"),
+    "c5": dict(D=10, P=1 << 22, L=20, h=0.05, desc="config5: Neal's funnel 10-D, P=2^22, L=20"),
+    "c5l4": dict(D=10, P=1 << 22, L=4, h=0.05, desc="config5 HBM-bound variant: funnel 10-D, P=2^22, L=4"),
+    "c1": dict(D=2, P=1024, L=20, h=0.05, desc="config1: 2-D isotropic Gaussian, P=1024, L=20"),
+}
+
+
+def flops_per_unit(name, D):
+    """Algorithmic flops per particle-leapfrog-step: grad U + 7 D."""
+    if name == "c2":
+        return 2.0 * D * D + 7.0 * D
+    if name.startswith("c5"):
+        return 110.0
+    return 2.0 * D + 7.0 * D
+
+
+def bytes_per_particle_iter(D, es=4):
+    """Algorithmic HBM bytes per particle-iteration in production mode: read q, write q, read mass."""
+    return 2.0 * D * es + es
+
+
+def make_precision(D):
+    rng = np.random.RandomState(SEED)
+    A = rng.standard_normal((D, D))
+    return A @ A.T / D + np.eye(D)
+
+
+def make_potential(E, name, D):
+    if name == "c2":
+        return E.GaussianPotential(precision=make_precision(D))
+    if name.startswith("c5"):
+        return E.FunnelPotential(D, 3.0)
+    return E.HarmonicPotential(np.ones(D))
+
+
+def make_oracle_potential(O, name, D):
+    if name == "c2":
+        return O.DenseGaussian(make_precision(D))
+    if name.startswith("c5"):
+        return O.Funnel(D, 3.0)
+    return O.DiagGaussian(np.ones(D))
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------
+def cpu_port_rate(name, cfg, sample_particles, iters):
+    """particle-leapfrog-steps/s of the NumPy float64 oracle (oracle/hmc_oracle.py) on a
+    bounded sample of the workload: `sample_particles` particles, `iters` HMC iterations."""
+    from oracle import hmc_oracle as O
+
+    D, L, h = cfg["D"], cfg["L"], cfg["h"]
+    pot = make_oracle_potential(O, name, D)
+    rng = np.random.RandomState(SEED)
+    q = rng.standard_normal((D, sample_particles))
+    mass = np.ones(sample_particles)
+    times = []
+    for _ in range(iters):
+        z = rng.standard_normal((D, sample_particles))
+        u = rng.uniform(size=sample_particles)
+        t0 = time.perf_counter()
+        q, _, _, _, _ = O.hmc_iter(q, z, u, mass, 1 / KB, h, L, pot)
+        times.append(time.perf_counter() - t0)
+    return sample_particles * L / float(np.median(times)), times
+
+
+def run_reference_arm(args, cfg, rank):
+    if rank != 0:
+        return
+    name = args.config
+    sample = min(cfg["P"], 1 << 14 if name == "c2" else 1 << 17)
+    rng_iters = args.warmup + args.steps
+    rate, times = cpu_port_rate(name, cfg, sample, rng_iters)
+    times = times[args.warmup:]
+    ms = 1e3 * float(np.mean(times))
+    value = sample * cfg["L"] / (ms * 1e-3)
+    threads = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "particle-leapfrog-steps/sec", "value": value,
+        "unit": "particle-leapfrog-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": cfg["desc"], "D": cfg["D"], "P": cfg["P"], "L": cfg["L"], "h": cfg["h"]},
+        "cpu_baseline": {"value": value, "unit": "particle-leapfrog-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} of {cfg['P']} particles per step (NumPy float64 oracle port of "
+                                   "src/integrator.py:105-120 + src/HMC.py:154-176, BLAS threads = host cores); "
+                                   "the reference itself is pure Python + JAX and cannot run here (no jax wheel)"},
+        "e2e": {"value": value, "unit": "particle-leapfrog-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# main arm
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = CONFIGS[args.config]
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import physicsbasedbayesianinference_b200 as E
+    from physicsbasedbayesianinference_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = _lib.Context.get(local_rank)
+    if os.environ.get("EHMC_DENSE_OCC"):
+        ctx.set_option("dense_occupancy", float(os.environ["EHMC_DENSE_OCC"]))
+
+    D, P, L, h = cfg["D"], cfg["P"], cfg["L"], cfg["h"]
+    # strong scaling: contiguous particle ranges per rank
+    p_lo = rank * P // world
+    p_hi = (rank + 1) * P // world
+    Pl = p_hi - p_lo
+    pot = make_potential(E, args.config, D)
+
+    ens = E.Ensemble(D, Pl, dtype=np.float32, device=dev, seed=SEED, particleOffset=p_lo)
+    ens.setPosition(1.0)
+    hmc = E.HMC(ens, L * h + 1e-9, h, None, potential=pot, seed=SEED, bugCompat=False)
+    assert hmc.integrator.numSteps == L
+
+    fp32_peak = ctx.measure_fp32_peak(300.0) if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        hmc.step(1 / KB)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        hmc.step(1 / KB)
+        ev[i + 1].record()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = P * L * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e through the host-facing API ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        qh_t = torch.empty((D, Pl), dtype=torch.float32, pin_memory=True)
+        qh_t.copy_(ens.q)
+        ens_h = E.Ensemble(D, Pl, dtype=np.float32, seed=SEED, particleOffset=p_lo)
+        ens_h.q = qh_t.numpy()
+        ens_h.mass = torch.ones(Pl, dtype=torch.float32, pin_memory=True).numpy()
+        hmc_h = E.HMC(ens_h, L * h + 1e-9, h, None, potential=pot, rng="philox", seed=SEED, bugCompat=False)
+        acc_h = torch.empty(Pl, dtype=torch.uint8, pin_memory=True).numpy()
+        hmc_h.step(1 / KB, accept=acc_h)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            hmc_h.step(1 / KB, accept=acc_h)  # returns after q and accept are back in host memory
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        e2e = {"value": P * L * args.e2e_steps / e2e_s, "unit": "particle-leapfrog-steps/s",
+               "h2d_bytes_per_step": int(D * Pl * 4 + Pl * 4), "d2h_bytes_per_step": int(D * Pl * 4 + Pl),
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
+               "api": "HMC.step on a host-backed Ensemble -> ehmc_hmc_iter (host path, pinned buffers)"}
+
+    if rank == 0:
+        kern_ms = float(np.mean(per_step))  # one kernel per step on this stream
+        fl = flops_per_unit(args.config, D)
+        ach_tf = Pl * L * fl / (kern_ms * 1e-3) / 1e12
+        by = bytes_per_particle_iter(D) * Pl
+        ach_gbs = by / (kern_ms * 1e-3) / 1e9
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
+        info = ctx.device_info()
+        nominal_fp32 = info["sm_count"] * 128 * 2 * info["sm_clock_mhz"] * 1e6 / 1e12
+        compute_bound = ach_tf / fp32_peak > ach_gbs / hbm_peak
+        if compute_bound:
+            roof = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": ach_tf / fp32_peak, "traffic": None,
+                    "peak_source": "measured in this run (ehmc_measure_fp32_peak, register-only FFMA kernel); "
+                                   f"nominal {nominal_fp32:.1f} = SMs*128*2*max clock",
+                    "flops_per_unit": fl, "units_per_launch": Pl * L}
+        else:
+            roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "bytes_per_unit": bytes_per_particle_iter(D) / L, "units_per_launch": Pl * L}
+        roof["kernel_ms"] = kern_ms
+        roof["other"] = {"hbm_GBps": ach_gbs, "hbm_frac": ach_gbs / hbm_peak, "fp32_TFLOPs": ach_tf,
+                         "fp32_frac": ach_tf / fp32_peak}
+        cpu = None
+        if not args.no_cpu_baseline:
+            sample = min(P, 1 << 14 if args.config == "c2" else 1 << 17)
+            rate, times = cpu_port_rate(args.config, cfg, sample, 3)
+            cpu = {"value": rate, "unit": "particle-leapfrog-steps/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{sample} of {P} particles x 3 iterations, median (NumPy float64 oracle port, "
+                             f"BLAS on all host cores; {sum(times):.1f} s of CPU wall time)"}
+        line = {
+            "metric": "particle-leapfrog-steps/sec", "value": value, "unit": "particle-leapfrog-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "D": D, "P": P, "L": L, "h": h, "particles_per_gpu": Pl,
+                       "rng": "philox in-kernel", "l2": "inputs_exceed_l2" if D * Pl * 4 > 126e6 else "resident",
+                       "parallelism": f"particle-shard x{world}, no data-path collective"},
+            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,213 @@
+/*
+ * ehmc -- B200-native ensemble-HMC engine: C-ABI of the leapfrog hot path.
+ *
+ * This is the drop-in boundary.  The reference
+ * (Anton-Le/PhysicsBasedBayesianInference) is pure Python and has no FFI; what
+ * a binding for its hot path has to replace is the arithmetic of
+ *
+ *   Ensemble.setPosition / setMomentum      src/ensemble.py:63-93
+ *   Leapfrog.integrate                      src/integrator.py:94-123
+ *   StormerVerlet.integrate                 src/integrator.py:126-165
+ *   Integrator.getAccel (gradient call)     src/integrator.py:61-73
+ *   potential.* (U and grad U)              src/potential.py:18-53
+ *   HMC.getWeightsRatio + getSamples body   src/HMC.py:106-116, 150-179
+ *
+ * Each entry point below names the reference lines it stands in for.  The
+ * Python classes in physicsbasedbayesianinference_b200/ (same names and
+ * signatures as the reference's) bind these symbols through ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - All tensors are borrowed DLTensor views (ehmc_dlpack.h).  State arrays are
+ *    (D, P) = (numDimensions, numParticles) with the PARTICLE index contiguous
+ *    (stride[1] == 1), exactly the reference's C-order np.zeros((D, P)) layout
+ *    (src/ensemble.py:40-41); stride[0] >= P may be larger (a column slice of a
+ *    bigger ensemble is a valid shard).  dtype float32 or float64, the same for
+ *    every tensor of a call.
+ *  - Tensors on kDLCUDA are used in place and all work is enqueued on `stream`
+ *    (a cudaStream_t; NULL = legacy default stream) without any host sync.
+ *    Tensors on kDLCPU / kDLCUDAHost select the HOST path: the library stages
+ *    them through context-owned device buffers (chunked, double-buffered H2D /
+ *    kernel / D2H) and returns after the results are back in host memory.
+ *  - Every function returns EHMC_OK (0) or a negative ehmc_status; the message is
+ *    available from ehmc_last_error().  No C++ exception crosses this boundary.
+ *  - A context is bound to one CUDA device and is not thread-safe.
+ *  - There is NO CPU implementation behind this interface: without a CUDA device
+ *    ehmc_ctx_create fails with EHMC_ERR_CUDA.
+ *
+ * RNG stream (production mode, z == NULL / u == NULL): Philox4x32-10 with
+ *    counter = (particle id lo, particle id hi, block, iteration lo)
+ *    key     = (seed lo, seed hi ^ iteration hi)
+ *  where "particle id" is the GLOBAL index (particleOffset + column), so results
+ *  do not depend on how the ensemble is sharded over GPUs.  float32: block b
+ *  gives the standard normals of dimensions 4b..4b+3 (two Box-Muller pairs);
+ *  float64: block b gives dimensions 2b, 2b+1 from 53-bit uniforms.  The
+ *  Metropolis uniform uses block 0xFFFFFFFF.  oracle/hmc_oracle.py::philox_stream
+ *  is the bit-level specification used by the tests.
+ */
+#ifndef EHMC_H_
+#define EHMC_H_
+
+#include <stdint.h>
+
+#include "ehmc_dlpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EHMC_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define EHMC_API __attribute__((visibility("default")))
+#else
+#define EHMC_API
+#endif
+
+typedef struct ehmc_ctx ehmc_ctx;
+typedef struct ehmc_potential ehmc_potential;
+
+typedef enum {
+  EHMC_OK = 0,
+  EHMC_ERR_INVALID = -1,     /* bad argument: shape, dtype, stride, device, NULL */
+  EHMC_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, ...) */
+  EHMC_ERR_UNSUPPORTED = -3, /* valid request outside the built kernel set */
+  EHMC_ERR_NOMEM = -4
+} ehmc_status;
+
+/* Potential families (replace the reference's arbitrary `potential`/`gradient`
+ * Python callables, src/HMC.py:52-60, src/integrator.py:73). */
+typedef enum {
+  /* U = 0.5 * dot(k, q**2)  -- harmonicPotentialND, src/potential.py:18-27.
+   * params: k[D].  scalars: none. */
+  EHMC_FAMILY_DIAG_GAUSSIAN = 1,
+  /* U = 0.5 (q-mu)^T Lambda (q-mu) -- the Gaussian targets of src/tests/test_HMC.py:122-125.
+   * params: Lambda[D,D] (row-major), optional mu[D].  scalars: none. */
+  EHMC_FAMILY_DENSE_GAUSSIAN = 2,
+  /* Neal's funnel, v = q[0]: U = v^2/(2 s^2) + 0.5 e^{-v} sum_{k>=1} q_k^2 + 0.5 (D-1) v.
+   * params: none.  scalars: {D, s}. */
+  EHMC_FAMILY_FUNNEL = 3,
+  /* Each ensemble particle is a B-body system, coordinates d = c*B + b (src/potential.py:83-84):
+   * U = -G sum_{i<j} m_i m_j / sqrt(|r_i-r_j|^2 + eps^2); -grad_i U / m_i is getAccelNBody
+   * (src/potential.py:30-53) for eps = 0.  params: bodyMass[B].  scalars: {G, eps}. */
+  EHMC_FAMILY_NBODY = 4,
+  /* Bayesian logistic regression: U = sum_n softplus(x_n.q) - y_n x_n.q + 0.5 |q|^2 / s^2.
+   * params: X[N,D] (row-major), y[N].  scalars: {s}. */
+  EHMC_FAMILY_LOGISTIC = 5
+} ehmc_family;
+
+typedef enum {
+  EHMC_LEAPFROG = 0,      /* method="Leapfrog",       src/HMC.py:62-65 */
+  EHMC_STORMER_VERLET = 1 /* method="Stormer-Verlet", src/HMC.py:66-69 */
+} ehmc_integrator;
+
+/* ehmc_hmc_args.flags */
+#define EHMC_FLAG_BUGCOMPAT_MOMENTUM 1u /* p_out of a rejected particle = its OLD POSITION   \
+                                           (src/HMC.py:176 writes oldQ, sic); off: old momentum */
+#define EHMC_FLAG_REJECT_NONFINITE 2u   /* reject when exp(oldH-newH) is NaN; the reference      \
+                                           ACCEPTS those (u > NaN is False, src/HMC.py:168-173) */
+
+typedef struct {
+  uint32_t struct_size;    /* sizeof(ehmc_hmc_args), for ABI growth */
+  uint32_t flags;          /* EHMC_FLAG_* */
+  int32_t integrator;      /* ehmc_integrator */
+  int32_t numSteps;        /* int(simulTime / stepSize), computed by the caller in Python exactly \
+                              like src/integrator.py:51 -- never in C */
+  double stepSize;         /* h */
+  double stepSizeSq;       /* h**2 as Python computes it (src/integrator.py:114) */
+  double boltzmann;        /* scipy.constants.Boltzmann */
+  double temperature;      /* momentum std = sqrt((mass * boltzmann) * temperature), ensemble.py:88 */
+  uint64_t seed;           /* Philox key */
+  uint64_t iteration;      /* HMC iteration index (Philox counter word 3) */
+  uint64_t particleOffset; /* global index of column 0 (multi-GPU shards) */
+} ehmc_hmc_args;
+
+/* ---- library / context ---------------------------------------------------- */
+EHMC_API int ehmc_version(void);
+/* Message of the last failing call on this thread (ctx may be NULL). */
+EHMC_API const char* ehmc_last_error(const ehmc_ctx* ctx);
+/* device < 0: current device.  Fails with EHMC_ERR_CUDA when no GPU is usable. */
+EHMC_API int ehmc_ctx_create(int device, ehmc_ctx** out);
+EHMC_API int ehmc_ctx_destroy(ehmc_ctx* ctx);
+/* Number of kernels of THIS library launched through ctx since creation. */
+EHMC_API int ehmc_ctx_launch_count(const ehmc_ctx* ctx, uint64_t* out);
+/* out[0]=SM count, out[1]=SM clock MHz (max), out[2]=total HBM bytes, out[3]=L2 bytes. */
+EHMC_API int ehmc_ctx_device_info(const ehmc_ctx* ctx, double out[4]);
+/* Tuning knobs: "dense_occupancy" (1|2: CTAs/SM variant of the float32 dense kernel),
+ * "host_chunk_mb" (bytes of state per staged chunk on the host path). */
+EHMC_API int ehmc_ctx_set_option(ehmc_ctx* ctx, const char* name, double value);
+/* Measures the sustained FP32 FMA rate of the device with a register-only FFMA
+ * kernel (2 flop per FMA) for about `millis` ms; the FP32 roofline denominator
+ * (MEASURED_PEAKS.json records none).  Synchronises the device. */
+EHMC_API int ehmc_measure_fp32_peak(ehmc_ctx* ctx, double millis, double* tflops_out);
+
+/* ---- potentials ------------------------------------------------------------ */
+/* Builds a device-resident, kernel-ready copy of the family's parameters (params may
+ * live on host or device, float32 or float64).  `dtype_bits` (32 or 64) selects the
+ * precision the potential will be used with. */
+EHMC_API int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* const* params, int nparams,
+                          const double* scalars, int nscalars, int dtype_bits, ehmc_potential** out);
+EHMC_API int ehmc_potential_destroy(ehmc_potential* pot);
+/* U(q) and/or grad U(q) for every column of q[D,P]: the vectorised form of the
+ * reference's potential(q[:, i]) / gradient(q[:, i]) callables (src/HMC.py:102,
+ * src/integrator.py:73; harmonicPotentialND on a (D,P) array, tests/test_potential.py:23).
+ * energy_out[P] and grad_out[D,P] are each optional (NULL). */
+EHMC_API int ehmc_potential_eval(ehmc_ctx* ctx, const ehmc_potential* pot, const DLTensor* q,
+                        DLTensor* energy_out, DLTensor* grad_out, void* stream);
+
+/* ---- ensemble initialisation (src/ensemble.py:63-93) ----------------------- */
+/* q <- N(0, qStd^2) from the Philox stream with iteration word 0xFFFFFFFFFFFFFFFF. */
+EHMC_API int ehmc_set_position(ehmc_ctx* ctx, DLTensor* q, double qStd, uint64_t seed,
+                      uint64_t particleOffset, void* stream);
+/* p <- z * sqrt((mass * boltzmann) * temperature), z from Philox (seed, iteration). */
+EHMC_API int ehmc_set_momentum(ehmc_ctx* ctx, DLTensor* p, const DLTensor* mass, double boltzmann,
+                      double temperature, uint64_t seed, uint64_t iteration,
+                      uint64_t particleOffset, void* stream);
+/* Raw stream: z[D,P] standard normals and/or u[P] uniforms in [0,1) (either may be NULL)
+ * exactly as ehmc_hmc_iter would draw them for (seed, iteration). */
+EHMC_API int ehmc_philox_fill(ehmc_ctx* ctx, DLTensor* z, DLTensor* u, uint64_t seed, uint64_t iteration,
+                     uint64_t particleOffset, void* stream);
+
+/* ---- integrators ----------------------------------------------------------- */
+/* Leapfrog.integrate(), src/integrator.py:105-120: advances q, p IN PLACE by
+ * numSteps steps (numSteps + 1 gradient evaluations), one fused kernel. */
+EHMC_API int ehmc_leapfrog(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p,
+                  const DLTensor* mass, double stepSize, double stepSizeSq, int numSteps,
+                  void* stream);
+/* StormerVerlet.integrate(), src/integrator.py:142-163 (numSteps + 1 position updates,
+ * backward-difference momentum). */
+EHMC_API int ehmc_stormer_verlet(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p,
+                        const DLTensor* mass, double stepSize, double stepSizeSq, int numSteps,
+                        void* stream);
+/* Reference N-body mode (Integrator(..., gradient=None), src/integrator.py:57-59,75-85):
+ * the ensemble's P particles ARE the bodies (D = 3 typically), acceleration from
+ * getAccelNBody (src/potential.py:30-53) with G = gravConst; body i finishes all its
+ * steps before body i+1 starts (the reference's sequential-in-time order). */
+EHMC_API int ehmc_integrate_nbody_mode(ehmc_ctx* ctx, int integrator, DLTensor* q, DLTensor* p,
+                              const DLTensor* mass, double gravConst, double stepSize,
+                              double stepSizeSq, int numSteps, void* stream);
+
+/* ---- one HMC iteration: the body of getSamples' loop, src/HMC.py:154-179 ---- */
+/* momentum refresh (ensemble.py:88-91) -> oldH (HMC.py:108-110) -> integrate (:161) ->
+ * newH (:111-114) -> ratio = exp(oldH-newH) (:115) -> reject iff u > min(1, ratio)
+ * (:168-173) -> q restored where rejected (:175).
+ *   q        [D,P] in/out
+ *   p_out    [D,P] optional: the momentum the reference stores in momentum_hmc (:179):
+ *            un-flipped integrated p where accepted; where rejected see EHMC_FLAG_BUGCOMPAT_MOMENTUM
+ *   mass     [P]
+ *   z        [D,P] optional standard normals (the reference's MT19937 draws, parity mode);
+ *            NULL -> Philox
+ *   u        [P]   optional Metropolis uniforms; NULL -> Philox
+ *   accept_out [P] uint8, optional: 1 = accepted
+ *   stats_out  [2D+3] float64, optional, OVERWRITTEN with this call's sums over the P
+ *            particles: {n_accept, sum min(1,ratio), sum H(kept state), sum_i q[d,i] (D),
+ *            sum_i q[d,i]^2 (D)} -- the per-iteration ensemble statistics that cross GPUs.
+ */
+EHMC_API int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p_out,
+                  const DLTensor* mass, const ehmc_hmc_args* args, const DLTensor* z,
+                  const DLTensor* u, DLTensor* accept_out, DLTensor* stats_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EHMC_H_ */

@@ -1,0 +1,204 @@
+"""HMC driver -- host mirror of the reference's ``src/HMC.py``.
+
+``HMC.getSamples`` keeps the reference's signature and return value
+(``samples[D, P, S]``, ``momenta[D, P, S]``) but every iteration of its loop body
+(src/HMC.py:154-179: momentum refresh, old Hamiltonian, trajectory, new
+Hamiltonian, Metropolis test, restore) is ONE fused CUDA kernel launched through
+``ehmc_hmc_iter``.
+
+RNG.  ``rng="numpy"`` (default for host ensembles) draws the momentum normals
+and the Metropolis uniforms from NumPy's global MT19937 in the reference's order
+ and feeds them to the kernel, so ``np.random.seed(s)`` followed
+by ``getSamples`` reproduces the reference's chain.  ``rng="philox"`` (default for
+device ensembles) draws inside the kernel from the counter-based Philox stream.
+
+Reference quirks kept, both visible only in the
+returned momenta: the stored momentum is the un-flipped integrated ``p``
+(src/HMC.py:164 rebinds a local), and rejected particles get their OLD POSITION
+written into ``p`` (src/HMC.py:176 ``= oldQ[:, mask]``, sic).  ``bugCompat=False``
+stores the old momentum instead.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .ensemble import boltzmannConst
+from .integrator import Leapfrog, StormerVerlet
+from .potential import Potential, _descriptor
+
+
+class HMC:
+    """Class with getSamples method (src/HMC.py:20-71)."""
+
+    def __init__(self, ensemble, simulTime, stepSize, density, potential=None, gradient=None, method="Leapfrog",
+                 rng=None, seed=None, bugCompat=True, rejectNonFinite=False):
+        """
+        ensemble (Ensemble)
+        simulTime (float): duration of the Hamiltonian simulation
+        stepSize (float)
+        density: kept for signature compatibility; a potential-family descriptor (or an
+                 object with a ``.potential`` descriptor) is accepted here too
+        potential: potential-family descriptor equal to -ln(density)
+        gradient: optional, the descriptor's ``.gradient`` (or the descriptor)
+        method (str): "Leapfrog" or "Stormer-Verlet"
+        """
+        self.ensemble = ensemble
+        self.simulTime = simulTime
+        self.stepSize = stepSize
+        self.density = density
+
+        desc = None
+        for cand in (potential, gradient, density, getattr(density, "potential", None)):
+            if cand is None:
+                continue
+            try:
+                desc = _descriptor(cand)
+                break
+            except TypeError:
+                continue
+        if desc is None:
+            _descriptor(potential if potential is not None else (gradient if gradient is not None else density))
+        self.potential = desc
+        self.gradient = desc.gradient
+
+        if method == "Leapfrog":
+            self.integrator = Leapfrog(ensemble, stepSize, simulTime, self.gradient)
+        elif method == "Stormer-Verlet":
+            self.integrator = StormerVerlet(ensemble, stepSize, simulTime, self.gradient)
+        else:
+            raise ValueError("Invalid integration method selected.")
+        self.method = method
+
+        if rng is None:
+            rng = "philox" if ensemble.onDevice else "numpy"
+        if rng not in ("numpy", "philox"):
+            raise ValueError("rng must be 'numpy' or 'philox'")
+        self.rng = rng
+        self.seed = ensemble.seed if seed is None else int(seed)
+        self.bugCompat = bool(bugCompat)
+        self.rejectNonFinite = bool(rejectNonFinite)
+        self.iteration = 0  # Philox iteration counter (persists across getSamples calls)
+        self.lastAccept = None
+
+    # U(x) = -log(p(x))
+    def potentialFunc(self, q):
+        """Potential at position q (src/HMC.py:75-84), evaluated on the GPU."""
+        return self.potential(q)
+
+    def _kinetic(self, p):
+        m = self.ensemble.mass
+        return 0.5 * (p * p).sum(0) / m
+
+    def getWeights(self, q, p):
+        """exp(-H) of every particle (src/HMC.py:86-104)."""
+        h = self._kinetic(p) + self.potential(q)
+        return np.exp(-h) if isinstance(h, np.ndarray) else h.neg().exp()
+
+    def getWeightsRatio(self, newQ, newP, oldQ, oldP):
+        """exp(oldH - newH) of every particle (src/HMC.py:106-116)."""
+        oldH = self._kinetic(oldP) + self.potential(oldQ)
+        newH = self._kinetic(newP) + self.potential(newQ)
+        d = oldH - newH
+        return np.exp(d) if isinstance(d, np.ndarray) else d.exp()
+
+    def print_information(self):
+        print("integrator: ", self.integrator)
+        print("final integration time: ", self.simulTime)
+        print("time step: ", self.stepSize)
+
+    # ------------------------------------------------------------------------------------
+    def _flags(self):
+        return (_lib.FLAG_BUGCOMPAT_MOMENTUM if self.bugCompat else 0) | (
+            _lib.FLAG_REJECT_NONFINITE if self.rejectNonFinite else 0)
+
+    def _args(self, temperature):
+        integ = _lib.LEAPFROG if self.method == "Leapfrog" else _lib.STORMER_VERLET
+        return _lib.make_args(self.stepSize, self.stepSize**2, self.integrator.numSteps, boltzmannConst, temperature,
+                              integ, self._flags(), self.seed, self.iteration, self.ensemble.particleOffset)
+
+    def step(self, temperature, p_out=None, accept=None, stats=None, z=None, u=None):
+        """One HMC iteration on ``integrator.q`` in place (the body of getSamples' loop)."""
+        q = self.integrator.q
+        host = isinstance(q, np.ndarray)
+        ctx = _lib.Context.get(None if host else q.device.index)
+        bits = (q.dtype.itemsize if host else q.element_size()) * 8
+        mass = self.integrator.mass
+        if host:
+            mass = np.ascontiguousarray(mass, dtype=q.dtype)
+        args = self._args(temperature)
+        _lib.hmc_iter(ctx, self.potential.handle(bits, ctx), q, mass, args, p_out=p_out, z=z, u=u, accept=accept,
+                      stats=stats, stream=_lib.current_stream_ptr(q))
+        self.iteration += 1
+
+    def getSamples(self, numSamples, temperature, qStd):
+        """Get samples from HMC (src/HMC.py:123-183).
+
+        Returns (samples_hmc, momentum_hmc), each (numDimensions, numParticles, numSamples),
+        NumPy float64 for host ensembles, torch tensors on the device for device ensembles.
+        """
+        ens = self.ensemble
+        D, P = ens.numDimensions, ens.numParticles
+        host = not ens.onDevice
+        if host:
+            samples_hmc = np.zeros((D, P, numSamples))
+            momentum_hmc = np.zeros_like(samples_hmc)
+        else:
+            import torch
+
+            samples_hmc = torch.zeros((D, P, numSamples), dtype=ens.dtype, device=ens.device)
+            momentum_hmc = torch.zeros_like(samples_hmc)
+
+        self.print_information()
+        self.integrator.q = ens.setPosition(qStd)
+        dt = self.integrator.q.dtype
+
+        if host:
+            p_buf = np.empty((D, P), dtype=dt)
+            acc = np.empty(P, dtype=np.uint8)
+        else:
+            p_buf = torch.empty((D, P), dtype=dt, device=ens.device)
+            acc = torch.empty(P, dtype=torch.uint8, device=ens.device)
+
+        for i in range(numSamples):
+            if i % 100 == 0:
+                print("HMC iteration ", i + 1)
+            z = u = None
+            if self.rng == "numpy":
+                # the reference's draws, in its order: norm.rvs((D,P)) for the momenta
+                # (ensemble.py:89-91, == standard_normal * pStd bit for bit), then uniform(P)
+                z = np.random.standard_normal((D, P))
+                u = np.random.uniform(size=P)
+                if host:
+                    z = z.astype(dt, copy=False)
+                    u = u.astype(dt, copy=False)
+                else:
+                    z = torch.from_numpy(z).to(device=ens.device, dtype=dt)
+                    u = torch.from_numpy(u).to(device=ens.device, dtype=dt)
+            self.step(temperature, p_out=p_buf, accept=acc, z=z, u=u)
+            self.integrator.p = p_buf
+            ens.p = p_buf
+            samples_hmc[:, :, i] = self.integrator.q
+            momentum_hmc[:, :, i] = self.integrator.p
+        ens.q = self.integrator.q
+        self.lastAccept = acc
+        return samples_hmc, momentum_hmc
+
+
+class GaussianDensity:
+    """Density object for the ``density`` argument: a multivariate normal whose
+    ``.potential`` is the matching GaussianPotential descriptor (the role played by
+    ``lambda q: multivariate_normal.pdf(q, mean, cov)`` in src/tests/test_HMC.py:48)."""
+
+    def __init__(self, mean, cov):
+        from .potential import GaussianPotential
+
+        self.mean = np.asarray(mean, dtype=np.float64)
+        self.cov = np.asarray(cov, dtype=np.float64)
+        self.potential = GaussianPotential(cov=self.cov, mean=self.mean)
+        d = self.mean.shape[0]
+        self._lognorm = 0.5 * (d * np.log(2 * np.pi) + np.linalg.slogdet(self.cov)[1])
+
+    def __call__(self, q):
+        u = self.potential(q)
+        return np.exp(-(u + self._lognorm)) if isinstance(u, (np.ndarray, np.floating, float)) else (-(u + self._lognorm)).exp()

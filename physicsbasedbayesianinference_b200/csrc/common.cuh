@@ -1,0 +1,178 @@
+// Shared device-side definitions for the ehmc kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ehmc {
+
+typedef unsigned long long u64;
+
+// ---------------------------------------------------------------------------
+// Arithmetic traits.
+// float : plain operators, nvcc may contract to FFMA (tolerance 1e-5, north_star).
+// double: explicit round-to-nearest mul/add so nothing is contracted -- the fp64
+//         mode evaluates the reference's expressions (src/integrator.py:112-118) in
+//         the reference's order and is bit-identical to NumPy for element-wise work.
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Ar;
+
+template <>
+struct Ar<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+  static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+  // x / m with a precomputed reciprocal (1 ulp off a true divide; fp32 tolerance 1e-5)
+  static __device__ __forceinline__ float divm(float x, float m, float inv_m) { return x * inv_m; }
+  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+  static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+};
+
+template <>
+struct Ar<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dadd_rn(a, -b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double divm(double x, double m, double) { return x / m; }
+  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+  static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Bit-level spec: oracle/hmc_oracle.py.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+#define EHMC_UNIFORM_BLOCK 0xFFFFFFFFu
+
+struct PhiloxKey {
+  uint2 key;
+  uint32_t it;
+  __device__ __forceinline__ PhiloxKey(u64 seed, u64 iteration) {
+    key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iteration >> 32));
+    it = (uint32_t)iteration;
+  }
+  __device__ __forceinline__ uint4 block(u64 pid, uint32_t blk) const {
+    return philox4x32_10(make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), blk, it), key);
+  }
+};
+
+// Standard normals of one Philox block.
+// float : 4 normals (dims 4b .. 4b+3);  double: 2 normals (dims 2b, 2b+1).
+template <typename T>
+struct NormalBlock;
+
+template <>
+struct NormalBlock<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void draw(const PhiloxKey& K, u64 pid, uint32_t blk, float* z) {
+    const uint4 r = K.block(pid, blk);
+    const float s = 5.9604644775390625e-8f;  // 2^-24
+    const float u1a = (float)((r.x >> 8) + 1u) * s, u2a = (float)(r.y >> 8) * s;
+    const float u1b = (float)((r.z >> 8) + 1u) * s, u2b = (float)(r.w >> 8) * s;
+    const float ra = sqrtf(-2.0f * logf(u1a)), rb = sqrtf(-2.0f * logf(u1b));
+    float sa, ca, sb, cb;
+    sincospif(2.0f * u2a, &sa, &ca);
+    sincospif(2.0f * u2b, &sb, &cb);
+    z[0] = ra * ca;
+    z[1] = ra * sa;
+    z[2] = rb * cb;
+    z[3] = rb * sb;
+  }
+  static __device__ __forceinline__ float uniform(const PhiloxKey& K, u64 pid) {
+    const uint4 r = K.block(pid, EHMC_UNIFORM_BLOCK);
+    return (float)(r.x >> 8) * 5.9604644775390625e-8f;
+  }
+};
+
+template <>
+struct NormalBlock<double> {
+  static constexpr int N = 2;
+  static __device__ __forceinline__ u64 u53(uint32_t a, uint32_t b) {
+    return ((u64)(a >> 6) << 27) | (u64)(b >> 5);
+  }
+  static __device__ __forceinline__ void draw(const PhiloxKey& K, u64 pid, uint32_t blk, double* z) {
+    const uint4 r = K.block(pid, blk);
+    const double s = 1.1102230246251565e-16;  // 2^-53
+    const double u1 = ((double)u53(r.x, r.y) + 1.0) * s, u2 = (double)u53(r.z, r.w) * s;
+    const double rr = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z[0] = rr * cs;
+    z[1] = rr * sn;
+  }
+  static __device__ __forceinline__ double uniform(const PhiloxKey& K, u64 pid) {
+    const uint4 r = K.block(pid, EHMC_UNIFORM_BLOCK);
+    return (double)u53(r.x, r.y) * 1.1102230246251565e-16;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Kernel argument block shared by every fused trajectory kernel.
+// (D,P) arrays: element [d, i] at base[d * ld + i].
+// ---------------------------------------------------------------------------
+template <typename T>
+struct IterArgs {
+  T* q;
+  long long q_ld;
+  T* p;  // integrate: momentum in/out.  hmc: optional momentum_hmc output (may be null)
+  long long p_ld;
+  const T* mass;
+  const T* z;  // optional fed standard normals (null -> Philox)
+  long long z_ld;
+  const T* u;              // optional fed uniforms (null -> Philox)
+  unsigned char* accept;   // optional
+  double* partials;        // optional [gridDim.x][2D+3] block partial sums
+  long long P;
+  int D;
+  int L;
+  unsigned flags;
+  T h, h2;
+  double kB, temp;
+  u64 seed, iter, offset;
+};
+
+constexpr unsigned FLAG_BUGCOMPAT = 1u;
+constexpr unsigned FLAG_REJECT_NONFINITE = 2u;
+
+constexpr int INTEG_LEAPFROG = 0;
+constexpr int INTEG_STORMER = 1;
+
+// momentum std of one particle: sqrt((m * kB) * T) in double (src/ensemble.py:88);
+// double because m*kB underflows float for molecular masses (tests/test_ensemble.py:74-80).
+template <typename T>
+__device__ __forceinline__ T momentum_std(T m, double kB, double temp) {
+  return (T)sqrt(__dmul_rn(__dmul_rn((double)m, kB), temp));
+}
+
+// Metropolis rule of src/HMC.py:168-173: reject iff u > min(1, exp(oldH - newH)).
+// np.minimum propagates NaN and (u > NaN) is False -> the reference ACCEPTS NaN ratios.
+template <typename T>
+__device__ __forceinline__ bool metropolis_reject(T oldH, T newH, T u, unsigned flags, T* accp_out) {
+  const T ratio = Ar<T>::exp_(Ar<T>::sub(oldH, newH));
+  const T accp = ratio < T(1) ? ratio : T(1);  // NaN -> 1 -> never rejected, as in the reference
+  *accp_out = accp;
+  bool rej = u > accp;
+  if ((flags & FLAG_REJECT_NONFINITE) && !(ratio == ratio)) rej = true;
+  return rej;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace ehmc

@@ -1,0 +1,823 @@
+// C-ABI of the ehmc engine (include/ehmc.h): argument validation, potential
+// packing, kernel dispatch, host-buffer staging.  No torch types, no exceptions.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "host_defs.h"
+#include "k_misc.cuh"
+
+using namespace ehmc;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int ehmc_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int DevBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return EHMC_OK;
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  const size_t want = bytes + bytes / 8;
+  if (cudaMalloc(&ptr, want) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(EHMC_ERR_NOMEM, "cudaMalloc(%zu) failed", want);
+  }
+  cap = want;
+  return EHMC_OK;
+}
+
+void DevBuf::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+
+// ---------------------------------------------------------------------------
+// DLTensor views
+// ---------------------------------------------------------------------------
+struct View {
+  char* data = nullptr;
+  int bits = 0;
+  int code = 0;
+  bool host = false;
+  int ndim = 0;
+  long long shape[2] = {1, 1};
+  long long ld = 0;  // elements between rows (2-D) ; 1-D: unused
+};
+
+static int parse(const DLTensor* t, const char* name, int ndim, View* v) {
+  if (t == nullptr) return fail(EHMC_ERR_INVALID, "%s: NULL tensor", name);
+  if (t->ndim != ndim) return fail(EHMC_ERR_INVALID, "%s: expected %d-D tensor, got %d-D", name, ndim, t->ndim);
+  if (t->dtype.lanes != 1) return fail(EHMC_ERR_INVALID, "%s: vector dtypes unsupported", name);
+  v->bits = t->dtype.bits;
+  v->code = t->dtype.code;
+  v->ndim = ndim;
+  switch (t->device.device_type) {
+    case kDLCUDA:
+    case kDLCUDAManaged:
+      v->host = false;
+      break;
+    case kDLCPU:
+    case kDLCUDAHost:
+      v->host = true;
+      break;
+    default:
+      return fail(EHMC_ERR_INVALID, "%s: unsupported device type %d", name, t->device.device_type);
+  }
+  for (int i = 0; i < ndim; ++i) {
+    v->shape[i] = t->shape[i];
+    if (t->shape[i] < 0) return fail(EHMC_ERR_INVALID, "%s: negative extent", name);
+  }
+  const long long inner = t->strides ? t->strides[ndim - 1] : 1;
+  if (inner != 1 && v->shape[ndim - 1] > 1)
+    return fail(EHMC_ERR_INVALID, "%s: innermost (particle) stride must be 1, got %lld", name, inner);
+  if (ndim == 2) {
+    v->ld = t->strides ? t->strides[0] : t->shape[1];
+    if (v->shape[0] > 1 && v->ld < v->shape[1])
+      return fail(EHMC_ERR_INVALID, "%s: row stride %lld < row length %lld", name, v->ld, v->shape[1]);
+    if (v->shape[0] <= 1 && v->ld < v->shape[1]) v->ld = v->shape[1];
+  }
+  v->data = static_cast<char*>(t->data) + t->byte_offset;
+  if (v->data == nullptr && v->shape[0] * v->shape[1] > 0) return fail(EHMC_ERR_INVALID, "%s: NULL data", name);
+  return EHMC_OK;
+}
+
+static int parse_float(const DLTensor* t, const char* name, int ndim, int bits, View* v) {
+  TRY(parse(t, name, ndim, v));
+  if (v->code != kDLFloat || (v->bits != 32 && v->bits != 64))
+    return fail(EHMC_ERR_INVALID, "%s: dtype must be float32 or float64", name);
+  if (bits && v->bits != bits)
+    return fail(EHMC_ERR_INVALID, "%s: dtype float%d does not match float%d of the call", name, v->bits, bits);
+  return EHMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// library / context
+// ---------------------------------------------------------------------------
+extern "C" int ehmc_version(void) { return EHMC_VERSION; }
+
+extern "C" const char* ehmc_last_error(const ehmc_ctx*) { return g_err; }
+
+extern "C" int ehmc_ctx_create(int device, ehmc_ctx** out) {
+  if (out == nullptr) return fail(EHMC_ERR_INVALID, "ehmc_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(EHMC_ERR_CUDA, "no usable CUDA device (%s); ehmc has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= n) return fail(EHMC_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  ehmc_ctx* c = new (std::nothrow) ehmc_ctx();
+  if (!c) return fail(EHMC_ERR_NOMEM, "out of host memory");
+  c->device = device;
+  if (cudaGetDeviceProperties(&c->prop, device) != cudaSuccess) {
+    delete c;
+    return fail(EHMC_ERR_CUDA, "cudaGetDeviceProperties failed");
+  }
+  if (c->prop.major < 10) {
+    const int major = c->prop.major, minor = c->prop.minor;
+    delete c;
+    return fail(EHMC_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a (B200) only", major, minor);
+  }
+  *out = c;
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_ctx_destroy(ehmc_ctx* c) {
+  if (!c) return EHMC_OK;
+  cudaSetDevice(c->device);
+  c->partials.release();
+  c->stage_stats.release();
+  for (int i = 0; i < N_STAGE; ++i) {
+    c->stage[i].release();
+    if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+  }
+  delete c;
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_ctx_launch_count(const ehmc_ctx* c, uint64_t* out) {
+  if (!c || !out) return fail(EHMC_ERR_INVALID, "ehmc_ctx_launch_count: NULL argument");
+  *out = c->launches;
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_ctx_device_info(const ehmc_ctx* c, double out[4]) {
+  if (!c || !out) return fail(EHMC_ERR_INVALID, "ehmc_ctx_device_info: NULL argument");
+  int clk = 0;
+  cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, c->device);
+  out[0] = c->prop.multiProcessorCount;
+  out[1] = clk / 1000.0;
+  out[2] = (double)c->prop.totalGlobalMem;
+  out[3] = (double)c->prop.l2CacheSize;
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) {
+  if (!c || !name) return fail(EHMC_ERR_INVALID, "ehmc_ctx_set_option: NULL argument");
+  if (!strcmp(name, "dense_occupancy")) {
+    if (value != 1 && value != 2) return fail(EHMC_ERR_INVALID, "dense_occupancy must be 1 or 2");
+    c->dense_occupancy = (int)value;
+  } else if (!strcmp(name, "host_chunk_mb")) {
+    if (!(value >= 1 && value <= 4096)) return fail(EHMC_ERR_INVALID, "host_chunk_mb must be in [1, 4096]");
+    c->host_chunk_bytes = (long long)value << 20;
+  } else {
+    return fail(EHMC_ERR_INVALID, "unknown option '%s'", name);
+  }
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_measure_fp32_peak(ehmc_ctx* c, double millis, double* tflops_out) {
+  if (!c || !tflops_out) return fail(EHMC_ERR_INVALID, "ehmc_measure_fp32_peak: NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  float* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 4));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int blocks = c->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  const double flop_per_launch = (double)blocks * threads * iters * 16.0 * 8.0 * 2.0;
+  double best = 0.0, elapsed = 0.0;
+  k_fma_peak<<<blocks, threads>>>(d, 64, 0.999f, 0.001f);  // warm-up
+  c->launches++;
+  while (elapsed < millis) {
+    cudaEventRecord(e0);
+    k_fma_peak<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+    c->launches++;
+    cudaEventRecord(e1);
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    elapsed += ms;
+    best = std::max(best, flop_per_launch / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  CUDA_TRY(cudaGetLastError());
+  *tflops_out = best;
+  return EHMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// potentials
+// ---------------------------------------------------------------------------
+static int fetch_param(const DLTensor* t, const char* name, int ndim, std::vector<double>* out, View* v) {
+  TRY(parse_float(t, name, ndim, 0, v));
+  const long long rows = ndim == 2 ? v->shape[0] : 1, cols = v->shape[ndim - 1];
+  const size_t es = v->bits / 8;
+  std::vector<char> tmp((size_t)rows * cols * es);
+  const size_t pitch = (ndim == 2 ? v->ld : cols) * es;
+  if (rows * cols > 0)
+    CUDA_TRY(cudaMemcpy2D(tmp.data(), cols * es, v->data, pitch, cols * es, rows,
+                          v->host ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost));
+  out->resize((size_t)rows * cols);
+  for (size_t i = 0; i < out->size(); ++i)
+    (*out)[i] = v->bits == 32 ? (double)reinterpret_cast<float*>(tmp.data())[i] : reinterpret_cast<double*>(tmp.data())[i];
+  return EHMC_OK;
+}
+
+template <typename T>
+static int upload(const std::vector<double>& h, void** dptr) {
+  std::vector<T> t(h.size());
+  for (size_t i = 0; i < h.size(); ++i) t[i] = (T)h[i];
+  *dptr = nullptr;
+  if (h.empty()) return EHMC_OK;
+  CUDA_TRY(cudaMalloc(dptr, sizeof(T) * t.size()));
+  CUDA_TRY(cudaMemcpy(*dptr, t.data(), sizeof(T) * t.size(), cudaMemcpyHostToDevice));
+  return EHMC_OK;
+}
+
+static int upload_bits(int bits, const std::vector<double>& h, void** dptr) {
+  return bits == 32 ? upload<float>(h, dptr) : upload<double>(h, dptr);
+}
+
+extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* const* params, int nparams,
+                                     const double* scalars, int nscalars, int dtype_bits, ehmc_potential** out) {
+  if (!ctx || !out) return fail(EHMC_ERR_INVALID, "ehmc_potential_create: NULL argument");
+  *out = nullptr;
+  if (dtype_bits != 32 && dtype_bits != 64) return fail(EHMC_ERR_INVALID, "dtype_bits must be 32 or 64");
+  if (nparams < 0 || nscalars < 0 || (nparams > 0 && !params) || (nscalars > 0 && !scalars))
+    return fail(EHMC_ERR_INVALID, "ehmc_potential_create: bad params/scalars");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ehmc_potential* p = new (std::nothrow) ehmc_potential();
+  if (!p) return fail(EHMC_ERR_NOMEM, "out of host memory");
+  p->ctx = ctx;
+  p->family = family;
+  p->bits = dtype_bits;
+  p->scalars.assign(scalars, scalars + nscalars);
+  int rc = EHMC_OK;
+  View v;
+  switch (family) {
+    case EHMC_FAMILY_DIAG_GAUSSIAN: {
+      if (nparams != 1) { rc = fail(EHMC_ERR_INVALID, "diag gaussian: params = {k[D]}"); break; }
+      rc = fetch_param(params[0], "k", 1, &p->hp0, &v);
+      if (rc) break;
+      p->D = (int)p->hp0.size();
+      if (p->D < 1) { rc = fail(EHMC_ERR_INVALID, "diag gaussian: empty k"); break; }
+      if (p->D > 32 && p->D <= 128) {
+        // route through the dense kernel with Lambda = diag(k)
+        std::vector<double> lam((size_t)p->D * p->D, 0.0);
+        for (int d = 0; d < p->D; ++d) lam[(size_t)d * p->D + d] = p->hp0[d];
+        p->hp0.swap(lam);
+        p->hp1.assign(p->D, 0.0);
+        p->family = EHMC_FAMILY_DENSE_GAUSSIAN;
+      } else if (p->D > 128) {
+        rc = fail(EHMC_ERR_UNSUPPORTED, "diag gaussian: D = %d > 128 not built", p->D);
+      }
+      break;
+    }
+    case EHMC_FAMILY_DENSE_GAUSSIAN: {
+      if (nparams < 1 || nparams > 2) { rc = fail(EHMC_ERR_INVALID, "dense gaussian: params = {Lambda[D,D], mu[D]?}"); break; }
+      rc = fetch_param(params[0], "Lambda", 2, &p->hp0, &v);
+      if (rc) break;
+      if (v.shape[0] != v.shape[1] || v.shape[0] < 1) { rc = fail(EHMC_ERR_INVALID, "Lambda must be square"); break; }
+      p->D = (int)v.shape[0];
+      if (nparams == 2 && params[1] != nullptr) {
+        rc = fetch_param(params[1], "mu", 1, &p->hp1, &v);
+        if (rc) break;
+        if ((int)p->hp1.size() != p->D) { rc = fail(EHMC_ERR_INVALID, "mu must have D entries"); break; }
+      } else {
+        p->hp1.assign(p->D, 0.0);
+      }
+      if (p->D > 128) rc = fail(EHMC_ERR_UNSUPPORTED, "dense gaussian: D = %d > 128 not built", p->D);
+      break;
+    }
+    case EHMC_FAMILY_FUNNEL: {
+      if (nscalars != 2) { rc = fail(EHMC_ERR_INVALID, "funnel: scalars = {D, sigma_v}"); break; }
+      p->D = (int)scalars[0];
+      if (p->D < 2 || p->D > 32) { rc = fail(EHMC_ERR_UNSUPPORTED, "funnel: 2 <= D <= 32 (got %d)", p->D); break; }
+      if (!(scalars[1] > 0)) rc = fail(EHMC_ERR_INVALID, "funnel: sigma_v must be > 0");
+      break;
+    }
+    default:
+      rc = fail(EHMC_ERR_UNSUPPORTED, "potential family %d is not built into this library", family);
+  }
+  if (rc == EHMC_OK && p->family == EHMC_FAMILY_DENSE_GAUSSIAN) {
+    const int D = p->D;
+    rc = upload_bits(p->bits, p->hp0, &p->d2);
+    if (rc == EHMC_OK && D > 16) {
+      const int TN = dense_tn(D);
+      const int TNP = p->bits == 32 ? dense_tnp<float>(TN) : dense_tnp<double>(TN);
+      p->TN = TN;
+      std::vector<double> Ls((size_t)D * K2_WARPS_HOST * TNP, 0.0), mu((size_t)K2_WARPS_HOST * TN, 0.0);
+      for (int k = 0; k < D; ++k)
+        for (int w = 0; w < K2_WARPS_HOST; ++w)
+          for (int j = 0; j < TN; ++j) {
+            const int i = w * TN + j;
+            if (i < D) Ls[((size_t)k * K2_WARPS_HOST + w) * TNP + j] = p->hp0[(size_t)i * D + k];
+          }
+      for (int d = 0; d < D; ++d) mu[d] = p->hp1[d];
+      rc = upload_bits(p->bits, Ls, &p->d0);
+      if (rc == EHMC_OK) rc = upload_bits(p->bits, mu, &p->d1);
+    } else if (rc == EHMC_OK) {
+      rc = upload_bits(p->bits, p->hp1, &p->d1);
+    }
+  }
+  if (rc != EHMC_OK) {
+    ehmc_potential_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_potential_destroy(ehmc_potential* p) {
+  if (!p) return EHMC_OK;
+  if (p->ctx) cudaSetDevice(p->ctx->device);
+  if (p->d0) cudaFree(p->d0);
+  if (p->d1) cudaFree(p->d1);
+  if (p->d2) cudaFree(p->d2);
+  delete p;
+  return EHMC_OK;
+}
+
+// number of CTAs the trajectory kernel uses for P particles (statistics partials)
+template <typename T>
+static long long traj_blocks(const ehmc_potential* p, long long P) {
+  if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) {
+    const int PT = dense_particles_per_cta<T>();
+    return (P + PT - 1) / PT;
+  }
+  return (P + K1_THREADS_HOST - 1) / K1_THREADS_HOST;
+}
+
+template <typename T>
+static int launch_traj(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc,
+                       cudaStream_t st) {
+  if (A.P == 0) return EHMC_OK;
+  if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) return launch_dense<T>(c, p, A, integ, hmc, st);
+  return launch_small<T>(c, p, A, integ, hmc, st);
+}
+
+// ---------------------------------------------------------------------------
+// argument assembly shared by integrate / hmc_iter
+// ---------------------------------------------------------------------------
+struct CallViews {
+  View q, p, mass, z, u, accept, stats;
+  bool has_p = false, has_z = false, has_u = false, has_accept = false, has_stats = false;
+  int bits = 0;
+  long long D = 0, P = 0;
+};
+
+static int check_same_place(const CallViews& v) {
+  const bool host = v.q.host;
+  if (v.mass.host != host || (v.has_p && v.p.host != host) || (v.has_z && v.z.host != host) ||
+      (v.has_u && v.u.host != host) || (v.has_accept && v.accept.host != host) ||
+      (v.has_stats && v.stats.host != host))
+    return fail(EHMC_ERR_INVALID, "all tensors of a call must live on the same side (all host or all device)");
+  return EHMC_OK;
+}
+
+template <typename T>
+static IterArgs<T> base_args(const CallViews& v, double h, double h2, int L) {
+  IterArgs<T> A;
+  memset(&A, 0, sizeof(A));
+  A.q = reinterpret_cast<T*>(v.q.data);
+  A.q_ld = v.q.ld;
+  A.p = v.has_p ? reinterpret_cast<T*>(v.p.data) : nullptr;
+  A.p_ld = v.has_p ? v.p.ld : 0;
+  A.mass = reinterpret_cast<const T*>(v.mass.data);
+  A.z = v.has_z ? reinterpret_cast<const T*>(v.z.data) : nullptr;
+  A.z_ld = v.has_z ? v.z.ld : 0;
+  A.u = v.has_u ? reinterpret_cast<const T*>(v.u.data) : nullptr;
+  A.accept = v.has_accept ? reinterpret_cast<unsigned char*>(v.accept.data) : nullptr;
+  A.partials = nullptr;
+  A.P = v.P;
+  A.D = (int)v.D;
+  A.L = L;
+  A.h = (T)h;
+  A.h2 = (T)h2;
+  return A;
+}
+
+// Device path of one iteration / integration.  Statistics go to stats_dev (device, 2D+3 doubles).
+template <typename T>
+static int run_device(ehmc_ctx* c, const ehmc_potential* pot, IterArgs<T> A, int integ, bool hmc, double* stats_dev,
+                      cudaStream_t st) {
+  const int NS = 2 * A.D + 3;
+  long long nblk = 0;
+  if (stats_dev != nullptr) {
+    nblk = traj_blocks<T>(pot, A.P);
+    TRY(c->partials.ensure(sizeof(double) * (size_t)std::max(1LL, nblk) * NS));
+    A.partials = static_cast<double*>(c->partials.ptr);
+  }
+  TRY(launch_traj<T>(c, pot, A, integ, hmc, st));
+  if (stats_dev != nullptr) {
+    k_stats_finalize<<<NS, 256, 0, st>>>(A.partials, (int)nblk, NS, stats_dev);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return EHMC_OK;
+}
+
+// Host path: particles are processed in column chunks; chunk k uses stream k % N_STAGE with
+// its own staging slab, so H2D of chunk k+1 / kernel of chunk k / D2H of chunk k-1 overlap.
+template <typename T>
+static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, IterArgs<T> proto, int integ, bool hmc) {
+  const long long D = v.D, P = v.P;
+  const int NS = 2 * (int)D + 3;
+  for (int i = 0; i < N_STAGE; ++i) {
+    if (!c->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+  }
+  // chunk size: multiple of 512 particles, ~32 MB of state per array, at least 3 chunks when P is large
+  long long chunk = std::max<long long>(512, c->host_chunk_bytes / (long long)(sizeof(T) * std::max<long long>(D, 1)));
+  chunk = (chunk / 512) * 512;
+  if (P > 3 * 512 && chunk * N_STAGE > P) chunk = std::max<long long>(512, ((P / N_STAGE + 511) / 512) * 512);
+  chunk = std::min(chunk, std::max<long long>(P, 1));
+  const long long nchunks = P == 0 ? 0 : (P + chunk - 1) / chunk;
+  // slab layout (elements of T): q[D][chunk] p[D][chunk] z[D][chunk] mass[chunk] u[chunk] | accept bytes
+  const size_t arr = (size_t)D * chunk;
+  const size_t slab_elems = 3 * arr + 2 * (size_t)chunk;
+  const size_t slab_bytes = slab_elems * sizeof(T) + (size_t)chunk + 64;
+  for (int i = 0; i < N_STAGE; ++i) TRY(c->stage[i].ensure(slab_bytes));
+  long long blocks_total = 0;
+  std::vector<long long> blk_off((size_t)nchunks + 1, 0);
+  for (long long k = 0; k < nchunks; ++k) {
+    const long long n = std::min(chunk, P - k * chunk);
+    blk_off[k] = blocks_total;
+    blocks_total += traj_blocks<T>(pot, n);
+  }
+  if (v.has_stats) {
+    TRY(c->partials.ensure(sizeof(double) * (size_t)std::max(1LL, blocks_total) * NS));
+    TRY(c->stage_stats.ensure(sizeof(double) * NS));
+  }
+  const size_t es = sizeof(T);
+  for (long long k = 0; k < nchunks; ++k) {
+    const int s = (int)(k % N_STAGE);
+    cudaStream_t st = c->streams[s];
+    const long long c0 = k * chunk, n = std::min(chunk, P - c0);
+    T* base = static_cast<T*>(c->stage[s].ptr);
+    T* dq = base;
+    T* dp = base + arr;
+    T* dz = base + 2 * arr;
+    T* dm = base + 3 * arr;
+    T* du = dm + chunk;
+    unsigned char* dacc = reinterpret_cast<unsigned char*>(du + chunk);
+    // the slab is reused every N_STAGE chunks: stream order already serialises the reuse
+    CUDA_TRY(cudaMemcpy2DAsync(dq, chunk * es, v.q.data + c0 * es, v.q.ld * es, n * es, D, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dm, v.mass.data + c0 * es, n * es, cudaMemcpyHostToDevice, st));
+    if (!hmc)
+      CUDA_TRY(cudaMemcpy2DAsync(dp, chunk * es, v.p.data + c0 * es, v.p.ld * es, n * es, D, cudaMemcpyHostToDevice, st));
+    if (v.has_z)
+      CUDA_TRY(cudaMemcpy2DAsync(dz, chunk * es, v.z.data + c0 * es, v.z.ld * es, n * es, D, cudaMemcpyHostToDevice, st));
+    if (v.has_u) CUDA_TRY(cudaMemcpyAsync(du, v.u.data + c0 * es, n * es, cudaMemcpyHostToDevice, st));
+    IterArgs<T> A = proto;
+    A.q = dq;
+    A.q_ld = chunk;
+    A.p = v.has_p ? dp : nullptr;
+    A.p_ld = chunk;
+    A.mass = dm;
+    A.z = v.has_z ? dz : nullptr;
+    A.z_ld = chunk;
+    A.u = v.has_u ? du : nullptr;
+    A.accept = v.has_accept ? dacc : nullptr;
+    A.P = n;
+    A.offset = proto.offset + (u64)c0;
+    A.partials = v.has_stats ? static_cast<double*>(c->partials.ptr) + (size_t)blk_off[k] * NS : nullptr;
+    TRY(launch_traj<T>(c, pot, A, integ, hmc, st));
+    CUDA_TRY(cudaMemcpy2DAsync(v.q.data + c0 * es, v.q.ld * es, dq, chunk * es, n * es, D, cudaMemcpyDeviceToHost, st));
+    if (v.has_p)
+      CUDA_TRY(cudaMemcpy2DAsync(v.p.data + c0 * es, v.p.ld * es, dp, chunk * es, n * es, D, cudaMemcpyDeviceToHost, st));
+    if (v.has_accept) CUDA_TRY(cudaMemcpyAsync(v.accept.data + c0, dacc, n, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < N_STAGE; ++i) CUDA_TRY(cudaStreamSynchronize(c->streams[i]));
+  if (v.has_stats) {
+    cudaStream_t st = c->streams[0];
+    k_stats_finalize<<<NS, 256, 0, st>>>(static_cast<double*>(c->partials.ptr), (int)blocks_total, NS,
+                                         static_cast<double*>(c->stage_stats.ptr));
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(v.stats.data, c->stage_stats.ptr, sizeof(double) * NS, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return EHMC_OK;
+}
+
+static int common_checks(ehmc_ctx* ctx, const ehmc_potential* pot, const DLTensor* q, const DLTensor* mass,
+                         CallViews* v, const char* fn) {
+  if (!ctx || !pot) return fail(EHMC_ERR_INVALID, "%s: NULL context or potential", fn);
+  if (pot->ctx != ctx) return fail(EHMC_ERR_INVALID, "%s: potential belongs to another context", fn);
+  TRY(parse_float(q, "q", 2, 0, &v->q));
+  v->bits = v->q.bits;
+  v->D = v->q.shape[0];
+  v->P = v->q.shape[1];
+  if (v->bits != pot->bits)
+    return fail(EHMC_ERR_INVALID, "%s: q is float%d but the potential was created for float%d", fn, v->bits, pot->bits);
+  if (v->D != pot->D)
+    return fail(EHMC_ERR_INVALID, "%s: q has %lld dimensions, the potential has %d", fn, v->D, pot->D);
+  TRY(parse_float(mass, "mass", 1, v->bits, &v->mass));
+  if (v->mass.shape[0] != v->P) return fail(EHMC_ERR_INVALID, "%s: mass must have P = %lld entries", fn, v->P);
+  return EHMC_OK;
+}
+
+static int integrate_entry(ehmc_ctx* ctx, const ehmc_potential* pot, int integ, DLTensor* q, DLTensor* p,
+                           const DLTensor* mass, double h, double h2, int L, void* stream, const char* fn) {
+  CallViews v;
+  TRY(common_checks(ctx, pot, q, mass, &v, fn));
+  if (L < 0) return fail(EHMC_ERR_INVALID, "%s: numSteps < 0", fn);
+  TRY(parse_float(p, "p", 2, v.bits, &v.p));
+  v.has_p = true;
+  if (v.p.shape[0] != v.D || v.p.shape[1] != v.P) return fail(EHMC_ERR_INVALID, "%s: p must have q's shape", fn);
+  TRY(check_same_place(v));
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (v.bits == 32) {
+    IterArgs<float> A = base_args<float>(v, h, h2, L);
+    return v.q.host ? run_host<float>(ctx, pot, v, A, integ, false) : run_device<float>(ctx, pot, A, integ, false, nullptr, st);
+  }
+  IterArgs<double> A = base_args<double>(v, h, h2, L);
+  return v.q.host ? run_host<double>(ctx, pot, v, A, integ, false) : run_device<double>(ctx, pot, A, integ, false, nullptr, st);
+}
+
+extern "C" int ehmc_leapfrog(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p, const DLTensor* mass,
+                             double stepSize, double stepSizeSq, int numSteps, void* stream) {
+  return integrate_entry(ctx, pot, INTEG_LEAPFROG, q, p, mass, stepSize, stepSizeSq, numSteps, stream, "ehmc_leapfrog");
+}
+
+extern "C" int ehmc_stormer_verlet(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p,
+                                   const DLTensor* mass, double stepSize, double stepSizeSq, int numSteps,
+                                   void* stream) {
+  return integrate_entry(ctx, pot, INTEG_STORMER, q, p, mass, stepSize, stepSizeSq, numSteps, stream,
+                         "ehmc_stormer_verlet");
+}
+
+extern "C" int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p_out,
+                             const DLTensor* mass, const ehmc_hmc_args* a, const DLTensor* z, const DLTensor* u,
+                             DLTensor* accept_out, DLTensor* stats_out, void* stream) {
+  const char* fn = "ehmc_hmc_iter";
+  CallViews v;
+  TRY(common_checks(ctx, pot, q, mass, &v, fn));
+  if (!a) return fail(EHMC_ERR_INVALID, "%s: args is NULL", fn);
+  if (a->struct_size != sizeof(ehmc_hmc_args))
+    return fail(EHMC_ERR_INVALID, "%s: args.struct_size %u != %zu", fn, a->struct_size, sizeof(ehmc_hmc_args));
+  if (a->numSteps < 0) return fail(EHMC_ERR_INVALID, "%s: numSteps < 0", fn);
+  if (a->integrator != EHMC_LEAPFROG && a->integrator != EHMC_STORMER_VERLET)
+    return fail(EHMC_ERR_INVALID, "%s: Invalid integration method selected.", fn);
+  if (p_out) {
+    TRY(parse_float(p_out, "p_out", 2, v.bits, &v.p));
+    v.has_p = true;
+    if (v.p.shape[0] != v.D || v.p.shape[1] != v.P) return fail(EHMC_ERR_INVALID, "%s: p_out must have q's shape", fn);
+  }
+  if (z) {
+    TRY(parse_float(z, "z", 2, v.bits, &v.z));
+    v.has_z = true;
+    if (v.z.shape[0] != v.D || v.z.shape[1] != v.P) return fail(EHMC_ERR_INVALID, "%s: z must have q's shape", fn);
+  }
+  if (u) {
+    TRY(parse_float(u, "u", 1, v.bits, &v.u));
+    v.has_u = true;
+    if (v.u.shape[0] != v.P) return fail(EHMC_ERR_INVALID, "%s: u must have P entries", fn);
+  }
+  if (accept_out) {
+    TRY(parse(accept_out, "accept_out", 1, &v.accept));
+    v.has_accept = true;
+    if (v.accept.bits != 8 || v.accept.shape[0] != v.P)
+      return fail(EHMC_ERR_INVALID, "%s: accept_out must be uint8/bool[P]", fn);
+  }
+  if (stats_out) {
+    TRY(parse_float(stats_out, "stats_out", 1, 64, &v.stats));
+    v.has_stats = true;
+    if (v.stats.shape[0] != 2 * v.D + 3) return fail(EHMC_ERR_INVALID, "%s: stats_out must be float64[2D+3]", fn);
+  }
+  TRY(check_same_place(v));
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto fill = [&](auto& A) {
+    A.flags = a->flags;
+    A.kB = a->boltzmann;
+    A.temp = a->temperature;
+    A.seed = a->seed;
+    A.iter = a->iteration;
+    A.offset = a->particleOffset;
+  };
+  if (v.bits == 32) {
+    IterArgs<float> A = base_args<float>(v, a->stepSize, a->stepSizeSq, a->numSteps);
+    fill(A);
+    if (v.q.host) return run_host<float>(ctx, pot, v, A, a->integrator, true);
+    return run_device<float>(ctx, pot, A, a->integrator, true,
+                             v.has_stats ? reinterpret_cast<double*>(v.stats.data) : nullptr, st);
+  }
+  IterArgs<double> A = base_args<double>(v, a->stepSize, a->stepSizeSq, a->numSteps);
+  fill(A);
+  if (v.q.host) return run_host<double>(ctx, pot, v, A, a->integrator, true);
+  return run_device<double>(ctx, pot, A, a->integrator, true,
+                            v.has_stats ? reinterpret_cast<double*>(v.stats.data) : nullptr, st);
+}
+
+// ---------------------------------------------------------------------------
+// potential evaluation
+// ---------------------------------------------------------------------------
+template <typename T>
+static int eval_device(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
+                       long long g_ld, cudaStream_t st) {
+  if (P == 0) return EHMC_OK;
+  if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN) {
+    const T* mu = static_cast<const T*>(p->d1);
+    k_eval_dense<T><<<(unsigned)((P + 127) / 128), 128, 0, st>>>(q, q_ld, P, p->D, static_cast<const T*>(p->d2), mu, e, g, g_ld);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return EHMC_OK;
+  }
+  return eval_small<T>(c, p, q, q_ld, P, e, g, g_ld, st);
+}
+
+template <typename T>
+static int eval_any(ehmc_ctx* c, const ehmc_potential* p, const View& q, const View* e, const View* g, cudaStream_t st) {
+  const long long D = q.shape[0], P = q.shape[1];
+  if (!q.host) {
+    return eval_device<T>(c, p, reinterpret_cast<const T*>(q.data), q.ld, P, e ? reinterpret_cast<T*>(e->data) : nullptr,
+                          g ? reinterpret_cast<T*>(g->data) : nullptr, g ? g->ld : 0, st);
+  }
+  // host path: one shot through stage[0]/stage[1] (evaluation is not a hot path)
+  const size_t es = sizeof(T);
+  TRY(c->stage[0].ensure(es * (size_t)(2 * D + 1) * std::max<long long>(P, 1)));
+  T* dq = static_cast<T*>(c->stage[0].ptr);
+  T* dg = dq + (size_t)D * P;
+  T* de = dg + (size_t)D * P;
+  if (P > 0) CUDA_TRY(cudaMemcpy2D(dq, P * es, q.data, q.ld * es, P * es, D, cudaMemcpyHostToDevice));
+  TRY(eval_device<T>(c, p, dq, P, P, e ? de : nullptr, g ? dg : nullptr, P, nullptr));
+  if (e && P > 0) CUDA_TRY(cudaMemcpy(e->data, de, P * es, cudaMemcpyDeviceToHost));
+  if (g && P > 0) CUDA_TRY(cudaMemcpy2D(g->data, g->ld * es, dg, P * es, P * es, D, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_potential_eval(ehmc_ctx* ctx, const ehmc_potential* pot, const DLTensor* q, DLTensor* energy_out,
+                                   DLTensor* grad_out, void* stream) {
+  const char* fn = "ehmc_potential_eval";
+  if (!ctx || !pot) return fail(EHMC_ERR_INVALID, "%s: NULL context or potential", fn);
+  View vq, ve, vg;
+  TRY(parse_float(q, "q", 2, pot->bits, &vq));
+  if (vq.shape[0] != pot->D) return fail(EHMC_ERR_INVALID, "%s: q has %lld dimensions, the potential has %d", fn, vq.shape[0], pot->D);
+  if (energy_out) {
+    TRY(parse_float(energy_out, "energy_out", 1, pot->bits, &ve));
+    if (ve.shape[0] != vq.shape[1] || ve.host != vq.host) return fail(EHMC_ERR_INVALID, "%s: energy_out must be [P] beside q", fn);
+  }
+  if (grad_out) {
+    TRY(parse_float(grad_out, "grad_out", 2, pot->bits, &vg));
+    if (vg.shape[0] != vq.shape[0] || vg.shape[1] != vq.shape[1] || vg.host != vq.host)
+      return fail(EHMC_ERR_INVALID, "%s: grad_out must be [D,P] beside q", fn);
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pot->bits == 32) return eval_any<float>(ctx, pot, vq, energy_out ? &ve : nullptr, grad_out ? &vg : nullptr, st);
+  return eval_any<double>(ctx, pot, vq, energy_out ? &ve : nullptr, grad_out ? &vg : nullptr, st);
+}
+
+// ---------------------------------------------------------------------------
+// Philox fills
+// ---------------------------------------------------------------------------
+template <typename T>
+static int fill_any(ehmc_ctx* c, const View* out, const View* u, const View* mass, int mode, double scale, double kB,
+                    double temp, uint64_t seed, uint64_t iter, uint64_t off, cudaStream_t st) {
+  const long long P = out ? out->shape[1] : u->shape[0];
+  const int D = out ? (int)out->shape[0] : 0;
+  if (P == 0) return EHMC_OK;
+  const bool host = out ? out->host : u->host;
+  const size_t es = sizeof(T);
+  const unsigned grid = (unsigned)((P + 127) / 128);
+  if (!host) {
+    k_philox_fill<T><<<grid, 128, 0, st>>>(out ? reinterpret_cast<T*>(out->data) : nullptr, out ? out->ld : 0, P, D,
+                                           u ? reinterpret_cast<T*>(u->data) : nullptr,
+                                           mass ? reinterpret_cast<const T*>(mass->data) : nullptr, mode, scale, kB,
+                                           temp, seed, iter, off);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return EHMC_OK;
+  }
+  TRY(c->stage[0].ensure(es * (size_t)(D + 2) * P));
+  T* dout = static_cast<T*>(c->stage[0].ptr);
+  T* du = dout + (size_t)D * P;
+  T* dm = du + P;
+  if (mass) CUDA_TRY(cudaMemcpy(dm, mass->data, P * es, cudaMemcpyHostToDevice));
+  k_philox_fill<T><<<grid, 128>>>(out ? dout : nullptr, P, P, D, u ? du : nullptr, mass ? dm : nullptr, mode, scale, kB,
+                                  temp, seed, iter, off);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (out && D > 0) CUDA_TRY(cudaMemcpy2D(out->data, out->ld * es, dout, P * es, P * es, D, cudaMemcpyDeviceToHost));
+  if (u) CUDA_TRY(cudaMemcpy(u->data, du, P * es, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_philox_fill(ehmc_ctx* ctx, DLTensor* z, DLTensor* u, uint64_t seed, uint64_t iteration,
+                                uint64_t particleOffset, void* stream) {
+  if (!ctx || (!z && !u)) return fail(EHMC_ERR_INVALID, "ehmc_philox_fill: NULL argument");
+  View vz, vu;
+  int bits = 0;
+  if (z) {
+    TRY(parse_float(z, "z", 2, 0, &vz));
+    bits = vz.bits;
+  }
+  if (u) {
+    TRY(parse_float(u, "u", 1, bits, &vu));
+    bits = vu.bits;
+    if (z && (vu.shape[0] != vz.shape[1] || vu.host != vz.host))
+      return fail(EHMC_ERR_INVALID, "ehmc_philox_fill: u must be [P] beside z");
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bits == 32)
+    return fill_any<float>(ctx, z ? &vz : nullptr, u ? &vu : nullptr, nullptr, 0, 1.0, 0, 0, seed, iteration, particleOffset, st);
+  return fill_any<double>(ctx, z ? &vz : nullptr, u ? &vu : nullptr, nullptr, 0, 1.0, 0, 0, seed, iteration, particleOffset, st);
+}
+
+extern "C" int ehmc_set_position(ehmc_ctx* ctx, DLTensor* q, double qStd, uint64_t seed, uint64_t particleOffset,
+                                 void* stream) {
+  if (!ctx) return fail(EHMC_ERR_INVALID, "ehmc_set_position: NULL context");
+  View vq;
+  TRY(parse_float(q, "q", 2, 0, &vq));
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint64_t it = ~0ULL;
+  if (vq.bits == 32) return fill_any<float>(ctx, &vq, nullptr, nullptr, 0, qStd, 0, 0, seed, it, particleOffset, st);
+  return fill_any<double>(ctx, &vq, nullptr, nullptr, 0, qStd, 0, 0, seed, it, particleOffset, st);
+}
+
+extern "C" int ehmc_set_momentum(ehmc_ctx* ctx, DLTensor* p, const DLTensor* mass, double boltzmann, double temperature,
+                                 uint64_t seed, uint64_t iteration, uint64_t particleOffset, void* stream) {
+  if (!ctx) return fail(EHMC_ERR_INVALID, "ehmc_set_momentum: NULL context");
+  View vp, vm;
+  TRY(parse_float(p, "p", 2, 0, &vp));
+  TRY(parse_float(mass, "mass", 1, vp.bits, &vm));
+  if (vm.shape[0] != vp.shape[1] || vm.host != vp.host)
+    return fail(EHMC_ERR_INVALID, "ehmc_set_momentum: mass must be [P] beside p");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vp.bits == 32)
+    return fill_any<float>(ctx, &vp, nullptr, &vm, 1, 1.0, boltzmann, temperature, seed, iteration, particleOffset, st);
+  return fill_any<double>(ctx, &vp, nullptr, &vm, 1, 1.0, boltzmann, temperature, seed, iteration, particleOffset, st);
+}
+
+// ---------------------------------------------------------------------------
+// reference N-body mode
+// ---------------------------------------------------------------------------
+template <typename T>
+static int nbody_mode_any(ehmc_ctx* c, int integ, const View& q, const View& p, const View& m, double G, double h,
+                          double h2, int L, cudaStream_t st) {
+  const long long D = q.shape[0], P = q.shape[1];
+  if (P == 0) return EHMC_OK;
+  const size_t es = sizeof(T);
+  if (!q.host) {
+    k_nbody_mode<T><<<1, 128, 0, st>>>(reinterpret_cast<T*>(q.data), q.ld, reinterpret_cast<T*>(p.data), p.ld,
+                                       reinterpret_cast<const T*>(m.data), (int)P, (int)D, (T)G, (T)h, (T)h2, L, integ);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return EHMC_OK;
+  }
+  TRY(c->stage[0].ensure(es * (size_t)(2 * D + 1) * P));
+  T* dq = static_cast<T*>(c->stage[0].ptr);
+  T* dp = dq + (size_t)D * P;
+  T* dm = dp + (size_t)D * P;
+  CUDA_TRY(cudaMemcpy2D(dq, P * es, q.data, q.ld * es, P * es, D, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy2D(dp, P * es, p.data, p.ld * es, P * es, D, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dm, m.data, P * es, cudaMemcpyHostToDevice));
+  k_nbody_mode<T><<<1, 128>>>(dq, P, dp, P, dm, (int)P, (int)D, (T)G, (T)h, (T)h2, L, integ);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy2D(q.data, q.ld * es, dq, P * es, P * es, D, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy2D(p.data, p.ld * es, dp, P * es, P * es, D, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_integrate_nbody_mode(ehmc_ctx* ctx, int integrator, DLTensor* q, DLTensor* p, const DLTensor* mass,
+                                         double gravConst, double stepSize, double stepSizeSq, int numSteps,
+                                         void* stream) {
+  const char* fn = "ehmc_integrate_nbody_mode";
+  if (!ctx) return fail(EHMC_ERR_INVALID, "%s: NULL context", fn);
+  if (integrator != EHMC_LEAPFROG && integrator != EHMC_STORMER_VERLET)
+    return fail(EHMC_ERR_INVALID, "%s: Invalid integration method selected.", fn);
+  if (numSteps < 0) return fail(EHMC_ERR_INVALID, "%s: numSteps < 0", fn);
+  View vq, vp, vm;
+  TRY(parse_float(q, "q", 2, 0, &vq));
+  TRY(parse_float(p, "p", 2, vq.bits, &vp));
+  TRY(parse_float(mass, "mass", 1, vq.bits, &vm));
+  if (vq.shape[0] > 4) return fail(EHMC_ERR_UNSUPPORTED, "%s: numDimensions <= 4 (got %lld)", fn, vq.shape[0]);
+  if (vp.shape[0] != vq.shape[0] || vp.shape[1] != vq.shape[1] || vm.shape[0] != vq.shape[1])
+    return fail(EHMC_ERR_INVALID, "%s: shape mismatch", fn);
+  if (vp.host != vq.host || vm.host != vq.host) return fail(EHMC_ERR_INVALID, "%s: tensors on different sides", fn);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vq.bits == 32) return nbody_mode_any<float>(ctx, integrator, vq, vp, vm, gravConst, stepSize, stepSizeSq, numSteps, st);
+  return nbody_mode_any<double>(ctx, integrator, vq, vp, vm, gravConst, stepSize, stepSizeSq, numSteps, st);
+}

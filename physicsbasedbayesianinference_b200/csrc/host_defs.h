@@ -1,0 +1,90 @@
+// Host-side definitions shared by the translation units of _ehmc.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/ehmc.h"
+#include "common.cuh"
+
+// ---- errors ------------------------------------------------------------------
+int ehmc_fail(int code, const char* fmt, ...);
+#define fail ehmc_fail
+
+#define CUDA_TRY(expr)                                                                                         \
+  do {                                                                                                         \
+    cudaError_t e__ = (expr);                                                                                  \
+    if (e__ != cudaSuccess)                                                                                    \
+      return fail(EHMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define TRY(expr)                     \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != EHMC_OK) return rc__; \
+  } while (0)
+
+// ---- context / potential objects ------------------------------------------------
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+};
+
+constexpr int N_STAGE = 3;  // host path: chunks in flight
+
+struct ehmc_ctx {
+  int device = 0;
+  cudaDeviceProp prop;
+  uint64_t launches = 0;
+  DevBuf partials;        // block partial sums for the statistics
+  DevBuf stage[N_STAGE];  // host path staging (one slab per in-flight chunk)
+  DevBuf stage_stats;
+  cudaStream_t streams[N_STAGE] = {nullptr, nullptr, nullptr};
+  // tuning options (ehmc_ctx_set_option)
+  int dense_occupancy = 2;        // CTAs/SM the float32 dense kernel is compiled for (1 or 2)
+  long long host_chunk_bytes = 32LL << 20;
+};
+
+struct ehmc_potential {
+  ehmc_ctx* ctx = nullptr;
+  int family = 0;
+  int D = 0;
+  int bits = 32;
+  std::vector<double> hp0, hp1;  // host copies of the parameters (double)
+  std::vector<double> scalars;
+  void* d0 = nullptr;  // dense: packed Ls ; nbody: body masses ; logistic: X
+  void* d1 = nullptr;  // dense: mu (padded) ; logistic: y
+  void* d2 = nullptr;  // dense: plain Lambda row-major (eval kernel)
+  int TN = 0;          // dense tile selection
+};
+
+// ---- launchers (explicitly instantiated for float / double in inst_*.cu) ----------
+namespace ehmc {
+
+constexpr int K1_THREADS_HOST = 128;
+constexpr int K2_WARPS_HOST = 8;
+
+// fused trajectory kernels, D <= 32 register-resident families
+template <typename T>
+int launch_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);
+// dense Gaussian, 16 < D <= 128
+template <typename T>
+int launch_dense(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);
+template <typename T>
+int dense_particles_per_cta();
+int dense_tn(int D);
+template <typename T>
+int dense_tnp(int TN);
+// potential evaluation for the register-resident families
+template <typename T>
+int eval_small(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
+               long long g_ld, cudaStream_t st);
+
+}  // namespace ehmc

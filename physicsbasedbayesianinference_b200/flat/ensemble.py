@@ -1,0 +1,12 @@
+"""Flat-module shim: ``from ensemble import ...`` as in the reference's src/ensemble.py."""
+import os as _os
+import sys as _sys
+
+_root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+if _root not in _sys.path:
+    _sys.path.insert(0, _root)
+
+from physicsbasedbayesianinference_b200.ensemble import *  # noqa: E402,F401,F403
+from physicsbasedbayesianinference_b200 import ensemble as _m  # noqa: E402
+
+globals().update({k: v for k, v in vars(_m).items() if not k.startswith("__")})

@@ -1,0 +1,172 @@
+"""Potentials -- host mirror of the reference's ``src/potential.py``.
+
+The reference hands arbitrary Python callables (``potential(q[:, i])``,
+``gradient(q[:, i])``) to the integrator (src/integrator.py:73, src/HMC.py:102).
+A GPU engine cannot call Python per particle, so potentials are *family
+descriptors*: objects that are callable like the reference's functions
+(``pot(q)`` -> U, ``pot.gradient(q)`` -> grad U, for ``q`` of shape (D,) or (D, P))
+AND carry the family id + parameters the fused CUDA kernels consume.  Every
+evaluation runs on the GPU through ``ehmc_potential_eval``; there is no CPU path.
+
+Reference names kept: harmonicPotentialND, getAccelNBody, gravitationalPotential,
+nBodyPotential, noPotential (src/potential.py:18-142).  The finite-difference
+helpers nBodyForce / getForceArray are numerical-differentiation fallbacks that the
+HMC path never uses: they raise NotImplementedError
+and point to the analytic ``.gradient``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+# scipy.constants.G as imported by the reference (src/potential.py:13)
+gravConst = 6.6743e-11
+
+
+class Potential:
+    """Base class of the potential-family descriptors."""
+
+    family = 0
+
+    def __init__(self, numDimensions):
+        self.numDimensions = int(numDimensions)
+        self._handles = {}
+
+    # -- parameters handed to ehmc_potential_create ---------------------------------
+    def _params(self):
+        return []
+
+    def _scalars(self):
+        return []
+
+    def handle(self, bits, ctx=None):
+        """Device-resident parameter pack for float32/float64 kernels (cached)."""
+        ctx = ctx or _lib.Context.get()
+        key = (id(ctx), int(bits))
+        h = self._handles.get(key)
+        if h is None:
+            h = _lib.PotentialHandle(ctx, self.family, self._params(), self._scalars(), bits)
+            self._handles[key] = h
+        return h
+
+    # -- evaluation (always on the GPU) ------------------------------------------------
+    def _eval(self, q, want_energy, want_grad):
+        ctx = _lib.Context.get()
+        if isinstance(q, np.ndarray) or not hasattr(q, "is_cuda"):
+            qa = np.asarray(q)
+            one = qa.ndim == 1
+            dt = np.float32 if qa.dtype == np.float32 else np.float64
+            q2 = np.ascontiguousarray(qa.reshape(qa.shape[0], -1), dtype=dt)
+            e = np.empty(q2.shape[1], dtype=dt) if want_energy else None
+            g = np.empty_like(q2) if want_grad else None
+            _lib.potential_eval(ctx, self.handle(q2.dtype.itemsize * 8, ctx), q2, e, g)
+            if one:
+                return (e[0] if want_energy else None), (g[:, 0] if want_grad else None)
+            return e, g
+        import torch
+
+        one = q.dim() == 1
+        q2 = q.reshape(q.shape[0], -1).contiguous()
+        e = torch.empty(q2.shape[1], dtype=q2.dtype, device=q2.device) if want_energy else None
+        g = torch.empty_like(q2) if want_grad else None
+        _lib.potential_eval(ctx, self.handle(q2.element_size() * 8, ctx), q2, e, g, _lib.current_stream_ptr(q2))
+        if one:
+            return (e[0] if want_energy else None), (g[:, 0] if want_grad else None)
+        return e, g
+
+    def __call__(self, q):
+        return self._eval(q, True, False)[0]
+
+    def gradient(self, q):
+        return self._eval(q, False, True)[1]
+
+
+class HarmonicPotential(Potential):
+    """U = 0.5 * dot(k, q**2) -- harmonicPotentialND (src/potential.py:18-27)."""
+
+    family = _lib.FAMILY_DIAG_GAUSSIAN
+
+    def __init__(self, springConsts):
+        self.springConsts = np.atleast_1d(np.asarray(springConsts, dtype=np.float64)).copy()
+        super().__init__(self.springConsts.shape[0])
+
+    def _params(self):
+        return [self.springConsts]
+
+
+class GaussianPotential(Potential):
+    """U = 0.5 (q - mean)^T precision (q - mean): minus the log of a multivariate
+    normal density up to its constant, which cancels in oldH - newH (src/HMC.py:108-115).
+    The targets of src/tests/test_HMC.py:46-49 and :122-125."""
+
+    family = _lib.FAMILY_DENSE_GAUSSIAN
+
+    def __init__(self, precision=None, mean=None, cov=None):
+        if (precision is None) == (cov is None):
+            raise ValueError("give exactly one of precision= or cov=")
+        if precision is None:
+            precision = np.linalg.inv(np.asarray(cov, dtype=np.float64))
+        self.precision = np.ascontiguousarray(precision, dtype=np.float64)
+        if self.precision.ndim != 2 or self.precision.shape[0] != self.precision.shape[1]:
+            raise ValueError("precision must be a square matrix")
+        d = self.precision.shape[0]
+        self.mean = np.zeros(d) if mean is None else np.ascontiguousarray(mean, dtype=np.float64)
+        if self.mean.shape != (d,):
+            raise ValueError("mean must have one entry per dimension")
+        super().__init__(d)
+
+    def _params(self):
+        return [self.precision, self.mean]
+
+
+class FunnelPotential(Potential):
+    """Neal's funnel: v = q[0] ~ N(0, sigmaV^2), q[k] ~ N(0, e^v)."""
+
+    family = _lib.FAMILY_FUNNEL
+
+    def __init__(self, numDimensions, sigmaV=3.0):
+        self.sigmaV = float(sigmaV)
+        super().__init__(numDimensions)
+
+    def _scalars(self):
+        return [self.numDimensions, self.sigmaV]
+
+
+def _descriptor(potential):
+    """Resolve what a user passed as potential=/gradient= to a descriptor."""
+    if isinstance(potential, Potential):
+        return potential
+    owner = getattr(potential, "__self__", None)  # bound .gradient / .__call__
+    if isinstance(owner, Potential):
+        return owner
+    raise TypeError(
+        "potential/gradient must be a potential-family descriptor from "
+        "physicsbasedbayesianinference_b200.potential (HarmonicPotential, GaussianPotential, "
+        "FunnelPotential, ...) or its .gradient; arbitrary Python callables cannot run inside the "
+        "fused CUDA trajectory kernels and this engine has no CPU fallback")
+
+
+# ---------------------------------------------------------------------------
+# reference-named functions (src/potential.py)
+# ---------------------------------------------------------------------------
+def harmonicPotentialND(q, springConsts):
+    """src/potential.py:18-27 -- q is (D,) or (D, P); evaluated on the GPU."""
+    return HarmonicPotential(springConsts)(q)
+
+
+def noPotential(q):
+    """src/potential.py:141-142."""
+    return 0
+
+
+def nBodyForce(q, mass):
+    raise NotImplementedError(
+        "nBodyForce is the reference's finite-difference fallback (src/potential.py:104-119), never used by "
+        "the HMC path; use NBodyPotential(mass).gradient(q) (analytic, on the GPU)")
+
+
+def getForceArray(q, potentialFunc, dq):
+    """src/potential.py:122-138 computed -approx_fprime per particle; here: the analytic
+    gradient of a descriptor, evaluated on the GPU."""
+    return -_descriptor(potentialFunc).gradient(q)

@@ -1,0 +1,559 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C-ABI
+(ctypes -> _ehmc.so), against
+  * the golden vectors produced by the UNMODIFIED reference (tests/golden/*.npz),
+  * the NumPy oracle on the same seeded inputs,
+  * size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star): trajectories within 1e-5 relative in float32 and 1e-12 in
+float64 ("relative" = max |a-b| / max |b| over the compared array); accept/reject
+decisions identical away from threshold ties (|u - min(1, ratio)| < TIE).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hmc_oracle as O
+from tests.conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.float32: 1e-5, np.float64: 1e-12}
+TIE = {np.float32: 2e-3, np.float64: 1e-9}
+KB = O.BOLTZMANN
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def E():
+    import physicsbasedbayesianinference_b200 as pkg
+
+    pkg._lib.Context.get()  # fails loudly when the extension or the GPU is missing
+    return pkg
+
+
+def descriptor(E, g):
+    """(engine descriptor, oracle potential) for a golden case."""
+    if "k" in g:
+        return E.HarmonicPotential(g["k"]), O.DiagGaussian(g["k"])
+    if "prec" in g:
+        return E.GaussianPotential(precision=g["prec"], mean=g["mean"]), O.DenseGaussian(g["prec"], g["mean"])
+    if "sigma_v" in g:
+        return E.FunnelPotential(int(g["D"]), float(g["sigma_v"])), O.Funnel(int(g["D"]), float(g["sigma_v"]))
+    if "body_mass" in g:
+        return (E.potential.NBodyPotential(g["body_mass"], G=float(g["G"]), eps=float(g["eps"])),
+                O.NBody(g["body_mass"], float(g["G"]), float(g["eps"])))
+    if "X" in g:
+        return (E.potential.LogisticPotential(g["X"], g["y"], float(g["prior_scale"])),
+                O.Logistic(g["X"], g["y"], float(g["prior_scale"])))
+    raise KeyError
+
+
+# ---------------------------------------------------------------------------
+# known answers of the reference's own tests
+# ---------------------------------------------------------------------------
+def test_KA1_harmonic_potential_is_33(E):
+    """src/tests/test_potential.py:14-25 through the CUDA evaluation kernel."""
+    ens = E.Ensemble(2, 10)
+    ens.q[:, 0] = np.array([3.0, 4.0])
+    pot = E.harmonicPotentialND(ens.q, np.array([2, 3]))
+    assert pot[0] == 33
+    assert np.all(pot[1:] == 0)
+    assert E.harmonicPotentialND(np.array([3.0, 4.0]), np.array([2.0, 3.0])) == 33
+
+
+def test_potential_eval_matches_oracle(E):
+    rng = np.random.RandomState(1)
+    cases = [
+        (E.HarmonicPotential([2.0, 3.0, 4.0]), O.DiagGaussian([2.0, 3.0, 4.0]), 3),
+        (E.FunnelPotential(10, 3.0), O.Funnel(10, 3.0), 10),
+    ]
+    A = rng.standard_normal((20, 20))
+    prec = A @ A.T / 20 + np.eye(20)
+    mu = rng.standard_normal(20)
+    cases.append((E.GaussianPotential(precision=prec, mean=mu), O.DenseGaussian(prec, mu), 20))
+    prec2 = np.linalg.inv(np.array([[4.0, -3.0], [-3.0, 4.0]]))
+    cases.append((E.GaussianPotential(precision=prec2, mean=[5.0, 5.0]), O.DenseGaussian(prec2, [5.0, 5.0]), 2))
+    for pe, po, D in cases:
+        q = rng.standard_normal((D, 37))
+        for dt in (np.float64, np.float32):
+            qq = q.astype(dt)
+            assert rel_err(pe(qq), po.energy(q)) < 10 * RTOL[dt]
+            assert rel_err(pe.gradient(qq), po.grad(q)) < 10 * RTOL[dt]
+        # (D,) input -> scalar / (D,) like the reference's per-particle callables
+        assert np.shape(pe(q[:, 0])) == ()
+        assert pe.gradient(q[:, 0]).shape == (D,)
+
+
+# ---------------------------------------------------------------------------
+# integrators vs the reference's golden vectors
+# ---------------------------------------------------------------------------
+INTEG = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "integrate_*.npz")))
+
+
+@pytest.mark.parametrize("name", INTEG)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("backing", ["host", "device"])
+def test_integrate_golden(E, name, dt, backing):
+    import torch
+
+    g = load_golden(name)
+    D, P = g["q0"].shape
+    cls = E.StormerVerlet if "Stormer" in name else E.Leapfrog
+    if backing == "host":
+        ens = E.Ensemble(D, P, dtype=dt)
+        ens.mass = g["mass"].astype(dt)
+        ens.q[:] = g["q0"]
+        ens.p[:] = g["p0"]
+    else:
+        ens = E.Ensemble(D, P, dtype=dt, device="cuda")
+        tdt = torch.float64 if dt == np.float64 else torch.float32
+        ens.mass = torch.tensor(g["mass"], dtype=tdt, device="cuda")
+        ens.q.copy_(torch.tensor(g["q0"], dtype=tdt))
+        ens.p.copy_(torch.tensor(g["p0"], dtype=tdt))
+    pot = E.HarmonicPotential(g["k"])
+    integ = cls(ens, float(g["h"]), float(g["final_time"]), pot.gradient)
+    assert integ.numSteps == int(g["L"])
+    q, p = integ.integrate()
+    assert q is ens.q and p is ens.p  # in place, same objects
+    qn = q if backing == "host" else q.cpu().numpy()
+    pn = p if backing == "host" else p.cpu().numpy()
+    # long trajectories (h = 0.01: 444 steps) accumulate rounding: scale the fp32 bound with sqrt(L)
+    tol = RTOL[dt] * (max(1.0, np.sqrt(int(g["L"]) / 50.0)) if dt == np.float32 else 1.0)
+    assert rel_err(qn, g["q1"]) < tol
+    assert rel_err(pn, g["p1"]) < tol
+    if dt == np.float64:
+        # element-wise family in float64: the kernel evaluates the reference's expressions in
+        # the reference's order without FMA contraction -> bit-identical
+        assert np.array_equal(qn, g["q1"]) and np.array_equal(pn, g["p1"])
+
+
+def test_harmonic_analytic_KA3(E):
+    """tests/test_integrator_harmonic.py:27-38 at numSteps*h: O(h^2) convergence on the GPU."""
+    g = load_golden("integrate_Leapfrog_unitmass_h0.01")
+    k, m = g["k"], g["mass"]
+    errs = []
+    for h in (1e-1, 1e-2, 1e-3):
+        ens = E.Ensemble(2, 16)
+        ens.q[:] = g["q0"]
+        ens.p[:] = g["p0"]
+        integ = E.Leapfrog(ens, h, float(g["final_time"]), E.HarmonicPotential(k))
+        t = integ.numSteps * h
+        om = np.sqrt(np.outer(k, 1 / m))
+        qa = g["q0"] * np.cos(om * t) + g["p0"] / m / om * np.sin(om * t)
+        q, _ = integ.integrate()
+        errs.append(rel_err(q, qa))
+    assert errs[0] / errs[1] == pytest.approx(100, rel=0.2)
+    assert errs[1] / errs[2] == pytest.approx(100, rel=0.2)
+
+
+@pytest.mark.parametrize("method", ["Leapfrog", "StormerVerlet"])
+def test_nbody_reference_mode(E, method):
+    """Integrator(..., gradient=None): Sun/Earth/Moon of tests/test_integrator_solar_system.py."""
+    g = load_golden("nbody_mode_" + method)
+    ens = E.Ensemble(3, 3)
+    ens.mass = g["mass"].copy()
+    ens.q[:] = g["q0"]
+    ens.p[:] = g["p0"]
+    cls = E.Leapfrog if method == "Leapfrog" else E.StormerVerlet
+    integ = cls(ens, float(g["h"]), float(g["final_time"]), None)
+    for c in range(g["q"].shape[0]):
+        q, p = integ.integrate()
+        assert rel_err(q, g["q"][c]) < 1e-12
+        assert rel_err(p, g["p"][c]) < 1e-10
+
+
+# ---------------------------------------------------------------------------
+# HMC iterations vs the reference's golden chains (fed the reference's own z / u)
+# ---------------------------------------------------------------------------
+HMC_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "hmc_*.npz")))
+
+
+def _supported(E, g):
+    try:
+        return descriptor(E, g)
+    except AttributeError:
+        return None
+
+
+@pytest.mark.parametrize("name", HMC_CASES)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_hmc_golden_single_iterations(E, name, dt):
+    """Every iteration started from the REFERENCE's state: q, stored momentum and accept
+    decision of one fused-kernel iteration vs the reference (host path of the C-ABI)."""
+    g = load_golden(name)
+    d = _supported(E, g)
+    if d is None:
+        pytest.skip("family not built yet")
+    pe, po = d
+    D, P, S, L = int(g["D"]), int(g["P"]), int(g["S"]), int(g["L"])
+    method = "Stormer-Verlet" if "stormer" in name else "Leapfrog"
+    ens = E.Ensemble(D, P, dtype=dt)
+    ens.mass = g["mass"].astype(dt)
+    hmc = E.HMC(ens, float(g["simul_time"]), float(g["h"]), None, potential=pe, method=method)
+    assert hmc.integrator.numSteps == L
+    q_prev = g["z_init"] * float(g["q_std"])
+    n_tie = 0
+    for it in range(S):
+        z, u = g["z"][it], g["u"][it]
+        _, _, acc_ref, oldH, newH = O.hmc_iter(q_prev, z, u, g["mass"], float(g["temperature"]), float(g["h"]), L, po,
+                                               method)
+        hmc.integrator.q = np.ascontiguousarray(q_prev, dtype=dt)
+        p_out = np.empty((D, P), dtype=dt)
+        acc = np.empty(P, dtype=np.uint8)
+        hmc.step(float(g["temperature"]), p_out=p_out, accept=acc, z=z.astype(dt), u=u.astype(dt))
+        with np.errstate(over="ignore"):
+            margin = np.abs(u - np.minimum(1, np.exp(oldH - newH)))
+        clear = margin > TIE[dt]
+        assert np.array_equal(acc.astype(bool)[clear], acc_ref[clear]), "accept/reject differs away from a tie"
+        same = acc.astype(bool) == acc_ref
+        n_tie += int((~same).sum())
+        assert rel_err(hmc.integrator.q[:, same], g["samples"][:, same, it]) < RTOL[dt]
+        assert rel_err(p_out[:, same], g["momenta"][:, same, it]) < RTOL[dt]
+        q_prev = g["samples"][:, :, it]
+    assert n_tie <= 1
+
+
+@pytest.mark.parametrize("name", HMC_CASES)
+def test_hmc_golden_chain_float64(E, name):
+    """Whole chain in float64, chained on the GPU's own state, must track the reference."""
+    g = load_golden(name)
+    d = _supported(E, g)
+    if d is None:
+        pytest.skip("family not built yet")
+    pe, _ = d
+    D, P, S = int(g["D"]), int(g["P"]), int(g["S"])
+    method = "Stormer-Verlet" if "stormer" in name else "Leapfrog"
+    ens = E.Ensemble(D, P)
+    ens.mass = g["mass"].copy()
+    hmc = E.HMC(ens, float(g["simul_time"]), float(g["h"]), None, potential=pe, method=method)
+    hmc.integrator.q = np.ascontiguousarray(g["z_init"] * float(g["q_std"]))
+    for it in range(S):
+        p_out = np.empty((D, P))
+        hmc.step(float(g["temperature"]), p_out=p_out, z=g["z"][it].copy(), u=g["u"][it].copy())
+        assert rel_err(hmc.integrator.q, g["samples"][:, :, it]) < 1e-11
+        assert rel_err(p_out, g["momenta"][:, :, it]) < 1e-11
+
+
+def test_getSamples_drop_in_numpy_stream(E, capsys):
+    """np.random.seed(s); HMC(...).getSamples(...) reproduces the reference's chain:
+    same RNG stream, same print-out, same (D,P,S) arrays (tests/golden/hmc_iso2d)."""
+    g = load_golden("hmc_iso2d")
+    np.random.seed(20221018)
+    ens = E.Ensemble(2, 64)
+    hmc = E.HMC(ens, float(g["simul_time"]), float(g["h"]), None, potential=E.HarmonicPotential(g["k"]))
+    samples, momenta = hmc.getSamples(int(g["S"]), float(g["temperature"]), float(g["q_std"]))
+    out = capsys.readouterr().out
+    assert "HMC iteration  1" in out and "time step:  0.05" in out
+    assert samples.shape == (2, 64, 12) and samples.dtype == np.float64
+    assert rel_err(samples, g["samples"]) < 1e-12
+    assert rel_err(momenta, g["momenta"]) < 1e-12
+
+
+def test_bugcompat_flag(E):
+    """bugCompat=False stores the OLD MOMENTUM of rejected particles instead of the old
+    position (src/HMC.py:176)."""
+    g = load_golden("hmc_iso2d_rough")
+    po = O.DiagGaussian(g["k"])
+    D, P = 2, 64
+    q0 = g["z_init"] * float(g["q_std"])
+    z, u = g["z"][0], g["u"][0]
+    qn, p_fix, acc, _, _ = O.hmc_iter(q0, z, u, g["mass"], float(g["temperature"]), float(g["h"]), int(g["L"]), po,
+                                      bug_compat=False)
+    assert (~acc).sum() > 0
+    ens = E.Ensemble(D, P)
+    hmc = E.HMC(ens, float(g["simul_time"]), float(g["h"]), None, potential=E.HarmonicPotential(g["k"]),
+                bugCompat=False)
+    hmc.integrator.q = q0.copy()
+    p_out = np.empty((D, P))
+    hmc.step(float(g["temperature"]), p_out=p_out, z=z.copy(), u=u.copy())
+    assert rel_err(p_out, p_fix) < 1e-12 and rel_err(hmc.integrator.q, qn) < 1e-12
+
+
+# ---------------------------------------------------------------------------
+# Philox production stream
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_philox_stream_matches_spec(E, dt):
+    D, P, seed, it, off = 11, 300, 0x1234567890ABCDEF, 5, 1000
+    z = np.empty((D, P), dtype=dt)
+    u = np.empty(P, dtype=dt)
+    E._lib.philox_fill(E._lib.Context.get(), z, u, seed, it, off)
+    zr, ur = O.philox_stream(seed, it, np.arange(P) + off, D, dt)
+    assert np.array_equal(u.astype(np.float64), ur)  # integer stream -> exact
+    assert np.max(np.abs(z - zr)) < (5e-6 if dt == np.float32 else 1e-13)
+
+
+@pytest.mark.parametrize("case", ["diag2", "funnel10", "dense20", "dense100"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_production_mode_equals_fed_mode(E, case, dt):
+    """z = u = NULL (Philox inside the kernel) == feeding ehmc_philox_fill's output."""
+    import torch
+
+    rng = np.random.RandomState(7)
+    P = 1000
+    if case == "diag2":
+        D, pe = 2, E.HarmonicPotential([1.0, 2.0])
+    elif case == "funnel10":
+        D, pe = 10, E.FunnelPotential(10, 3.0)
+    else:
+        D = 20 if case == "dense20" else 100
+        A = rng.standard_normal((D, D))
+        pe = E.GaussianPotential(precision=A @ A.T / D + np.eye(D), mean=rng.standard_normal(D))
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    q0 = torch.tensor(rng.standard_normal((D, P)), dtype=tdt, device="cuda")
+    mass = torch.tensor(rng.uniform(0.5, 2.0, P), dtype=tdt, device="cuda")
+    ctx = E._lib.Context.get()
+    h = pe.handle(32 if dt == np.float32 else 64, ctx)
+    args = E._lib.make_args(0.1, 0.1**2, 7, KB, 1 / KB, seed=99, iteration=3, particle_offset=12345, flags=1)
+    qa, pa = q0.clone(), torch.empty_like(q0)
+    acc_a = torch.empty(P, dtype=torch.uint8, device="cuda")
+    E._lib.hmc_iter(ctx, h, qa, mass, args, p_out=pa, accept=acc_a)
+    z, u = torch.empty_like(q0), torch.empty(P, dtype=tdt, device="cuda")
+    E._lib.philox_fill(ctx, z, u, 99, 3, 12345)
+    qb, pb = q0.clone(), torch.empty_like(q0)
+    acc_b = torch.empty(P, dtype=torch.uint8, device="cuda")
+    E._lib.hmc_iter(ctx, h, qb, mass, args, p_out=pb, z=z, u=u, accept=acc_b)
+    torch.cuda.synchronize()
+    assert torch.equal(acc_a, acc_b)
+    assert torch.equal(qa, qb) and torch.equal(pa, pb)
+    assert 0 < int(acc_a.sum()) <= P
+
+
+# ---------------------------------------------------------------------------
+# sharding / host path / strides / edge sizes
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["diag2", "dense100"])
+def test_shard_invariance_and_column_views(E, case):
+    """Particles are independent: running column slices [0,a) and [a,P) with particleOffset
+    gives exactly the full run (what the multi-GPU sharding relies on); slices are strided
+    views (row stride P), exercising the ld != P path."""
+    import torch
+
+    rng = np.random.RandomState(11)
+    P, a = 777, 300
+    if case == "diag2":
+        D, pe = 2, E.HarmonicPotential([1.0, 2.0])
+    else:
+        D = 100
+        A = rng.standard_normal((D, D))
+        pe = E.GaussianPotential(precision=A @ A.T / D + np.eye(D))
+    q0 = torch.tensor(rng.standard_normal((D, P)), dtype=torch.float32, device="cuda")
+    mass = torch.ones(P, dtype=torch.float32, device="cuda")
+    ctx = E._lib.Context.get()
+    h = pe.handle(32, ctx)
+    mk = lambda off: E._lib.make_args(0.05, 0.05**2, 10, KB, 1 / KB, seed=5, iteration=9, particle_offset=off)
+    full = q0.clone()
+    st_full = torch.zeros(2 * D + 3, dtype=torch.float64, device="cuda")
+    E._lib.hmc_iter(ctx, h, full, mass, mk(0), stats=st_full)
+    parts = q0.clone()
+    st = [torch.zeros(2 * D + 3, dtype=torch.float64, device="cuda") for _ in range(2)]
+    E._lib.hmc_iter(ctx, h, parts[:, :a], mass[:a], mk(0), stats=st[0])
+    E._lib.hmc_iter(ctx, h, parts[:, a:], mass[a:], mk(a), stats=st[1])
+    torch.cuda.synchronize()
+    assert torch.equal(full, parts)
+    # the statistics are plain sums over particles -> shard sums add up (allreduce semantics)
+    assert torch.allclose(st_full, st[0] + st[1], rtol=1e-12, atol=1e-9)
+    qf = full.double().cpu().numpy()
+    assert st_full[0].item() <= P
+    np.testing.assert_allclose(st_full[3:3 + D].cpu().numpy(), qf.sum(1), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(st_full[3 + D:].cpu().numpy(), (qf * qf).sum(1), rtol=1e-9)
+
+
+@pytest.mark.parametrize("case", ["diag2", "dense100"])
+def test_host_path_equals_device_path(E, case):
+    import torch
+
+    rng = np.random.RandomState(13)
+    P = 5000
+    if case == "diag2":
+        D, pe = 2, E.HarmonicPotential([1.0, 2.0])
+    else:
+        D = 100
+        A = rng.standard_normal((D, D))
+        pe = E.GaussianPotential(precision=A @ A.T / D + np.eye(D))
+    q0 = rng.standard_normal((D, P)).astype(np.float32)
+    mass = rng.uniform(0.5, 2, P).astype(np.float32)
+    ctx = E._lib.Context.get()
+    h = pe.handle(32, ctx)
+    args = E._lib.make_args(0.05, 0.05**2, 10, KB, 1 / KB, seed=5, iteration=2)
+    qh, ph = q0.copy(), np.empty_like(q0)
+    acc_h = np.empty(P, dtype=np.uint8)
+    st_h = np.zeros(2 * D + 3)
+    E._lib.hmc_iter(ctx, h, qh, mass, args, p_out=ph, accept=acc_h, stats=st_h)
+    qd = torch.tensor(q0, device="cuda")
+    pd = torch.empty_like(qd)
+    acc_d = torch.empty(P, dtype=torch.uint8, device="cuda")
+    st_d = torch.zeros(2 * D + 3, dtype=torch.float64, device="cuda")
+    E._lib.hmc_iter(ctx, h, qd, torch.tensor(mass, device="cuda"), args, p_out=pd, accept=acc_d, stats=st_d)
+    torch.cuda.synchronize()
+    assert np.array_equal(qh, qd.cpu().numpy()) and np.array_equal(ph, pd.cpu().numpy())
+    assert np.array_equal(acc_h, acc_d.cpu().numpy())
+    np.testing.assert_allclose(st_h, st_d.cpu().numpy(), rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("P", [1, 31, 129, 1000])
+@pytest.mark.parametrize("case", ["diag3", "dense40"])
+def test_ragged_particle_counts_vs_oracle(E, P, case):
+    rng = np.random.RandomState(P)
+    if case == "diag3":
+        D = 3
+        k = np.array([2.0, 3.0, 4.0])
+        pe, po = E.HarmonicPotential(k), O.DiagGaussian(k)
+    else:
+        D = 40
+        A = rng.standard_normal((D, D))
+        prec = A @ A.T / D + np.eye(D)
+        mu = rng.standard_normal(D)
+        pe, po = E.GaussianPotential(precision=prec, mean=mu), O.DenseGaussian(prec, mu)
+    q0 = rng.standard_normal((D, P))
+    z = rng.standard_normal((D, P))
+    u = rng.uniform(size=P)
+    mass = rng.uniform(0.5, 2, P)
+    qr, pr, accr, oh, nh = O.hmc_iter(q0, z, u, mass, 1 / KB, 0.2, 9, po)
+    ens = E.Ensemble(D, P)
+    ens.mass = mass
+    hmc = E.HMC(ens, 9 * 0.2 + 1e-9, 0.2, None, potential=pe)
+    hmc.integrator.q = q0.copy()
+    p_out = np.empty((D, P))
+    acc = np.empty(P, dtype=np.uint8)
+    hmc.step(1 / KB, p_out=p_out, accept=acc, z=z, u=u)
+    assert np.array_equal(acc.astype(bool), accr)
+    assert rel_err(hmc.integrator.q, qr) < 1e-12 and rel_err(p_out, pr) < 1e-12
+
+
+def test_zero_steps_and_empty(E):
+    ens = E.Ensemble(2, 8)
+    ens.q[:] = 1.5
+    ens.p[:] = -0.5
+    q, p = E.Leapfrog(ens, 0.1, 0.05, E.HarmonicPotential([1.0, 1.0])).integrate()  # int(0.05/0.1) == 0
+    assert np.all(q == 1.5) and np.all(p == -0.5)
+    ens0 = E.Ensemble(2, 0)
+    q, p = E.Leapfrog(ens0, 0.1, 1.0, E.HarmonicPotential([1.0, 1.0])).integrate()
+    assert q.shape == (2, 0)
+
+
+def test_error_behaviour(E):
+    ens = E.Ensemble(2, 4)
+    with pytest.raises(ValueError, match="Invalid integration method"):
+        E.HMC(ens, 1.0, 0.1, None, potential=E.HarmonicPotential([1.0, 1.0]), method="Euler")
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        E.HMC(ens, 1.0, 0.1, None, potential=lambda q: 0.5 * np.dot(q, q))
+    with pytest.raises(IndexError):
+        ens.particle(5)
+    with pytest.raises(NotImplementedError):
+        E.Integrator(ens, 0.1, 1.0, E.HarmonicPotential([1.0, 1.0])).integrate()
+    with pytest.raises(ValueError):
+        E.Leapfrog(ens, 0.1, 1.0, E.HarmonicPotential([1.0, 1.0, 1.0]))
+    # C-ABI validation: mismatched dtype
+    ctx = E._lib.Context.get()
+    h = E.HarmonicPotential([1.0, 1.0]).handle(64, ctx)
+    with pytest.raises(E._lib.EhmcError, match="float"):
+        E._lib.leapfrog(ctx, h, np.zeros((2, 4), np.float32), np.zeros((2, 4), np.float32), np.ones(4, np.float32),
+                        0.1, 0.01, 3)
+    with pytest.raises(E._lib.EhmcError, match="stride"):
+        E._lib.leapfrog(ctx, h, np.zeros((4, 2)).T, np.zeros((2, 4)), np.ones(4), 0.1, 0.01, 3)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE sizes: size-independent properties + spot parity on a particle subset
+# ---------------------------------------------------------------------------
+def _subset_parity(E, pe, po, D, P, L, h, dt, seed, tol):
+    import torch
+
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    q0 = torch.randn((D, P), dtype=tdt, device="cuda", generator=gen)
+    z = torch.randn((D, P), dtype=tdt, device="cuda", generator=gen)
+    u = torch.rand(P, dtype=tdt, device="cuda", generator=gen)
+    mass = torch.ones(P, dtype=tdt, device="cuda")
+    ctx = E._lib.Context.get()
+    args = E._lib.make_args(h, h**2, L, KB, 1 / KB, flags=1)
+    q = q0.clone()
+    p = torch.empty_like(q)
+    acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+    stats = torch.zeros(2 * D + 3, dtype=torch.float64, device="cuda")
+    E._lib.hmc_iter(ctx, pe.handle(32 if dt == np.float32 else 64, ctx), q, mass, args, p_out=p, z=z, u=u, accept=acc,
+                    stats=stats)
+    torch.cuda.synchronize()
+    idx = torch.randperm(P, generator=torch.Generator().manual_seed(seed))[:192].sort().values.cuda()
+    sub = lambda t: t[..., idx].double().cpu().numpy()
+    qr, pr, accr, oh, nh = O.hmc_iter(sub(q0), sub(z), sub(u), np.ones(len(idx)), 1 / KB, h, L, po)
+    with np.errstate(over="ignore"):
+        clear = np.abs(sub(u) - np.minimum(1, np.exp(oh - nh))) > TIE[dt]
+    a = sub(acc).astype(bool)
+    assert np.array_equal(a[clear], accr[clear])
+    same = a == accr
+    assert rel_err(sub(q)[:, same], qr[:, same]) < tol
+    assert rel_err(sub(p)[:, same], pr[:, same]) < tol
+    n_acc = int(acc.sum().item())
+    assert stats[0].item() == n_acc and 0.2 * P < n_acc <= P
+    return q0, q, acc
+
+
+def test_config2_full_size_dense100(E):
+    """BASELINE config 2: D = 100, P = 2^20, L = 50 (float32).  Spot parity of 192 random
+    particles against the oracle + acceptance statistics."""
+    rng = np.random.RandomState(20221018)
+    A = rng.standard_normal((100, 100))
+    prec = A @ A.T / 100 + np.eye(100)
+    pe, po = E.GaussianPotential(precision=prec), O.DenseGaussian(prec)
+    _subset_parity(E, pe, po, 100, 1 << 20, 50, 0.05, np.float32, 1, 1e-5)
+
+
+def test_config5_full_size_funnel(E):
+    """BASELINE config 5: Neal's funnel, D = 10, P = 2^22, L = 20 (float32)."""
+    pe, po = E.FunnelPotential(10, 3.0), O.Funnel(10, 3.0)
+    _subset_parity(E, pe, po, 10, 1 << 22, 20, 0.02, np.float32, 2, 1e-5)
+
+
+def test_config1_full_run(E):
+    """BASELINE config 1 exactly: D = 2, P = 1024, L = 20, 1000 iterations, float64, fed the
+    reference's MT19937 stream; compared with the oracle chain (which is bit-equal to the
+    reference on the golden prefix)."""
+    np.random.seed(20221018)
+    ens = E.Ensemble(2, 1024)
+    hmc = E.HMC(ens, 1.0, 0.05, None, potential=E.HarmonicPotential([1.0, 1.0]))
+    samples, momenta = hmc.getSamples(1000, 1 / KB, 1.0)
+    np.random.seed(20221018)
+    s_ref, m_ref = O.get_samples(2, 1024, np.ones(1024), O.DiagGaussian([1.0, 1.0]), 1000, 1 / KB, 1.0, 1.0, 0.05)
+    assert rel_err(samples, s_ref) < 1e-12 and rel_err(momenta, m_ref) < 1e-12
+    # the target is N(0, I): ensemble moments after burn-in
+    x = samples[:, :, 200:]
+    assert abs(x.mean()) < 0.02 and abs(x.var() - 1.0) < 0.03
+
+
+@pytest.mark.parametrize("case", ["diag2", "dense100", "funnel10"])
+def test_reversibility_property(E, case):
+    """Leapfrog is time reversible: integrate, flip p, integrate again -> back at the start.
+    A size-independent property checked at 2^18 particles on the device path."""
+    import torch
+
+    rng = np.random.RandomState(3)
+    P = 1 << 18
+    if case == "diag2":
+        D, pe = 2, E.HarmonicPotential([1.0, 2.0])
+    elif case == "funnel10":
+        D, pe = 10, E.FunnelPotential(10, 3.0)
+    else:
+        D = 100
+        A = rng.standard_normal((D, D))
+        pe = E.GaussianPotential(precision=A @ A.T / D + np.eye(D))
+    ens = E.Ensemble(D, P, dtype=np.float64, device="cuda")
+    ens.q.normal_(generator=torch.Generator(device="cuda").manual_seed(1))
+    ens.p.normal_(generator=torch.Generator(device="cuda").manual_seed(2))
+    q0, p0 = ens.q.clone(), ens.p.clone()
+    integ = E.Leapfrog(ens, 0.02, 0.2, pe)
+    integ.integrate()
+    assert not torch.allclose(ens.q, q0)
+    ens.p.neg_()
+    integ.integrate()
+    ens.p.neg_()
+    assert (ens.q - q0).abs().max().item() < 1e-10 * max(1.0, q0.abs().max().item())
+    assert (ens.p - p0).abs().max().item() < 1e-10 * max(1.0, p0.abs().max().item())
