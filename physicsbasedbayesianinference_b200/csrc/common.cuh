@@ -82,10 +82,14 @@ struct NormalBlock<float> {
     const float s = 5.9604644775390625e-8f;  // 2^-24
     const float u1a = (float)((r.x >> 8) + 1u) * s, u2a = (float)(r.y >> 8) * s;
     const float u1b = (float)((r.z >> 8) + 1u) * s, u2b = (float)(r.w >> 8) * s;
-    const float ra = sqrtf(-2.0f * logf(u1a)), rb = sqrtf(-2.0f * logf(u1b));
-    float sa, ca, sb, cb;
-    sincospif(2.0f * u2a, &sa, &ca);
-    sincospif(2.0f * u2b, &sb, &cb);
+    // Box-Muller on the SFU: r = sqrt(-2 ln u1) via lg2.approx (clamped: u1 -> 1 may give a tiny
+    // positive lg2 error), angle via sin/cos.approx on [-pi, pi).  Absolute error ~5e-7, far below
+    // the sampling noise; the integer stream (and therefore u) stays exact.
+    const float c = -1.3862943611198906f;  // -2 ln 2
+    const float ra = sqrtf(fmaxf(c * __log2f(u1a), 0.0f)), rb = sqrtf(fmaxf(c * __log2f(u1b), 0.0f));
+    const float ta = 6.283185307179586f * (u2a - 0.5f), tb = 6.283185307179586f * (u2b - 0.5f);
+    // cos(2 pi u) = -cos(2 pi (u - 1/2)), sin likewise
+    const float sa = -__sinf(ta), ca = -__cosf(ta), sb = -__sinf(tb), cb = -__cosf(tb);
     z[0] = ra * ca;
     z[1] = ra * sa;
     z[2] = rb * cb;
@@ -141,6 +145,7 @@ struct IterArgs {
   unsigned flags;
   T h, h2;
   double kB, temp;
+  double pscale;  // sqrt(kB * temp), host-computed
   u64 seed, iter, offset;
 };
 
@@ -153,8 +158,16 @@ constexpr int INTEG_STORMER = 1;
 // momentum std of one particle: sqrt((m * kB) * T) in double (src/ensemble.py:88);
 // double because m*kB underflows float for molecular masses (tests/test_ensemble.py:74-80).
 template <typename T>
-__device__ __forceinline__ T momentum_std(T m, double kB, double temp) {
-  return (T)sqrt(__dmul_rn(__dmul_rn((double)m, kB), temp));
+__device__ __forceinline__ T momentum_std(T m, double kB, double temp, double pscale);
+template <>
+__device__ __forceinline__ double momentum_std<double>(double m, double kB, double temp, double) {
+  return sqrt(__dmul_rn(__dmul_rn(m, kB), temp));
+}
+// float32 mode: sqrt(m) * sqrt(kB T), the scalar factor pscale = sqrt(kB T) formed in double on the
+// host; 2 ulp (float) from the reference expression, no double-precision work per particle.
+template <>
+__device__ __forceinline__ float momentum_std<float>(float m, double, double, double pscale) {
+  return sqrtf(m) * (float)pscale;
 }
 
 // Metropolis rule of src/HMC.py:168-173: reject iff u > min(1, exp(oldH - newH)).

@@ -605,6 +605,7 @@ extern "C" int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor*
     A.flags = a->flags;
     A.kB = a->boltzmann;
     A.temp = a->temperature;
+    A.pscale = std::sqrt(a->boltzmann * a->temperature);
     A.seed = a->seed;
     A.iter = a->iteration;
     A.offset = a->particleOffset;

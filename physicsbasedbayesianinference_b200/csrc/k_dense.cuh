@@ -116,7 +116,7 @@ k_dense(const IterArgs<T> A, const DenseArgs<T> pa, const int integ, const int h
     valid[t] = pbase + t < A.P;
     m[t] = valid[t] ? A.mass[pbase + t] : T(1);
     inv_m[t] = T(1) / m[t];
-    pstd[t] = hmc ? momentum_std<T>(m[t], A.kB, A.temp) : T(0);
+    pstd[t] = hmc ? momentum_std<T>(m[t], A.kB, A.temp, A.pscale) : T(0);
   }
   const bool full = pbase + TM <= A.P;
   const bool qvec = full && (A.q_ld % TM == 0) && ((reinterpret_cast<uintptr_t>(A.q) & 15) == 0);

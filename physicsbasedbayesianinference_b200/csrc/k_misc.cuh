@@ -70,7 +70,7 @@ __global__ void k_philox_fill(T* out, long long ld, long long P, int D, T* u, co
   const PhiloxKey K(seed, iter);
   if (out != nullptr) {
     T s = (T)scale;
-    if (mode == 1) s = momentum_std<T>(mass[i], kB, temp);
+    if (mode == 1) s = momentum_std<T>(mass[i], kB, temp, sqrt(kB * temp));
     constexpr int NB = NormalBlock<T>::N;
     for (int b = 0; b * NB < D; ++b) {
       T zz[NB];

@@ -167,12 +167,12 @@ __device__ __forceinline__ T integrate_regs(const Pot& pot, T (&q)[DT], T (&p)[D
 }
 
 template <typename T, int DT>
-__device__ __forceinline__ T kinetic(const T (&p)[DT], T m) {
+__device__ __forceinline__ T kinetic(const T (&p)[DT], T m, T inv_m) {
   // 0.5 * dot(p, p) / m                         HMC.py:109
   T s = T(0);
 #pragma unroll
   for (int d = 0; d < DT; ++d) s = Ar<T>::add(s, Ar<T>::mul(p[d], p[d]));
-  return Ar<T>::mul(T(0.5), s) / m;
+  return Ar<T>::divm(Ar<T>::mul(T(0.5), s), m, inv_m);
 }
 
 // Block-level partial sums of NS values -> partials[blockIdx.x * NS + j].
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> A, const
 
   T pstd = T(0);
   if (HMC) {
-    pstd = momentum_std<T>(m, A.kB, A.temp);
+    pstd = momentum_std<T>(m, A.kB, A.temp, A.pscale);
     draw_momentum<T, DT>(A, ic, pstd, p);
   } else {
 #pragma unroll
@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> A, const
   }
 
   T K0 = T(0);
-  if (HMC) K0 = kinetic<T, DT>(p, m);
+  const T inv_m = T(1) / m;
+  if (HMC) K0 = kinetic<T, DT>(p, m, inv_m);
   T U0;
   const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, A.h, A.h2, A.L, HMC, &U0);
 
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> A, const
   }
 
   const T oldH = Ar<T>::add(K0, U0);
-  const T newH = Ar<T>::add(kinetic<T, DT>(p, m), U1);  // dot(-p,-p) == dot(p,p), HMC.py:164
+  const T newH = Ar<T>::add(kinetic<T, DT>(p, m, inv_m), U1);  // dot(-p,-p) == dot(p,p), HMC.py:164
   T u;
   if (A.u != nullptr)
     u = A.u[ic];

@@ -124,8 +124,10 @@ def test_integrate_golden(E, name, dt, backing):
     assert q is ens.q and p is ens.p  # in place, same objects
     qn = q if backing == "host" else q.cpu().numpy()
     pn = p if backing == "host" else p.cpu().numpy()
-    # long trajectories (h = 0.01: 444 steps) accumulate rounding: scale the fp32 bound with sqrt(L)
-    tol = RTOL[dt] * (max(1.0, np.sqrt(int(g["L"]) / 50.0)) if dt == np.float32 else 1.0)
+    # float32 and long trajectories (h = 0.01: 444 steps): rounding accumulates ~sqrt(L) for the
+    # velocity form and ~L for the two-step position Verlet recurrence (q = 2q - qPast + a h^2)
+    grow = int(g["L"]) / 50.0
+    tol = RTOL[dt] * (max(1.0, grow if "Stormer" in name else np.sqrt(grow)) if dt == np.float32 else 1.0)
     assert rel_err(qn, g["q1"]) < tol
     assert rel_err(pn, g["p1"]) < tol
     if dt == np.float64:
