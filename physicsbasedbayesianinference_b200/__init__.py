@@ -20,6 +20,8 @@ from .potential import (  # noqa: F401
     FunnelPotential,
     GaussianPotential,
     HarmonicPotential,
+    LogisticPotential,
+    NBodyPotential,
     Potential,
     harmonicPotentialND,
 )

@@ -146,8 +146,10 @@ extern "C" int ehmc_ctx_destroy(ehmc_ctx* c) {
   cudaSetDevice(c->device);
   c->partials.release();
   c->stage_stats.release();
+  c->pstats.release();
   for (int i = 0; i < N_STAGE; ++i) {
     c->stage[i].release();
+    c->uf[i].release();
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
   }
   delete c;
@@ -308,6 +310,33 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       if (!(scalars[1] > 0)) rc = fail(EHMC_ERR_INVALID, "funnel: sigma_v must be > 0");
       break;
     }
+    case EHMC_FAMILY_NBODY: {
+      if (nparams != 1 || nscalars != 2) { rc = fail(EHMC_ERR_INVALID, "nbody: params = {bodyMass[B]}, scalars = {G, eps}"); break; }
+      rc = fetch_param(params[0], "bodyMass", 1, &p->hp0, &v);
+      if (rc) break;
+      p->B = (int)p->hp0.size();
+      p->D = 3 * p->B;
+      if (p->B < 1) { rc = fail(EHMC_ERR_INVALID, "nbody: empty bodyMass"); break; }
+      if (p->B > 7000) { rc = fail(EHMC_ERR_UNSUPPORTED, "nbody: B = %d > 7000 bodies", p->B); break; }
+      if (!(scalars[1] >= 0)) { rc = fail(EHMC_ERR_INVALID, "nbody: eps must be >= 0"); break; }
+      rc = upload_bits(p->bits, p->hp0, &p->d0);
+      break;
+    }
+    case EHMC_FAMILY_LOGISTIC: {
+      if (nparams != 2 || nscalars != 1) { rc = fail(EHMC_ERR_INVALID, "logistic: params = {X[N,D], y[N]}, scalars = {priorScale}"); break; }
+      rc = fetch_param(params[0], "X", 2, &p->hp0, &v);
+      if (rc) break;
+      p->N = (int)v.shape[0];
+      p->D = (int)v.shape[1];
+      rc = fetch_param(params[1], "y", 1, &p->hp1, &v);
+      if (rc) break;
+      if ((int)p->hp1.size() != p->N) { rc = fail(EHMC_ERR_INVALID, "logistic: y must have N entries"); break; }
+      if (p->D < 1 || p->D > 256) { rc = fail(EHMC_ERR_UNSUPPORTED, "logistic: 1 <= D <= 256 (got %d)", p->D); break; }
+      if (!(scalars[0] > 0)) { rc = fail(EHMC_ERR_INVALID, "logistic: priorScale must be > 0"); break; }
+      rc = upload_bits(p->bits, p->hp0, &p->d0);
+      if (rc == EHMC_OK) rc = upload_bits(p->bits, p->hp1, &p->d1);
+      break;
+    }
     default:
       rc = fail(EHMC_ERR_UNSUPPORTED, "potential family %d is not built into this library", family);
   }
@@ -351,8 +380,14 @@ extern "C" int ehmc_potential_destroy(ehmc_potential* p) {
 }
 
 // number of CTAs the trajectory kernel uses for P particles (statistics partials)
+// families whose trajectory kernel reports statistics per particle ([P][3]) and needs k_colstats
+static bool per_particle_stats(const ehmc_potential* p) {
+  return p->family == EHMC_FAMILY_NBODY || p->family == EHMC_FAMILY_LOGISTIC;
+}
+
 template <typename T>
 static long long traj_blocks(const ehmc_potential* p, long long P) {
+  if (per_particle_stats(p)) return P;
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) {
     const int PT = dense_particles_per_cta<T>();
     return (P + PT - 1) / PT;
@@ -362,8 +397,10 @@ static long long traj_blocks(const ehmc_potential* p, long long P) {
 
 template <typename T>
 static int launch_traj(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc,
-                       cudaStream_t st) {
+                       cudaStream_t st, int slot = 0) {
   if (A.P == 0) return EHMC_OK;
+  if (p->family == EHMC_FAMILY_NBODY) return launch_nbody<T>(c, p, A, integ, hmc, st);
+  if (p->family == EHMC_FAMILY_LOGISTIC) return launch_logistic<T>(c, p, A, integ, hmc, st, slot);
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) return launch_dense<T>(c, p, A, integ, hmc, st);
   return launch_small<T>(c, p, A, integ, hmc, st);
 }
@@ -413,7 +450,8 @@ static IterArgs<T> base_args(const CallViews& v, double h, double h2, int L) {
 template <typename T>
 static int run_device(ehmc_ctx* c, const ehmc_potential* pot, IterArgs<T> A, int integ, bool hmc, double* stats_dev,
                       cudaStream_t st) {
-  const int NS = 2 * A.D + 3;
+  const bool pps = per_particle_stats(pot);
+  const int NS = pps ? 3 : 2 * A.D + 3;
   long long nblk = 0;
   if (stats_dev != nullptr) {
     nblk = traj_blocks<T>(pot, A.P);
@@ -421,10 +459,11 @@ static int run_device(ehmc_ctx* c, const ehmc_potential* pot, IterArgs<T> A, int
     A.partials = static_cast<double*>(c->partials.ptr);
   }
   TRY(launch_traj<T>(c, pot, A, integ, hmc, st));
-  if (stats_dev != nullptr) {
+  if (stats_dev != nullptr && A.P > 0) {
     k_stats_finalize<<<NS, 256, 0, st>>>(A.partials, (int)nblk, NS, stats_dev);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (pps) TRY(colstats<T>(c, A.q, A.q_ld, A.P, A.D, stats_dev, st));
   }
   return EHMC_OK;
 }
@@ -456,8 +495,12 @@ static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, 
     blk_off[k] = blocks_total;
     blocks_total += traj_blocks<T>(pot, n);
   }
+  const bool pps = per_particle_stats(pot);
   if (v.has_stats) {
-    TRY(c->partials.ensure(sizeof(double) * (size_t)std::max(1LL, blocks_total) * NS));
+    // fused families: one row of NS sums per CTA.  per-particle families: [P][3] rows in pstats plus
+    // one row of coordinate sums per chunk (k_colstats) in partials.
+    TRY(c->partials.ensure(sizeof(double) * (size_t)std::max(1LL, pps ? nchunks : blocks_total) * NS));
+    if (pps) TRY(c->pstats.ensure(sizeof(double) * 3 * (size_t)std::max(1LL, P)));
     TRY(c->stage_stats.ensure(sizeof(double) * NS));
   }
   const size_t es = sizeof(T);
@@ -492,8 +535,18 @@ static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, 
     A.accept = v.has_accept ? dacc : nullptr;
     A.P = n;
     A.offset = proto.offset + (u64)c0;
-    A.partials = v.has_stats ? static_cast<double*>(c->partials.ptr) + (size_t)blk_off[k] * NS : nullptr;
-    TRY(launch_traj<T>(c, pot, A, integ, hmc, st));
+    if (!v.has_stats)
+      A.partials = nullptr;
+    else if (pps)
+      A.partials = static_cast<double*>(c->pstats.ptr) + (size_t)c0 * 3;
+    else
+      A.partials = static_cast<double*>(c->partials.ptr) + (size_t)blk_off[k] * NS;
+    TRY(launch_traj<T>(c, pot, A, integ, hmc, st, s));
+    if (v.has_stats && pps) {
+      double* row = static_cast<double*>(c->partials.ptr) + (size_t)k * NS;
+      CUDA_TRY(cudaMemsetAsync(row, 0, sizeof(double) * 3, st));
+      TRY(colstats<T>(c, dq, chunk, n, (int)D, row, st));
+    }
     CUDA_TRY(cudaMemcpy2DAsync(v.q.data + c0 * es, v.q.ld * es, dq, chunk * es, n * es, D, cudaMemcpyDeviceToHost, st));
     if (v.has_p)
       CUDA_TRY(cudaMemcpy2DAsync(v.p.data + c0 * es, v.p.ld * es, dp, chunk * es, n * es, D, cudaMemcpyDeviceToHost, st));
@@ -502,9 +555,14 @@ static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, 
   for (int i = 0; i < N_STAGE; ++i) CUDA_TRY(cudaStreamSynchronize(c->streams[i]));
   if (v.has_stats) {
     cudaStream_t st = c->streams[0];
-    k_stats_finalize<<<NS, 256, 0, st>>>(static_cast<double*>(c->partials.ptr), (int)blocks_total, NS,
+    k_stats_finalize<<<NS, 256, 0, st>>>(static_cast<double*>(c->partials.ptr), (int)(pps ? nchunks : blocks_total), NS,
                                          static_cast<double*>(c->stage_stats.ptr));
     c->launches++;
+    if (pps) {
+      k_stats_finalize<<<3, 256, 0, st>>>(static_cast<double*>(c->pstats.ptr), (int)P, 3,
+                                          static_cast<double*>(c->stage_stats.ptr));
+      c->launches++;
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(v.stats.data, c->stage_stats.ptr, sizeof(double) * NS, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -638,6 +696,8 @@ static int eval_device(ehmc_ctx* c, const ehmc_potential* p, const T* q, long lo
     CUDA_TRY(cudaGetLastError());
     return EHMC_OK;
   }
+  if (p->family == EHMC_FAMILY_NBODY) return eval_nbody<T>(c, p, q, q_ld, P, e, g, g_ld, st);
+  if (p->family == EHMC_FAMILY_LOGISTIC) return eval_logistic<T>(c, p, q, q_ld, P, e, g, g_ld, st);
   return eval_small<T>(c, p, q, q_ld, P, e, g, g_ld, st);
 }
 

@@ -46,6 +46,8 @@ struct ehmc_ctx {
   DevBuf partials;        // block partial sums for the statistics
   DevBuf stage[N_STAGE];  // host path staging (one slab per in-flight chunk)
   DevBuf stage_stats;
+  DevBuf pstats;          // per-particle statistics rows [P][3] (CTA-per-particle / unfused families)
+  DevBuf uf[N_STAGE];     // scratch of the unfused path: w, v, g [D][P] + K0, U0, U1 [P]
   cudaStream_t streams[N_STAGE] = {nullptr, nullptr, nullptr};
   // tuning options (ehmc_ctx_set_option)
   int dense_occupancy = 2;        // CTAs/SM the float32 dense kernel is compiled for (1 or 2)
@@ -63,6 +65,8 @@ struct ehmc_potential {
   void* d1 = nullptr;  // dense: mu (padded) ; logistic: y
   void* d2 = nullptr;  // dense: plain Lambda row-major (eval kernel)
   int TN = 0;          // dense tile selection
+  int B = 0;           // nbody: bodies per particle
+  int N = 0;           // logistic: data rows
 };
 
 // ---- launchers (explicitly instantiated for float / double in inst_*.cu) ----------
@@ -86,5 +90,22 @@ int dense_tnp(int TN);
 template <typename T>
 int eval_small(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
                long long g_ld, cudaStream_t st);
+
+// pairwise gravitational family (one CTA per ensemble particle)
+template <typename T>
+int launch_nbody(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);
+template <typename T>
+int eval_nbody(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
+               long long g_ld, cudaStream_t st);
+// sum_i q[d,i], sum_i q[d,i]^2 -> out[3 + d], out[3 + D + d]
+template <typename T>
+int colstats(ehmc_ctx* c, const T* q, long long q_ld, long long P, int D, double* out, cudaStream_t st);
+// logistic regression: unfused trajectory driver (gradient kernel + kick/drift kernels)
+template <typename T>
+int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st,
+                    int slot);
+template <typename T>
+int eval_logistic(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
+                  long long g_ld, cudaStream_t st);
 
 }  // namespace ehmc

@@ -1,0 +1,88 @@
+#pragma once
+
+#include "host_defs.h"
+#include "k_logistic.cuh"
+
+namespace ehmc {
+
+template <typename T>
+static LogisticArgs<T> logistic_args(const ehmc_potential* p) {
+  LogisticArgs<T> pa;
+  pa.X = static_cast<const T*>(p->d0);
+  pa.y = static_cast<const T*>(p->d1);
+  pa.N = p->N;
+  pa.D = p->D;
+  pa.inv_s2 = (T)(1.0 / (p->scalars[0] * p->scalars[0]));
+  return pa;
+}
+
+template <typename T>
+static int logistic_grad(ehmc_ctx* c, const ehmc_potential* p, const T* theta, long long t_ld, long long P, T* g,
+                         long long g_ld, T* e, cudaStream_t st) {
+  constexpr int PT = LogiTile<T>::PT;
+  const int D = p->D, DS = (D + 3) & ~3;
+  if (D > LG_DMAX) return fail(EHMC_ERR_UNSUPPORTED, "logistic: D = %d > %d", D, LG_DMAX);
+  const size_t sm = sizeof(T) * ((size_t)D * PT + (size_t)LG_NC * DS + (size_t)LG_NC * PT + LG_THREADS);
+  CUDA_TRY(cudaFuncSetAttribute(k_logistic_grad<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_logistic_grad<T><<<(unsigned)((P + PT - 1) / PT), LG_THREADS, sm, st>>>(theta, t_ld, P, g, g_ld, e,
+                                                                             logistic_args<T>(p));
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return EHMC_OK;
+}
+
+template <typename T>
+int eval_logistic(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
+                  long long g_ld, cudaStream_t st) {
+  return logistic_grad<T>(c, p, q, q_ld, P, g, g_ld, e, st);
+}
+
+// One HMC iteration / one integrate() call as a sequence of launches on `st`.
+template <typename T>
+int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st,
+                    int slot) {
+  const long long P = A.P;
+  const int D = A.D, L = A.L;
+  TRY(c->uf[slot].ensure(sizeof(T) * ((size_t)3 * D * P + 3 * (size_t)P)));
+  T* w = static_cast<T*>(c->uf[slot].ptr);
+  T* v = w + (size_t)D * P;
+  T* g = v + (size_t)D * P;
+  T* K0 = g + (size_t)D * P;
+  T* U0 = K0 + P;
+  T* U1 = U0 + P;
+  const unsigned grid = (unsigned)((P + 127) / 128);
+  const T h = A.h, h2 = A.h2;
+  k_uf_init<T><<<grid, 128, 0, st>>>(A, w, v, hmc ? K0 : nullptr, hmc ? 1 : 0);
+  c->launches++;
+  TRY(logistic_grad<T>(c, p, w, P, P, g, P, hmc ? U0 : nullptr, st));
+  if (integ == INTEG_LEAPFROG) {
+    if (L > 0) {
+      k_uf_kick_drift<T><<<grid, 128, 0, st>>>(w, v, g, A.mass, P, D, T(0.5) * h, h);
+      c->launches++;
+    }
+    for (int s = 0; s < L; ++s) {
+      const bool last = s == L - 1;
+      TRY(logistic_grad<T>(c, p, w, P, P, g, P, (hmc && last) ? U1 : nullptr, st));
+      k_uf_kick_drift<T><<<grid, 128, 0, st>>>(w, v, g, A.mass, P, D, last ? T(0.5) * h : h, last ? T(0) : h);
+      c->launches++;
+    }
+    if (L == 0 && hmc) CUDA_TRY(cudaMemcpyAsync(U1, U0, sizeof(T) * P, cudaMemcpyDeviceToDevice, st));
+  } else {
+    k_uf_sv_step<T><<<grid, 128, 0, st>>>(w, v, g, A.mass, P, D, h, h2, 1);
+    c->launches++;
+    for (int s = 0; s < L; ++s) {
+      TRY(logistic_grad<T>(c, p, w, P, P, g, P, nullptr, st));
+      k_uf_sv_step<T><<<grid, 128, 0, st>>>(w, v, g, A.mass, P, D, h, h2, 0);
+      c->launches++;
+    }
+    k_uf_sv_finish<T><<<grid, 128, 0, st>>>(w, v, P, D, h);
+    c->launches++;
+    if (hmc) TRY(logistic_grad<T>(c, p, w, P, P, nullptr, 0, U1, st));
+  }
+  k_uf_final<T><<<grid, 128, 0, st>>>(A, w, v, K0, U0, U1, hmc ? 1 : 0, A.partials);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return EHMC_OK;
+}
+
+}  // namespace ehmc

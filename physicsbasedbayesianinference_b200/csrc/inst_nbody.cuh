@@ -1,0 +1,71 @@
+#pragma once
+
+#include "host_defs.h"
+#include "k_nbody.cuh"
+
+namespace ehmc {
+
+static int nbody_threads(int B) {
+  int nt = 32;
+  while (nt * NB_TI < B && nt < 1024) nt <<= 1;
+  return nt;
+}
+
+template <typename T>
+static NBodyArgs<T> nbody_args(const ehmc_potential* p) {
+  NBodyArgs<T> pa;
+  pa.bmass = static_cast<const T*>(p->d0);
+  pa.B = p->B;
+  pa.G = (T)p->scalars[0];
+  pa.eps2 = (T)(p->scalars[1] * p->scalars[1]);
+  return pa;
+}
+
+template <typename T>
+int launch_nbody(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st) {
+  const int B = p->B, nt = nbody_threads(B);
+  if (nt * NB_TI < B) return fail(EHMC_ERR_UNSUPPORTED, "nbody: B = %d > %d bodies", B, 1024 * NB_TI);
+  const size_t sm = (size_t)B * 4 * sizeof(T) + 40 * sizeof(T);
+  if (sm > 227 * 1024) return fail(EHMC_ERR_UNSUPPORTED, "nbody: B = %d needs %zu B shared memory", B, sm);
+  const NBodyArgs<T> pa = nbody_args<T>(p);
+  const bool eps0 = p->scalars[1] == 0.0;
+  void (*k)(const IterArgs<T>, const NBodyArgs<T>, const int, const int);
+  if (nt <= 128)
+    k = eps0 ? k_nbody<T, true, 128> : k_nbody<T, false, 128>;
+  else if (nt <= 512)
+    k = eps0 ? k_nbody<T, true, 512> : k_nbody<T, false, 512>;
+  else
+    k = eps0 ? k_nbody<T, true, 1024> : k_nbody<T, false, 1024>;
+  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k<<<(unsigned)A.P, nt, sm, st>>>(A, pa, integ, hmc ? 1 : 0);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return EHMC_OK;
+}
+
+template <typename T>
+int eval_nbody(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
+               long long g_ld, cudaStream_t st) {
+  const int B = p->B;
+  int nt = 32;
+  while (nt < B && nt < 256) nt <<= 1;
+  const size_t sm = (size_t)B * 4 * sizeof(T) + 40 * sizeof(T);
+  if (sm > 227 * 1024) return fail(EHMC_ERR_UNSUPPORTED, "nbody: B = %d needs %zu B shared memory", B, sm);
+  const NBodyArgs<T> pa = nbody_args<T>(p);
+  auto k = p->scalars[1] == 0.0 ? k_nbody_eval<T, true> : k_nbody_eval<T, false>;
+  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k<<<(unsigned)P, nt, sm, st>>>(q, q_ld, e, g, g_ld, pa);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return EHMC_OK;
+}
+
+template <typename T>
+int colstats(ehmc_ctx* c, const T* q, long long q_ld, long long P, int D, double* out, cudaStream_t st) {
+  k_colstats<T><<<D, 256, 0, st>>>(q, q_ld, P, D, out);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return EHMC_OK;
+}
+
+}  // namespace ehmc

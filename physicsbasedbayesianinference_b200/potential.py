@@ -133,6 +133,50 @@ class FunnelPotential(Potential):
         return [self.numDimensions, self.sigmaV]
 
 
+class NBodyPotential(Potential):
+    """Every ensemble particle is a whole B-body system; coordinates are flattened
+    component-major, d = c*B + b (the reference's own convention, src/potential.py:83-84).
+
+    U = -G sum_{i<j} m_i m_j / sqrt(|r_i - r_j|^2 + eps^2)
+    (sign of samples/NBody/MiscFunctions.py:163-169; for eps = 0, -grad_i U / m_i is
+    getAccelNBody, src/potential.py:30-53)."""
+
+    family = _lib.FAMILY_NBODY
+
+    def __init__(self, masses, G=gravConst, eps=0.0):
+        self.masses = np.atleast_1d(np.asarray(masses, dtype=np.float64)).copy()
+        self.G = float(G)
+        self.eps = float(eps)
+        super().__init__(3 * self.masses.shape[0])
+
+    def _params(self):
+        return [self.masses]
+
+    def _scalars(self):
+        return [self.G, self.eps]
+
+
+class LogisticPotential(Potential):
+    """Bayesian logistic regression with a N(0, priorScale^2) prior:
+    U(theta) = sum_n [softplus(x_n.theta) - y_n x_n.theta] + 0.5 |theta|^2 / priorScale^2."""
+
+    family = _lib.FAMILY_LOGISTIC
+
+    def __init__(self, X, y, priorScale=1.0):
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.y = np.ascontiguousarray(y, dtype=np.float64)
+        if self.X.ndim != 2 or self.y.shape != (self.X.shape[0],):
+            raise ValueError("X must be (N, D) and y (N,)")
+        self.priorScale = float(priorScale)
+        super().__init__(self.X.shape[1])
+
+    def _params(self):
+        return [self.X, self.y]
+
+    def _scalars(self):
+        return [self.priorScale]
+
+
 def _descriptor(potential):
     """Resolve what a user passed as potential=/gradient= to a descriptor."""
     if isinstance(potential, Potential):
@@ -153,6 +197,33 @@ def _descriptor(potential):
 def harmonicPotentialND(q, springConsts):
     """src/potential.py:18-27 -- q is (D,) or (D, P); evaluated on the GPU."""
     return HarmonicPotential(springConsts)(q)
+
+
+def getAccelNBody(q, mass, i):
+    """Acceleration of the i-th body of an N-body system, q is (numDimensions=3, N)
+    (src/potential.py:30-53): a_i = G sum_{j != i} m_j (r_j - r_i) / |r_j - r_i|^3, evaluated on
+    the GPU as -grad_i U / m_i of the NBodyPotential family (one ensemble particle = the system)."""
+    q = np.asarray(q, dtype=np.float64)
+    mass = np.asarray(mass, dtype=np.float64)
+    if q.shape[0] != 3:
+        raise ValueError("getAccelNBody on the GPU supports 3-D positions")
+    g = NBodyPotential(mass, gravConst, 0.0).gradient(np.ascontiguousarray(q).reshape(-1))
+    return -g.reshape(3, -1)[:, i] / mass[i]
+
+
+def gravitationalPotential(r1, r2, mass1, mass2):
+    """Potential between two masses with the reference's sign, +G m1 m2 / |r1 - r2|
+    (src/potential.py:56-69; note SURVEY row N1: the physical sign is the opposite)."""
+    q = np.stack([np.asarray(r1, dtype=np.float64), np.asarray(r2, dtype=np.float64)], axis=1)
+    return -NBodyPotential([mass1, mass2], gravConst, 0.0)(np.ascontiguousarray(q).reshape(-1))
+
+
+def nBodyPotential(q, mass, shape=None):
+    """src/potential.py:72-101 (reference sign: + sum_{i<j} G m_i m_j / r_ij)."""
+    q = np.asarray(q, dtype=np.float64)
+    if shape is not None:
+        q = q.reshape(shape)
+    return -NBodyPotential(mass, gravConst, 0.0)(np.ascontiguousarray(q).reshape(-1))
 
 
 def noPotential(q):

@@ -559,3 +559,144 @@ def test_reversibility_property(E, case):
     ens.p.neg_()
     assert (ens.q - q0).abs().max().item() < 1e-10 * max(1.0, q0.abs().max().item())
     assert (ens.p - p0).abs().max().item() < 1e-10 * max(1.0, p0.abs().max().item())
+
+
+# ---------------------------------------------------------------------------
+# N-body and logistic families
+# ---------------------------------------------------------------------------
+def test_getAccelNBody_matches_reference(E):
+    """src/potential.py:30-53 through the CUDA N-body family, vs the reference's own output."""
+    g = load_golden("known_answers")
+    q, m = g["nbody_q"], g["nbody_m"]
+    for i in range(q.shape[1]):
+        a = E.potential.getAccelNBody(q, m, i)
+        assert rel_err(a, g["nbody_acc"][:, i]) < 1e-12
+    # reference-signed potentials (SURVEY row N1)
+    assert rel_err(E.potential.nBodyPotential(q, m), g["nbody_pot"]) < 1e-12
+    assert rel_err(E.potential.gravitationalPotential(q[:, 0], q[:, 1], m[0], m[1]), g["grav_pot_01"]) < 1e-12
+
+
+@pytest.mark.parametrize("B,eps", [(5, 0.0), (64, 0.05), (300, 0.0)])
+def test_nbody_eval_matches_oracle(E, B, eps):
+    rng = np.random.RandomState(B)
+    m = rng.uniform(0.5, 1.5, B) / B
+    pe, po = E.NBodyPotential(m, G=1.0, eps=eps), O.NBody(m, 1.0, eps)
+    q = rng.standard_normal((3 * B, 5))
+    for dt in (np.float64, np.float32):
+        assert rel_err(pe(q.astype(dt)), po.energy(q)) < 20 * RTOL[dt]
+        assert rel_err(pe.gradient(q.astype(dt)), po.grad(q)) < 20 * RTOL[dt]
+
+
+@pytest.mark.parametrize("N,D", [(40, 6), (1000, 256), (333, 37)])
+def test_logistic_eval_matches_oracle(E, N, D):
+    rng = np.random.RandomState(N)
+    X = rng.standard_normal((N, D)) / np.sqrt(D)
+    y = (rng.uniform(size=N) < 0.5).astype(np.float64)
+    pe, po = E.LogisticPotential(X, y, 2.0), O.Logistic(X, y, 2.0)
+    q = rng.standard_normal((D, 70))
+    for dt in (np.float64, np.float32):
+        assert rel_err(pe(q.astype(dt)), po.energy(q)) < 20 * RTOL[dt]
+        assert rel_err(pe.gradient(q.astype(dt)), po.grad(q)) < 20 * RTOL[dt]
+
+
+@pytest.mark.parametrize("family", ["nbody", "logistic"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_families_production_equals_fed_and_stats(E, family, dt):
+    import torch
+
+    rng = np.random.RandomState(17)
+    if family == "nbody":
+        B, P = 32, 40
+        D = 3 * B
+        pe = E.NBodyPotential(np.ones(B) / B, G=1.0, eps=0.05)
+        h, L = 0.01, 5
+    else:
+        N, D, P = 200, 24, 300
+        X = rng.standard_normal((N, D)) / np.sqrt(D)
+        y = (rng.uniform(size=N) < 0.5).astype(np.float64)
+        pe = E.LogisticPotential(X, y, 1.0)
+        h, L = 0.1, 5
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    q0 = torch.tensor(rng.standard_normal((D, P)), dtype=tdt, device="cuda")
+    mass = torch.tensor(rng.uniform(0.5, 2.0, P), dtype=tdt, device="cuda")
+    ctx = E._lib.Context.get()
+    hd = pe.handle(32 if dt == np.float32 else 64, ctx)
+    args = E._lib.make_args(h, h**2, L, KB, 1 / KB, seed=3, iteration=11, particle_offset=7, flags=0)
+    qa, pa = q0.clone(), torch.empty_like(q0)
+    acc_a = torch.empty(P, dtype=torch.uint8, device="cuda")
+    st = torch.zeros(2 * D + 3, dtype=torch.float64, device="cuda")
+    E._lib.hmc_iter(ctx, hd, qa, mass, args, p_out=pa, accept=acc_a, stats=st)
+    z, u = torch.empty_like(q0), torch.empty(P, dtype=tdt, device="cuda")
+    E._lib.philox_fill(ctx, z, u, 3, 11, 7)
+    qb, pb = q0.clone(), torch.empty_like(q0)
+    acc_b = torch.empty(P, dtype=torch.uint8, device="cuda")
+    E._lib.hmc_iter(ctx, hd, qb, mass, args, p_out=pb, z=z, u=u, accept=acc_b)
+    torch.cuda.synchronize()
+    assert torch.equal(acc_a, acc_b) and torch.equal(qa, qb) and torch.equal(pa, pb)
+    qf = qa.double().cpu().numpy()
+    assert st[0].item() == int(acc_a.sum().item())
+    np.testing.assert_allclose(st[3:3 + D].cpu().numpy(), qf.sum(1), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(st[3 + D:].cpu().numpy(), (qf * qf).sum(1), rtol=1e-9)
+    # host path gives the same answer
+    qh = q0.cpu().numpy().copy()
+    sth = np.zeros(2 * D + 3)
+    acc_h = np.empty(P, dtype=np.uint8)
+    E._lib.hmc_iter(ctx, hd, qh, mass.cpu().numpy(), args, accept=acc_h, stats=sth)
+    assert np.array_equal(qh, qa.cpu().numpy()) and np.array_equal(acc_h, acc_a.cpu().numpy())
+    np.testing.assert_allclose(sth, st.cpu().numpy(), rtol=1e-12, atol=1e-9)
+
+
+def test_config4_shape_nbody_subset(E):
+    """BASELINE config 4 shape: 4096 bodies x 3-D per particle (D = 12288), Plummer eps = 0.05,
+    L = 10, float32; 24 ensemble particles, 2 of them checked against the float64 oracle."""
+    import torch
+
+    B, P, L, h = 4096, 24, 10, 0.01
+    rng = np.random.RandomState(4)
+    m = np.ones(B) / B
+    pe, po = E.NBodyPotential(m, G=1.0, eps=0.05), O.NBody(m, 1.0, 0.05)
+    q0 = rng.standard_normal((3 * B, P))
+    z = rng.standard_normal((3 * B, P))
+    u = rng.uniform(size=P)
+    ens = E.Ensemble(3 * B, P, dtype=np.float32, device="cuda")
+    ens.q.copy_(torch.tensor(q0, dtype=torch.float32))
+    hmc = E.HMC(ens, L * h + 1e-9, h, None, potential=pe)
+    acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+    hmc.step(1 / KB, accept=acc, z=torch.tensor(z, dtype=torch.float32, device="cuda"),
+             u=torch.tensor(u, dtype=torch.float32, device="cuda"))
+    torch.cuda.synchronize()
+    sel = [0, P - 1]
+    qr, pr, accr, oh, nh = O.hmc_iter(q0[:, sel], z[:, sel], u[sel], np.ones(2), 1 / KB, h, L, po)
+    a = acc.cpu().numpy().astype(bool)[sel]
+    clear = np.abs(u[sel] - np.minimum(1, np.exp(oh - nh))) > 2e-3
+    assert np.array_equal(a[clear], accr[clear])
+    same = a == accr
+    assert rel_err(ens.q.cpu().numpy()[:, sel][:, same], qr[:, same]) < 1e-5
+
+
+def test_config3_shape_logistic_reduced(E):
+    """BASELINE config 3 shape reduced in N and P: X 4096 x 256, 512 particles, L = 10, float32."""
+    import torch
+
+    N, D, P, L, h = 4096, 256, 512, 10, 0.02
+    rng = np.random.RandomState(3)
+    X = rng.standard_normal((N, D)) / np.sqrt(D)
+    th = rng.standard_normal(D)
+    y = (rng.uniform(size=N) < 1 / (1 + np.exp(-X @ th))).astype(np.float64)
+    pe, po = E.LogisticPotential(X, y, 1.0), O.Logistic(X, y, 1.0)
+    q0 = rng.standard_normal((D, P))
+    z = rng.standard_normal((D, P))
+    u = rng.uniform(size=P)
+    qr, pr, accr, oh, nh = O.hmc_iter(q0, z, u, np.ones(P), 1 / KB, h, L, po)
+    ens = E.Ensemble(D, P, dtype=np.float32, device="cuda")
+    ens.q.copy_(torch.tensor(q0, dtype=torch.float32))
+    hmc = E.HMC(ens, L * h + 1e-9, h, None, potential=pe)
+    acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+    hmc.step(1 / KB, accept=acc, z=torch.tensor(z, dtype=torch.float32, device="cuda"),
+             u=torch.tensor(u, dtype=torch.float32, device="cuda"))
+    torch.cuda.synchronize()
+    a = acc.cpu().numpy().astype(bool)
+    clear = np.abs(u - np.minimum(1, np.exp(oh - nh))) > 2e-3
+    assert np.array_equal(a[clear], accr[clear])
+    same = a == accr
+    assert rel_err(ens.q.cpu().numpy()[:, same], qr[:, same]) < 1e-5
