@@ -219,6 +219,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.Context.get(local_rank)
+    if os.environ.get("EHMC_DENSE_PATH"):
+        ctx.set_option("dense_path", float(os.environ["EHMC_DENSE_PATH"]))
     if os.environ.get("EHMC_DENSE_OCC"):
         ctx.set_option("dense_occupancy", float(os.environ["EHMC_DENSE_OCC"]))
 

@@ -178,6 +178,9 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
   if (!strcmp(name, "dense_occupancy")) {
     if (value != 1 && value != 2) return fail(EHMC_ERR_INVALID, "dense_occupancy must be 1 or 2");
     c->dense_occupancy = (int)value;
+  } else if (!strcmp(name, "dense_path")) {
+    if (value != 0 && value != 1 && value != 2) return fail(EHMC_ERR_INVALID, "dense_path must be 0, 1 or 2");
+    c->dense_path = (int)value;
   } else if (!strcmp(name, "host_chunk_mb")) {
     if (!(value >= 1 && value <= 4096)) return fail(EHMC_ERR_INVALID, "host_chunk_mb must be in [1, 4096]");
     c->host_chunk_bytes = (long long)value << 20;
@@ -357,6 +360,30 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       for (int d = 0; d < D; ++d) mu[d] = p->hp1[d];
       rc = upload_bits(p->bits, Ls, &p->d0);
       if (rc == EHMC_OK) rc = upload_bits(p->bits, mu, &p->d1);
+      if (rc == EHMC_OK && p->bits == 32 && D <= 104) {
+        // 3xTF32 tensor-core operands: Lambda_hi = rna_tf32(Lambda), Lambda_lo = Lambda - Lambda_hi,
+        // canonical K-major no-swizzle UMMA layout [KP/4][NP][4] (B[n][k] = Lambda[n][k])
+        const int KP = (D + 7) / 8 * 8, NP = (KP + 15) / 16 * 16, NCH = NP / 16, K4 = KP / 4;
+        std::vector<double> bhi((size_t)K4 * NP * 4, 0.0), blo(bhi.size(), 0.0), mu2(KP, 0.0);
+        for (int n = 0; n < D; ++n)
+          for (int k = 0; k < D; ++k) {
+            const float x = (float)p->hp0[(size_t)n * D + k];
+            uint32_t b;
+            memcpy(&b, &x, 4);
+            b = (b + 0x1000u) & 0xFFFFE000u;
+            float hi;
+            memcpy(&hi, &b, 4);
+            const size_t o = ((size_t)(k / 4) * NP + n) * 4 + (k % 4);
+            bhi[o] = hi;
+            blo[o] = (double)(x - hi);
+          }
+        for (int d = 0; d < D; ++d) mu2[d] = p->hp1[d];
+        rc = upload<float>(bhi, &p->d3);
+        if (rc == EHMC_OK) rc = upload<float>(blo, &p->d4);
+        if (rc == EHMC_OK) rc = upload<float>(mu2, &p->d5);
+        p->tc_nch = NCH;
+        p->tc_kp = KP;
+      }
     } else if (rc == EHMC_OK) {
       rc = upload_bits(p->bits, p->hp1, &p->d1);
     }
@@ -375,6 +402,9 @@ extern "C" int ehmc_potential_destroy(ehmc_potential* p) {
   if (p->d0) cudaFree(p->d0);
   if (p->d1) cudaFree(p->d1);
   if (p->d2) cudaFree(p->d2);
+  if (p->d3) cudaFree(p->d3);
+  if (p->d4) cudaFree(p->d4);
+  if (p->d5) cudaFree(p->d5);
   delete p;
   return EHMC_OK;
 }
@@ -385,9 +415,16 @@ static bool per_particle_stats(const ehmc_potential* p) {
   return p->family == EHMC_FAMILY_NBODY || p->family == EHMC_FAMILY_LOGISTIC;
 }
 
+// the float32 dense family runs on the tensor cores (3xTF32) unless told otherwise
+static bool use_dense_tc(const ehmc_ctx* c, const ehmc_potential* p, int integ) {
+  return p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->bits == 32 && p->tc_nch >= 2 && integ == INTEG_LEAPFROG &&
+         c->dense_path != 1;
+}
+
 template <typename T>
-static long long traj_blocks(const ehmc_potential* p, long long P) {
+static long long traj_blocks(const ehmc_ctx* c, const ehmc_potential* p, long long P, int integ) {
   if (per_particle_stats(p)) return P;
+  if (use_dense_tc(c, p, integ)) return 8 * ((P + 127) / 128);
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) {
     const int PT = dense_particles_per_cta<T>();
     return (P + PT - 1) / PT;
@@ -401,6 +438,11 @@ static int launch_traj(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& 
   if (A.P == 0) return EHMC_OK;
   if (p->family == EHMC_FAMILY_NBODY) return launch_nbody<T>(c, p, A, integ, hmc, st);
   if (p->family == EHMC_FAMILY_LOGISTIC) return launch_logistic<T>(c, p, A, integ, hmc, st, slot);
+  if constexpr (sizeof(T) == 4) {
+    if (use_dense_tc(c, p, integ)) return launch_dense_tc(c, p, A, hmc, st);
+  }
+  if (c->dense_path == 2 && p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16 && sizeof(T) == 4)
+    return fail(EHMC_ERR_UNSUPPORTED, "dense_path = 2 (tensor cores) but this call is not eligible (D = %d, integrator %d)", p->D, integ);
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) return launch_dense<T>(c, p, A, integ, hmc, st);
   return launch_small<T>(c, p, A, integ, hmc, st);
 }
@@ -454,7 +496,7 @@ static int run_device(ehmc_ctx* c, const ehmc_potential* pot, IterArgs<T> A, int
   const int NS = pps ? 3 : 2 * A.D + 3;
   long long nblk = 0;
   if (stats_dev != nullptr) {
-    nblk = traj_blocks<T>(pot, A.P);
+    nblk = traj_blocks<T>(c, pot, A.P, integ);
     TRY(c->partials.ensure(sizeof(double) * (size_t)std::max(1LL, nblk) * NS));
     A.partials = static_cast<double*>(c->partials.ptr);
   }
@@ -493,7 +535,7 @@ static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, 
   for (long long k = 0; k < nchunks; ++k) {
     const long long n = std::min(chunk, P - k * chunk);
     blk_off[k] = blocks_total;
-    blocks_total += traj_blocks<T>(pot, n);
+    blocks_total += traj_blocks<T>(c, pot, n, integ);
   }
   const bool pps = per_particle_stats(pot);
   if (v.has_stats) {

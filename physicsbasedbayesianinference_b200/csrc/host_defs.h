@@ -51,6 +51,7 @@ struct ehmc_ctx {
   cudaStream_t streams[N_STAGE] = {nullptr, nullptr, nullptr};
   // tuning options (ehmc_ctx_set_option)
   int dense_occupancy = 2;        // CTAs/SM the float32 dense kernel is compiled for (1 or 2)
+  int dense_path = 0;             // 0 auto (tensor cores when eligible), 1 CUDA cores (exact fp32 FMA), 2 force TC
   long long host_chunk_bytes = 32LL << 20;
 };
 
@@ -64,6 +65,11 @@ struct ehmc_potential {
   void* d0 = nullptr;  // dense: packed Ls ; nbody: body masses ; logistic: X
   void* d1 = nullptr;  // dense: mu (padded) ; logistic: y
   void* d2 = nullptr;  // dense: plain Lambda row-major (eval kernel)
+  void* d3 = nullptr;  // dense float32 tensor-core path: Lambda_hi [KP/4][NP][4]
+  void* d4 = nullptr;  //                                 Lambda_lo
+  void* d5 = nullptr;  //                                 mu [NP]
+  int tc_nch = 0;      // 16-column chunks of the tensor-core path (0 = not eligible)
+  int tc_kp = 0;       // K padded to a multiple of 8
   int TN = 0;          // dense tile selection
   int B = 0;           // nbody: bodies per particle
   int N = 0;           // logistic: data rows
@@ -81,6 +87,8 @@ int launch_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int
 // dense Gaussian, 16 < D <= 128
 template <typename T>
 int launch_dense(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);
+// float32 3xTF32 tensor-core variant (leapfrog only)
+int launch_dense_tc(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, bool hmc, cudaStream_t st);
 template <typename T>
 int dense_particles_per_cta();
 int dense_tn(int D);

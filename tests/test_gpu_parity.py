@@ -700,3 +700,72 @@ def test_config3_shape_logistic_reduced(E):
     assert np.array_equal(a[clear], accr[clear])
     same = a == accr
     assert rel_err(ens.q.cpu().numpy()[:, same], qr[:, same]) < 1e-5
+
+
+# ---------------------------------------------------------------------------
+# dense Gaussian: tensor-core (3xTF32, tcgen05) path vs CUDA-core FP32 path vs oracle
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("D,P,L", [(20, 300, 7), (40, 129, 9), (100, 1000, 50), (104, 257, 12), (17, 64, 0), (56, 200, 3)])
+def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
+    import torch
+
+    rng = np.random.RandomState(D)
+    A = rng.standard_normal((D, D))
+    prec = A @ A.T / D + np.eye(D)
+    mu = rng.standard_normal(D)
+    pe, po = E.GaussianPotential(precision=prec, mean=mu), O.DenseGaussian(prec, mu)
+    q0 = rng.standard_normal((D, P)) + mu[:, None]
+    z = rng.standard_normal((D, P))
+    u = rng.uniform(size=P)
+    mass = rng.uniform(0.5, 2.0, P)
+    h = 0.05
+    qr, pr, accr, oh, nh = O.hmc_iter(q0, z, u, mass, 1 / KB, h, L, po)
+    ctx = E._lib.Context.get()
+    hd = pe.handle(32, ctx)
+    args = E._lib.make_args(h, h**2, L, KB, 1 / KB, flags=1)
+    out = {}
+    try:
+        for path in (1, 2):  # 1 = CUDA cores, 2 = tensor cores
+            ctx.set_option("dense_path", path)
+            q = torch.tensor(q0, dtype=torch.float32, device="cuda")
+            p = torch.empty_like(q)
+            acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+            st = torch.zeros(2 * D + 3, dtype=torch.float64, device="cuda")
+            E._lib.hmc_iter(ctx, hd, q, torch.tensor(mass, dtype=torch.float32, device="cuda"), args, p_out=p,
+                            z=torch.tensor(z, dtype=torch.float32, device="cuda"),
+                            u=torch.tensor(u, dtype=torch.float32, device="cuda"), accept=acc, stats=st)
+            torch.cuda.synchronize()
+            out[path] = (q.cpu().numpy(), p.cpu().numpy(), acc.cpu().numpy().astype(bool), st.cpu().numpy())
+    finally:
+        ctx.set_option("dense_path", 0)
+    with np.errstate(over="ignore"):
+        clear = np.abs(u - np.minimum(1, np.exp(oh - nh))) > TIE[np.float32]
+    for path in (1, 2):
+        q, p, a, st = out[path]
+        assert np.array_equal(a[clear], accr[clear]), f"path {path}"
+        same = a == accr
+        assert rel_err(q[:, same], qr[:, same]) < 1e-5, f"path {path}"
+        assert rel_err(p[:, same], pr[:, same]) < 1e-5, f"path {path}"
+        assert st[0] == a.sum()
+        np.testing.assert_allclose(st[3:3 + D], q.astype(np.float64).sum(1), rtol=1e-9, atol=1e-9)
+    print("D", D, "tc-vs-oracle", rel_err(out[2][0], qr), "cc-vs-oracle", rel_err(out[1][0], qr))
+
+
+def test_dense_tensor_core_integrate_only(E):
+    """Leapfrog.integrate() (no Metropolis) on the tensor-core path."""
+    import torch
+
+    D, P, L, h = 100, 500, 20, 0.05
+    rng = np.random.RandomState(8)
+    A = rng.standard_normal((D, D))
+    prec = A @ A.T / D + np.eye(D)
+    q0 = rng.standard_normal((D, P))
+    p0 = rng.standard_normal((D, P))
+    mass = rng.uniform(0.5, 2.0, P)
+    qr, pr = O.leapfrog(q0, p0, mass, h, L, O.DenseGaussian(prec).grad)
+    ens = E.Ensemble(D, P, dtype=np.float32, device="cuda")
+    ens.q.copy_(torch.tensor(q0, dtype=torch.float32))
+    ens.p.copy_(torch.tensor(p0, dtype=torch.float32))
+    ens.mass = torch.tensor(mass, dtype=torch.float32, device="cuda")
+    q, p = E.Leapfrog(ens, h, L * h + 1e-9, E.GaussianPotential(precision=prec)).integrate()
+    assert rel_err(q.cpu().numpy(), qr) < 1e-5 and rel_err(p.cpu().numpy(), pr) < 1e-5
