@@ -221,6 +221,8 @@ def main():
     ctx = _lib.Context.get(local_rank)
     if os.environ.get("EHMC_DENSE_PATH"):
         ctx.set_option("dense_path", float(os.environ["EHMC_DENSE_PATH"]))
+    if os.environ.get("EHMC_TC_DEBUG"):
+        ctx.set_option("tc_debug", float(os.environ["EHMC_TC_DEBUG"]))
     if os.environ.get("EHMC_DENSE_OCC"):
         ctx.set_option("dense_occupancy", float(os.environ["EHMC_DENSE_OCC"]))
 

@@ -147,6 +147,7 @@ extern "C" int ehmc_ctx_destroy(ehmc_ctx* c) {
   c->partials.release();
   c->stage_stats.release();
   c->pstats.release();
+  c->tc_prof_buf.release();
   for (int i = 0; i < N_STAGE; ++i) {
     c->stage[i].release();
     c->uf[i].release();
@@ -179,8 +180,25 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
     if (value != 1 && value != 2) return fail(EHMC_ERR_INVALID, "dense_occupancy must be 1 or 2");
     c->dense_occupancy = (int)value;
   } else if (!strcmp(name, "dense_path")) {
-    if (value != 0 && value != 1 && value != 2) return fail(EHMC_ERR_INVALID, "dense_path must be 0, 1 or 2");
+    if (value != 0 && value != 1 && value != 2 && value != 3) return fail(EHMC_ERR_INVALID, "dense_path must be 0..3");
     c->dense_path = (int)value;
+  } else if (!strcmp(name, "tc_prof")) {
+    c->tc_prof = (int)value;
+    if (c->tc_prof) {
+      TRY(c->tc_prof_buf.ensure(64 * sizeof(long long)));
+      CUDA_TRY(cudaMemset(c->tc_prof_buf.ptr, 0, 64 * sizeof(long long)));
+    }
+  } else if (!strcmp(name, "tc_prof_dump")) {
+    // debugging aid: print the trace to stderr
+    if (c->tc_prof_buf.ptr) {
+      long long h[64];
+      CUDA_TRY(cudaMemcpy(h, c->tc_prof_buf.ptr, sizeof(h), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "tc_prof start=%lld:", h[63]);
+      for (int i = 0; i < 62 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[63]);
+      fprintf(stderr, "\n");
+    }
+  } else if (!strcmp(name, "tc_debug")) {
+    c->tc_debug = (int)value;
   } else if (!strcmp(name, "host_chunk_mb")) {
     if (!(value >= 1 && value <= 4096)) return fail(EHMC_ERR_INVALID, "host_chunk_mb must be in [1, 4096]");
     c->host_chunk_bytes = (long long)value << 20;
@@ -361,7 +379,7 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       rc = upload_bits(p->bits, Ls, &p->d0);
       if (rc == EHMC_OK) rc = upload_bits(p->bits, mu, &p->d1);
       if (rc == EHMC_OK && p->bits == 32 && D <= 104) {
-        // 3xTF32 tensor-core operands: Lambda_hi = rna_tf32(Lambda), Lambda_lo = Lambda - Lambda_hi,
+        // 3xTF32 tensor-core operands: Lambda_hi = Lambda (the MMA truncates), Lambda_lo = Lambda - trunc(Lambda),
         // canonical K-major no-swizzle UMMA layout [KP/4][NP][4] (B[n][k] = Lambda[n][k])
         const int KP = (D + 7) / 8 * 8, NP = (KP + 15) / 16 * 16, NCH = NP / 16, K4 = KP / 4;
         std::vector<double> bhi((size_t)K4 * NP * 4, 0.0), blo(bhi.size(), 0.0), mu2(KP, 0.0);
@@ -370,11 +388,11 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
             const float x = (float)p->hp0[(size_t)n * D + k];
             uint32_t b;
             memcpy(&b, &x, 4);
-            b = (b + 0x1000u) & 0xFFFFE000u;
+            b &= 0xFFFFE000u;  // what the tf32 MMA reads of x (low 13 mantissa bits ignored)
             float hi;
             memcpy(&hi, &b, 4);
             const size_t o = ((size_t)(k / 4) * NP + n) * 4 + (k % 4);
-            bhi[o] = hi;
+            bhi[o] = x;  // the full float32 pattern is the "hi" operand
             blo[o] = (double)(x - hi);
           }
         for (int d = 0; d < D; ++d) mu2[d] = p->hp1[d];
@@ -424,7 +442,7 @@ static bool use_dense_tc(const ehmc_ctx* c, const ehmc_potential* p, int integ) 
 template <typename T>
 static long long traj_blocks(const ehmc_ctx* c, const ehmc_potential* p, long long P, int integ) {
   if (per_particle_stats(p)) return P;
-  if (use_dense_tc(c, p, integ)) return 8 * ((P + 127) / 128);
+  if (use_dense_tc(c, p, integ)) return c->dense_path == 2 ? 8 * ((P + 127) / 128) : 8 * ((P + 255) / 256);
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) {
     const int PT = dense_particles_per_cta<T>();
     return (P + PT - 1) / PT;
@@ -441,7 +459,7 @@ static int launch_traj(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& 
   if constexpr (sizeof(T) == 4) {
     if (use_dense_tc(c, p, integ)) return launch_dense_tc(c, p, A, hmc, st);
   }
-  if (c->dense_path == 2 && p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16 && sizeof(T) == 4)
+  if (c->dense_path >= 2 && p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16 && sizeof(T) == 4)
     return fail(EHMC_ERR_UNSUPPORTED, "dense_path = 2 (tensor cores) but this call is not eligible (D = %d, integrator %d)", p->D, integ);
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) return launch_dense<T>(c, p, A, integ, hmc, st);
   return launch_small<T>(c, p, A, integ, hmc, st);

@@ -53,6 +53,9 @@ struct ehmc_ctx {
   int dense_occupancy = 2;        // CTAs/SM the float32 dense kernel is compiled for (1 or 2)
   int dense_path = 0;             // 0 auto (tensor cores when eligible), 1 CUDA cores (exact fp32 FMA), 2 force TC
   long long host_chunk_bytes = 32LL << 20;
+  int tc_prof = 0;                // 1: record a clock64 trace of CTA 0 into tc_prof_buf (64 x int64)
+  DevBuf tc_prof_buf;
+  int tc_debug = 0;               // profiling knobs of the tensor-core kernels (see DenseTcArgs::dbg)
 };
 
 struct ehmc_potential {

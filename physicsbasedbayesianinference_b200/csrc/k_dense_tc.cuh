@@ -4,7 +4,7 @@
 // is re-issued L+1 times on on-chip state.  Here it runs as tcgen05.mma (kind::tf32,
 // M = 128, N = 16*NCH, K = 8 per instruction) with the accumulator in TMEM; float32
 // accuracy is recovered with the 3xTF32 split
-//       x = x_hi + x_lo,  Lambda = L_hi + L_lo   (hi = cvt.rna.tf32, lo = exact remainder)
+//       x = x_hi + x_lo,  Lambda = L_hi + L_lo   (hi = the 19 bits the MMA reads, lo = exact remainder)
 //       G ~= x_hi L_hi + x_lo L_hi + x_hi L_lo   (the dropped x_lo L_lo term is 2^-22 relative)
 // which tracks the float64 oracle to ~1e-6 over a 50-step trajectory (float32 FMA: 4e-7).
 //
@@ -51,6 +51,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
   } while (!ok);
+}
+// one elected lane of a converged warp (lets the compiler keep tcgen05 operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -123,6 +135,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+// what the tf32 MMA actually multiplies when handed a float32 bit pattern: the low 13 mantissa bits
+// are ignored.  The 3xTF32 split used here is x_hi = trunc(x) (implicit: x itself is the operand),
+// x_lo = x - trunc(x) (exact, stored explicitly).
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // K-major, no-swizzle shared-memory matrix descriptor of one K = 8 (two 16-byte chunks) slice of an
 // operand stored as [K/4][R][4] floats: core matrices (8 rows x 16 B) contiguous along the rows
@@ -160,6 +176,8 @@ struct DenseTcArgs {
   const float* Bhi;  // [K4][NP][4]
   const float* Blo;
   const float* mu;   // [KP] zero padded
+  int dbg;           // profiling knobs: 1 = issue no MMAs (commit only), 2 = skip the epilogue arithmetic
+  long long* prof;   // optional: clock64() trace of CTA 0 / tile 0 / thread 0 (see ehmc_ctx_set_option "tc_prof")
 };
 
 // One evaluation's epilogue for this thread's 8*NC columns starting at 8-column chunk cb:
@@ -180,8 +198,8 @@ __device__ __forceinline__ void tc_epilogue(float (&v)[8 * TcShape<K8>::C0], flo
     if (c < nc) {
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const float4 hi = Ahi[(2 * (cb + c) + t) * TC_M + row], lo = Alo[(2 * (cb + c) + t) * TC_M + row];
-        float x[4] = {hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w};
+        const float4 hi = Ahi[(2 * (cb + c) + t) * TC_M + row];  // x itself (see tf32_trunc)
+        float x[4] = {hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float gd = __uint_as_float(g[c][4 * t + e]);
@@ -190,10 +208,10 @@ __device__ __forceinline__ void tc_epilogue(float (&v)[8 * TcShape<K8>::C0], flo
           if (!LAST) x[e] = fmaf(h, v[8 * c + 4 * t + e], x[e]);
         }
         if (!LAST) {
-          float4 nh, nl;
-          nh.x = tf32_rna(x[0]); nh.y = tf32_rna(x[1]); nh.z = tf32_rna(x[2]); nh.w = tf32_rna(x[3]);
-          nl.x = x[0] - nh.x; nl.y = x[1] - nh.y; nl.z = x[2] - nh.z; nl.w = x[3] - nh.w;
-          Ahi[(2 * (cb + c) + t) * TC_M + row] = nh;
+          float4 nl;
+          nl.x = x[0] - tf32_trunc(x[0]); nl.y = x[1] - tf32_trunc(x[1]);
+          nl.z = x[2] - tf32_trunc(x[2]); nl.w = x[3] - tf32_trunc(x[3]);
+          Ahi[(2 * (cb + c) + t) * TC_M + row] = make_float4(x[0], x[1], x[2], x[3]);
           Alo[(2 * (cb + c) + t) * TC_M + row] = nl;
         }
       }
@@ -272,10 +290,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dense_tc(const IterArgs<float
             }
             Kpart = fmaf(p[e], p[e], Kpart);
           }
-          float4 hi, lo;
-          hi.x = tf32_rna(x[0]); hi.y = tf32_rna(x[1]); hi.z = tf32_rna(x[2]); hi.w = tf32_rna(x[3]);
-          lo.x = x[0] - hi.x; lo.y = x[1] - hi.y; lo.z = x[2] - hi.z; lo.w = x[3] - hi.w;
-          Ahi[k4 * TC_M + row] = hi;
+          float4 lo;
+          lo.x = x[0] - tf32_trunc(x[0]); lo.y = x[1] - tf32_trunc(x[1]);
+          lo.z = x[2] - tf32_trunc(x[2]); lo.w = x[3] - tf32_trunc(x[3]);
+          Ahi[k4 * TC_M + row] = make_float4(x[0], x[1], x[2], x[3]);
           Alo[k4 * TC_M + row] = lo;
         }
 #pragma unroll
@@ -378,8 +396,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_dense_tc(const IterArgs<float
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int k4 = 2 * (cb + c) + t;
-      const float4 hi = Ahi[k4 * TC_M + row], lo = Alo[k4 * TC_M + row];
-      const float x[4] = {hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w};
+      const float4 hi = Ahi[k4 * TC_M + row];
+      const float x[4] = {hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int d = 4 * k4 + e;

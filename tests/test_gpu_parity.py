@@ -725,7 +725,7 @@ def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
     args = E._lib.make_args(h, h**2, L, KB, 1 / KB, flags=1)
     out = {}
     try:
-        for path in (1, 2):  # 1 = CUDA cores, 2 = tensor cores
+        for path in (1, 2, 3):  # 1 = CUDA cores, 2 = tensor cores (one tile, SS), 3 = tensor cores (two tiles, TS)
             ctx.set_option("dense_path", path)
             q = torch.tensor(q0, dtype=torch.float32, device="cuda")
             p = torch.empty_like(q)
@@ -740,7 +740,7 @@ def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
         ctx.set_option("dense_path", 0)
     with np.errstate(over="ignore"):
         clear = np.abs(u - np.minimum(1, np.exp(oh - nh))) > TIE[np.float32]
-    for path in (1, 2):
+    for path in (1, 2, 3):
         q, p, a, st = out[path]
         assert np.array_equal(a[clear], accr[clear]), f"path {path}"
         same = a == accr
@@ -748,7 +748,8 @@ def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
         assert rel_err(p[:, same], pr[:, same]) < 1e-5, f"path {path}"
         assert st[0] == a.sum()
         np.testing.assert_allclose(st[3:3 + D], q.astype(np.float64).sum(1), rtol=1e-9, atol=1e-9)
-    print("D", D, "tc-vs-oracle", rel_err(out[2][0], qr), "cc-vs-oracle", rel_err(out[1][0], qr))
+    print("D", D, "tc2-vs-oracle", rel_err(out[3][0], qr), "tc-vs-oracle", rel_err(out[2][0], qr), "cc-vs-oracle",
+          rel_err(out[1][0], qr))
 
 
 def test_dense_tensor_core_integrate_only(E):
