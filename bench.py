@@ -82,54 +82,76 @@ def make_oracle_potential(O, name, D):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU through NVML (nvidia_ml_py) every
+    20 ms in a thread while the timed region runs; falls back to one nvidia-smi query."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        except Exception:
+            self.nvml = None
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.nvml is None:
+            return self._smi_once()
+        self.stop_flag.set()
+        self.thread.join(timeout=1)
+        n = self.nvml
         try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        sm = [x[0] for x in self.samples]
+        reasons = set()
+        for _, _, rs in self.samples:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                "sm_max_mhz": float(mx) if mx else None,
+                "power_w_max": max(x[1] for x in self.samples) if self.samples else None,
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvml, 20 ms period, during the timed region"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", "--query-gpu=clocks.sm,clocks.max.sm,power.draw",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            f = [float(x) for x in out.strip().split(",")]
+            return {"sm_mhz": f[0], "sm_max_mhz": f[1], "power_w_max": f[2], "samples": 1, "reasons": [],
+                    "source": "nvidia-smi single query (nvml unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
 
 
 # ---------------------------------------------------------------------------
@@ -188,13 +210,14 @@ def run_reference_arm(args, cfg, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ess-iters", type=int, default=150, help="iterations of the ESS/s phase (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = CONFIGS[args.config]
@@ -245,8 +268,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        hmc.step(1 / KB)
+    adaptive = args.config.startswith("c5")  # config 5: ensemble statistics all-reduced every iteration
+    group = dist.group.WORLD if world > 1 else None
+    if adaptive:
+        hmc.run(args.warmup, 1 / KB, adapt=True, group=group)
+    else:
+        for _ in range(args.warmup):
+            hmc.step(1 / KB)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -254,20 +282,51 @@ def main():
     launches0 = ctx.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
-    for i in range(args.steps):
-        hmc.step(1 / KB)
-        ev[i + 1].record()
+    if adaptive:
+        run_out = hmc.run(args.steps, 1 / KB, adapt=True, group=group)
+        for i in range(args.steps):
+            ev[i + 1] = ev[0]
+        ev[-1] = torch.cuda.Event(enable_timing=True)
+        ev[-1].record()
+    else:
+        for i in range(args.steps):
+            hmc.step(1 / KB)
+            ev[i + 1].record()
     barrier()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
-    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    per_step = [total_ms / args.steps] if adaptive else [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = P * L * args.steps / (total_ms * 1e-3)
+
+    # ---- ESS/s: min over dimensions of the ESS of traced chains, scaled to the ensemble ------
+    ess = None
+    if args.ess_iters > 0:
+        from physicsbasedbayesianinference_b200 import diagnostics
+
+        ntrace = min(256, Pl)
+        burn = 30
+        hmc.run(burn, 1 / KB, collectStats=False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = hmc.run(args.ess_iters, 1 / KB, traceParticles=ntrace, collectStats=False)
+        e1.record()
+        barrier()
+        tsec = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            m, scaled = diagnostics.ess_min_over_dims(r["trace"], numParticlesTotal=P)
+            ess = {"ess_per_sec": scaled / float(tsec.item()), "iterations": args.ess_iters,
+                   "ess_per_chain_per_iter_min_dim": m / (ntrace * args.ess_iters), "traced_chains": ntrace,
+                   "estimator": "FFT autocovariance averaged over traced chains + Geyer initial positive "
+                                "sequence, min over dimensions, scaled by P/traced"}
 
     # ---- e2e through the host-facing API ------------------------------------------------
     e2e = None
@@ -310,8 +369,25 @@ def main():
         hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
         info = ctx.device_info()
         nominal_fp32 = info["sm_count"] * 128 * 2 * info["sm_clock_mhz"] * 1e6 / 1e12
+        dense_tc = args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1"
         compute_bound = ach_tf / fp32_peak > ach_gbs / hbm_peak
-        if compute_bound:
+        if dense_tc:
+            # the gradient GEMM runs on tcgen05 (kind::tf32, 3 split passes): tensor-pipe roofline against
+            # the measured dense bf16 peak.  Executed tensor flops per algorithmic flop:
+            # 3 passes x (104*112)/(100*100) padding; tf32 runs at half the bf16 rate, so the ceiling of
+            # this formulation is peak / (2*3*1.165) in algorithmic TFLOP/s.
+            tpeak = peaks.get("bf16_tflops", 1590.0)
+            exec_factor = 3.0 * (104.0 * 112.0) / (D * D) if D == 100 else 3.0
+            roof = {"bound": "tensor", "achieved": ach_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_tf / tpeak,
+                    "traffic": None,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback"),
+                    "flops_per_unit": fl, "units_per_launch": Pl * L,
+                    "executed_tensor_tflops_tf32": ach_tf * exec_factor,
+                    "formulation_ceiling_frac": 1.0 / (2.0 * exec_factor),
+                    "note": "algorithmic fp32 flops (2 D^2 + 7 D per particle-step) over the measured bf16 peak; "
+                            "3xTF32 executes 3.49x those flops at the tf32 (half) rate, i.e. the tensor pipe is "
+                            "busy ~frac*2*3.49 of the time"}
+        elif compute_bound:
             roof = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": ach_tf / fp32_peak, "traffic": None,
                     "peak_source": "measured in this run (ehmc_measure_fp32_peak, register-only FFMA kernel); "
@@ -334,11 +410,14 @@ def main():
         line = {
             "metric": "particle-leapfrog-steps/sec", "value": value, "unit": "particle-leapfrog-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core split, fp32 accumulate)" if (args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1") else "f32",
+            "data": "synthetic",
             "config": {"workload": cfg["desc"], "D": D, "P": P, "L": L, "h": h, "particles_per_gpu": Pl,
                        "rng": "philox in-kernel", "l2": "inputs_exceed_l2" if D * Pl * 4 > 126e6 else "resident",
                        "parallelism": f"particle-shard x{world}, no data-path collective"},
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+            "ess": ess, "adaptation": ({"final_step_size": run_out["stepSize"][-1],
+                                        "accept_rate_last": run_out["acceptRate"][-1]} if adaptive else None),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

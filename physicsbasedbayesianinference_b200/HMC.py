@@ -185,6 +185,85 @@ class HMC:
         return samples_hmc, momentum_hmc
 
 
+    # ------------------------------------------------------------------------------------
+    def run(self, numIterations, temperature, *, adapt=False, targetAccept=0.8, adaptIterations=None,
+            traceParticles=0, group=None, collectStats=True):
+        """Production loop for device ensembles (build-defined; scales where getSamples'
+        (D, P, S) arrays cannot, SURVEY.md section 7 hard part 7).
+
+        Every iteration is one ehmc_hmc_iter launch on the resident ensemble with in-kernel
+        Philox draws.  Per-iteration ensemble statistics (2D+3 float64 sums) are produced by the
+        same launch, all-reduced across the ranks of `group` asynchronously and consumed one
+        iteration late (step-size adaptation, running moments).  Positions of the first
+        `traceParticles` local particles are kept for ESS estimation.
+
+        Returns dict(acceptRate[S], meanAcceptProb[S], meanH[S], stepSize[S], mean[D], var[D],
+        trace (D, traceParticles, S) or None).
+        """
+        import torch
+
+        from .parallel import StatsReducer, StepSizeAdapter, unpack_stats
+
+        ens = self.ensemble
+        if not ens.onDevice:
+            raise TypeError("HMC.run needs a device-backed Ensemble (device='cuda'); use getSamples for host arrays")
+        D, P = ens.numDimensions, ens.numParticles
+        dev = ens.device
+        reducer = StatsReducer(group)
+        world = reducer.dist.get_world_size(group) if reducer.enabled else 1
+        Ptot = float(P)
+        if reducer.enabled:
+            t = torch.tensor([P], dtype=torch.float64, device=dev)
+            reducer.dist.all_reduce(t, group=group)
+            Ptot = float(t.item())
+        adapter = StepSizeAdapter(self.stepSize, targetAccept) if adapt else None
+        adaptIterations = numIterations if adaptIterations is None else adaptIterations
+        stats = [torch.zeros(2 * D + 3, dtype=torch.float64, device=dev) for _ in range(2)]
+        host = torch.zeros(2 * D + 3, dtype=torch.float64).pin_memory()
+        out = dict(acceptRate=[], meanAcceptProb=[], meanH=[], stepSize=[])
+        sum1 = torch.zeros(D, dtype=torch.float64)
+        sum2 = torch.zeros(D, dtype=torch.float64)
+        nstat = 0
+        trace = (torch.empty((D, traceParticles, numIterations), dtype=ens.dtype, device=dev)
+                 if traceParticles else None)
+        self.integrator.q = ens.q
+        pending = None  # statistics tensor whose all-reduce is in flight
+
+        def consume(buf, it):
+            nonlocal nstat
+            reducer.wait()
+            host.copy_(buf)  # sync D2H of 2D+3 doubles
+            u = unpack_stats(host, D, Ptot)
+            out["acceptRate"].append(u["acceptRate"])
+            out["meanAcceptProb"].append(u["meanAcceptProb"])
+            out["meanH"].append(u["meanH"])
+            sum1.add_(host[3:3 + D])
+            sum2.add_(host[3 + D:3 + 2 * D])
+            nstat += 1
+            if adapter is not None and it < adaptIterations:
+                self.stepSize = adapter.update(u["meanAcceptProb"])
+                self.integrator.stepSize = self.stepSize
+                self.integrator.numSteps = int(self.simulTime / self.stepSize)  # src/integrator.py:51
+
+        for it in range(numIterations):
+            buf = stats[it & 1]
+            out["stepSize"].append(self.stepSize)
+            self.step(temperature, stats=buf if collectStats else None)
+            if trace is not None:
+                trace[:, :, it] = ens.q[:, :traceParticles]
+            if collectStats:
+                if pending is not None:
+                    consume(*pending)  # statistics of the PREVIOUS iteration (one iteration stale)
+                reducer.reduce_async(buf)
+                pending = (buf, it)
+        if pending is not None:
+            consume(*pending)
+        n = max(nstat, 1) * Ptot
+        mean = sum1 / n
+        out.update(mean=mean, var=sum2 / n - mean * mean, trace=trace, worldSize=world)
+        return out
+
+
 class GaussianDensity:
     """Density object for the ``density`` argument: a multivariate normal whose
     ``.potential`` is the matching GaussianPotential descriptor (the role played by

@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing of the ensemble: one process per GPU (torch.distributed, NCCL over
+NVLink/NVSwitch), particles sharded by contiguous ranges, model data replicated.
+
+Particles are independent (src/integrator.py:105-120 reads only column i; the accept test
+src/HMC.py:173-176 is per particle), so the data path needs NO collective.  Only the
+per-iteration ensemble statistics vector of ehmc_hmc_iter (2D+3 float64 sums: n_accept,
+sum acceptance probability, sum H, sum q_d, sum q_d^2) crosses GPUs, through one all-reduce
+that is issued asynchronously and consumed one iteration late, so its ~10-20 us latency is
+off the critical path.
+"""
+from __future__ import annotations
+
+import math
+
+
+def shard_range(numParticles, rank, worldSize):
+    """Contiguous particle range [lo, hi) of `rank` (global Philox ids: particleOffset = lo)."""
+    lo = rank * numParticles // worldSize
+    hi = (rank + 1) * numParticles // worldSize
+    return lo, hi
+
+
+class StatsReducer:
+    """Sums the statistics vectors of all ranks with one all-reduce per call.
+
+    reduce_async(t) starts the collective on `t` in place (no-op without a process group);
+    wait() blocks until the last started one is done.  Works with NCCL (CUDA tensors) and
+    gloo (CPU tensors; used by the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.work = None
+
+    def reduce_async(self, stats):
+        if self.enabled:
+            self.work = self.dist.all_reduce(stats, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return stats
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+
+
+class StepSizeAdapter:
+    """Ensemble-based step-size adaptation (build-defined; the reference has none, SURVEY.md
+    section 2).  The acceptance statistic is an average over the WHOLE ensemble (all GPUs), so a
+    plain Robbins-Monro update of log(h) towards the target acceptance is already low-noise:
+        log h <- log h + clip(gain_k * (mean acceptance probability - target)),  gain_k = gain0 / k^kappa
+    Every rank applies the same update to the same all-reduced numbers, so step sizes stay
+    identical on all ranks without a broadcast."""
+
+    def __init__(self, stepSize, target=0.8, gain0=1.5, kappa=0.5, minStep=1e-6, maxStep=1e3, maxMove=0.7):
+        self.logh = math.log(stepSize)
+        self.target = float(target)
+        self.gain0 = float(gain0)
+        self.kappa = float(kappa)
+        self.k = 0
+        self.lo, self.hi = math.log(minStep), math.log(maxStep)
+        self.maxMove = float(maxMove)  # cap of one update in log space
+
+    @property
+    def stepSize(self):
+        return math.exp(self.logh)
+
+    def update(self, meanAcceptProb):
+        if not math.isfinite(meanAcceptProb):
+            meanAcceptProb = 0.0
+        self.k += 1
+        move = self.gain0 / self.k**self.kappa * (meanAcceptProb - self.target)
+        self.logh += min(max(move, -self.maxMove), self.maxMove)
+        self.logh = min(max(self.logh, self.lo), self.hi)
+        return self.stepSize
+
+
+def unpack_stats(stats, numDimensions, numParticles):
+    """Named view of the 2D+3 statistics vector of ehmc_hmc_iter (summed over ranks) for an
+    ensemble of numParticles particles in total."""
+    D, P = numDimensions, float(numParticles)
+    s = [float(x) for x in stats[:3]]
+    mean = stats[3:3 + D] / P
+    var = stats[3 + D:3 + 2 * D] / P - mean * mean
+    return dict(acceptRate=s[0] / P, meanAcceptProb=s[1] / P, meanH=s[2] / P, mean=mean, var=var)

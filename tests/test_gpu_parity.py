@@ -770,3 +770,29 @@ def test_dense_tensor_core_integrate_only(E):
     ens.mass = torch.tensor(mass, dtype=torch.float32, device="cuda")
     q, p = E.Leapfrog(ens, h, L * h + 1e-9, E.GaussianPotential(precision=prec)).integrate()
     assert rel_err(q.cpu().numpy(), qr) < 1e-5 and rel_err(p.cpu().numpy(), pr) < 1e-5
+
+
+# ---------------------------------------------------------------------------
+# production loop: statistics, adaptation, ESS
+# ---------------------------------------------------------------------------
+def test_run_adaptation_and_moments(E):
+    """HMC.run on a 20-D correlated Gaussian: the adapted step size brings the ensemble
+    acceptance to the target, the streaming moments match the target covariance, ESS > 0."""
+    import torch
+
+    D, P = 20, 1 << 15
+    rng = np.random.RandomState(2)
+    A = rng.standard_normal((D, D))
+    prec = A @ A.T / D + np.eye(D)
+    cov = np.linalg.inv(prec)
+    ens = E.Ensemble(D, P, dtype=np.float32, device="cuda", seed=7)
+    ens.setPosition(1.0)
+    hmc = E.HMC(ens, 1.5, 0.02, None, potential=E.GaussianPotential(precision=prec), seed=7)
+    r = hmc.run(200, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=160)
+    assert abs(np.mean(r["meanAcceptProb"][170:]) - 0.8) < 0.05
+    assert hmc.stepSize > 0.05  # grew from the tiny initial value
+    r2 = hmc.run(120, 1 / KB, traceParticles=128)
+    np.testing.assert_allclose(r2["var"].numpy(), np.diag(cov), rtol=0.06)
+    assert np.all(np.abs(r2["mean"].numpy()) < 0.05)
+    m, scaled = E.diagnostics.ess_min_over_dims(r2["trace"], numParticlesTotal=P)
+    assert 0 < m <= 128 * 120 * 3 and scaled == pytest.approx(m * P / 128)
