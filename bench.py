@@ -39,6 +39,10 @@ CONFIGS = {
     "c5": dict(D=10, P=1 << 22, L=20, h=0.05, desc="config5: Neal's funnel 10-D, P=2^22, L=20"),
     "c5l4": dict(D=10, P=1 << 22, L=4, h=0.05, desc="config5 HBM-bound variant: funnel 10-D, P=2^22, L=4"),
     "c1": dict(D=2, P=1024, L=20, h=0.05, desc="config1: 2-D isotropic Gaussian, P=1024, L=20"),
+    "c3": dict(D=256, P=65536, L=10, h=0.01, N=100000,
+               desc="config3: Bayesian logistic regression, X 100k x 256, P=65536, L=10"),
+    "c4": dict(D=3 * 4096, P=1024, L=10, h=0.01, B=4096,
+               desc="config4: pairwise gravitational N-body, 4096 bodies x 3-D per particle, P=1024, L=10, eps=0.05"),
 }
 
 
@@ -48,6 +52,10 @@ def flops_per_unit(name, D):
         return 2.0 * D * D + 7.0 * D
     if name.startswith("c5"):
         return 110.0
+    if name == "c3":
+        return 4.0 * 100000 * D + 7.0 * D  # two GEMMs over the N data rows
+    if name == "c4":
+        return 20.0 * (D // 3) ** 2 + 7.0 * D  # 20-flop/interaction convention, all pairs
     return 2.0 * D + 7.0 * D
 
 
@@ -62,7 +70,21 @@ def make_precision(D):
     return A @ A.T / D + np.eye(D)
 
 
+def make_logistic_data(D, N):
+    rng = np.random.RandomState(SEED)
+    X = rng.standard_normal((N, D)) / np.sqrt(D)
+    theta = rng.standard_normal(D)
+    y = (rng.uniform(size=N) < 1.0 / (1.0 + np.exp(-X @ theta))).astype(np.float64)
+    return X, y
+
+
 def make_potential(E, name, D):
+    if name == "c3":
+        X, y = make_logistic_data(D, CONFIGS["c3"]["N"])
+        return E.LogisticPotential(X, y, 1.0, precision=os.environ.get("EHMC_LOGISTIC_PRECISION", "bf16"))
+    if name == "c4":
+        B = D // 3
+        return E.NBodyPotential(np.ones(B) / B, G=1.0, eps=0.05)
     if name == "c2":
         return E.GaussianPotential(precision=make_precision(D))
     if name.startswith("c5"):
@@ -71,6 +93,12 @@ def make_potential(E, name, D):
 
 
 def make_oracle_potential(O, name, D):
+    if name == "c3":
+        X, y = make_logistic_data(D, CONFIGS["c3"]["N"])
+        return O.Logistic(X, y, 1.0)
+    if name == "c4":
+        B = D // 3
+        return O.NBody(np.ones(B) / B, 1.0, 0.05)
     if name == "c2":
         return O.DenseGaussian(make_precision(D))
     if name.startswith("c5"):
@@ -181,7 +209,7 @@ def run_reference_arm(args, cfg, rank):
     if rank != 0:
         return
     name = args.config
-    sample = min(cfg["P"], 1 << 14 if name == "c2" else 1 << 17)
+    sample = min(cfg["P"], {"c2": 1 << 14, "c3": 64, "c4": 1}.get(name, 1 << 17))
     rng_iters = args.warmup + args.steps
     rate, times = cpu_port_rate(name, cfg, sample, rng_iters)
     times = times[args.warmup:]
@@ -370,6 +398,7 @@ def main():
         info = ctx.device_info()
         nominal_fp32 = info["sm_count"] * 128 * 2 * info["sm_clock_mhz"] * 1e6 / 1e12
         dense_tc = args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1"
+        logi_tc = args.config == "c3" and os.environ.get("EHMC_LOGISTIC_PRECISION", "bf16") == "bf16"
         compute_bound = ach_tf / fp32_peak > ach_gbs / hbm_peak
         if dense_tc:
             # the gradient GEMM runs on tcgen05 (kind::tf32, 3 split passes): tensor-pipe roofline against
@@ -387,6 +416,13 @@ def main():
                     "note": "algorithmic fp32 flops (2 D^2 + 7 D per particle-step) over the measured bf16 peak; "
                             "3xTF32 executes 3.49x those flops at the tf32 (half) rate, i.e. the tensor pipe is "
                             "busy ~frac*2*3.49 of the time"}
+        elif logi_tc:
+            tpeak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+            roof = {"bound": "tensor", "achieved": ach_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_tf / tpeak,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside "
+                    "a long step)", "flops_per_unit": fl, "units_per_launch": Pl * L,
+                    "note": "bf16 tcgen05 GEMM chain (X theta^T -> sigmoid-residual -> R^T X); kernel_ms is the whole "
+                            "iteration (L+1 gradient launches + kick/drift launches)"}
         elif compute_bound:
             roof = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": ach_tf / fp32_peak, "traffic": None,
@@ -402,7 +438,7 @@ def main():
                          "fp32_frac": ach_tf / fp32_peak}
         cpu = None
         if not args.no_cpu_baseline:
-            sample = min(P, 1 << 14 if args.config == "c2" else 1 << 17)
+            sample = min(P, {"c2": 1 << 14, "c3": 64, "c4": 1}.get(args.config, 1 << 17))
             rate, times = cpu_port_rate(args.config, cfg, sample, 3)
             cpu = {"value": rate, "unit": "particle-leapfrog-steps/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{sample} of {P} particles x 3 iterations, median (NumPy float64 oracle port, "
@@ -410,7 +446,8 @@ def main():
         line = {
             "metric": "particle-leapfrog-steps/sec", "value": value, "unit": "particle-leapfrog-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core split, fp32 accumulate)" if (args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1") else "f32",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": ("f32 (3xTF32 tensor-core split, fp32 accumulate)" if (args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1")
+                      else "f32 state, bf16 tensor-core gradient GEMMs (fp32 accumulate)" if (args.config == "c3" and os.environ.get("EHMC_LOGISTIC_PRECISION", "bf16") == "bf16") else "f32"),
             "data": "synthetic",
             "config": {"workload": cfg["desc"], "D": D, "P": P, "L": L, "h": h, "particles_per_gpu": Pl,
                        "rng": "philox in-kernel", "l2": "inputs_exceed_l2" if D * Pl * 4 > 126e6 else "resident",

@@ -344,7 +344,7 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       break;
     }
     case EHMC_FAMILY_LOGISTIC: {
-      if (nparams != 2 || nscalars != 1) { rc = fail(EHMC_ERR_INVALID, "logistic: params = {X[N,D], y[N]}, scalars = {priorScale}"); break; }
+      if (nparams != 2 || nscalars < 1 || nscalars > 2) { rc = fail(EHMC_ERR_INVALID, "logistic: params = {X[N,D], y[N]}, scalars = {priorScale, useTensorCores?}"); break; }
       rc = fetch_param(params[0], "X", 2, &p->hp0, &v);
       if (rc) break;
       p->N = (int)v.shape[0];
@@ -356,6 +356,37 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       if (!(scalars[0] > 0)) { rc = fail(EHMC_ERR_INVALID, "logistic: priorScale must be > 0"); break; }
       rc = upload_bits(p->bits, p->hp0, &p->d0);
       if (rc == EHMC_OK) rc = upload_bits(p->bits, p->hp1, &p->d1);
+      p->use_tc = (nscalars == 2 && scalars[1] != 0.0) ? 1 : 0;
+      if (rc == EHMC_OK && p->use_tc) {
+        if (p->bits != 32) { rc = fail(EHMC_ERR_INVALID, "logistic: the tensor-core path needs float32 state"); break; }
+        // bf16 chunks of 128 data rows in the canonical UMMA layout [DP/8][128][8] + y[128] (float)
+        const int D = p->D, N = p->N, DP = (D + 15) / 16 * 16, NB = 128, NC = (N + NB - 1) / NB;
+        const size_t cb = (size_t)DP * NB * 2 + NB * 4;
+        std::vector<unsigned char> buf(cb * NC, 0);
+        auto bf16 = [](float f) -> uint16_t {
+          uint32_t b;
+          memcpy(&b, &f, 4);
+          b += 0x7FFFu + ((b >> 16) & 1u);  // round to nearest even
+          return (uint16_t)(b >> 16);
+        };
+        for (int c = 0; c < NC; ++c) {
+          uint16_t* xs = reinterpret_cast<uint16_t*>(buf.data() + cb * c);
+          float* ys = reinterpret_cast<float*>(buf.data() + cb * c + (size_t)DP * NB * 2);
+          for (int r = 0; r < NB; ++r) {
+            const int n = c * NB + r;
+            ys[r] = n < N ? (float)p->hp1[n] : 0.5f;
+            if (n >= N) continue;
+            for (int d = 0; d < D; ++d)
+              xs[((size_t)(d / 8) * NB + r) * 8 + (d % 8)] = bf16((float)p->hp0[(size_t)n * D + d]);
+          }
+        }
+        if (cudaMalloc(&p->d6, buf.size()) != cudaSuccess) { rc = fail(EHMC_ERR_NOMEM, "cudaMalloc(%zu) failed", buf.size()); break; }
+        if (cudaMemcpy(p->d6, buf.data(), buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(EHMC_ERR_CUDA, "upload of the packed X failed"); break; }
+        p->lt_nc = NC;
+        p->lt_dp = DP;
+        p->lt_npad = NC * NB - N;
+        p->lt_chunk_bytes = (unsigned)cb;
+      }
       break;
     }
     default:
@@ -423,6 +454,7 @@ extern "C" int ehmc_potential_destroy(ehmc_potential* p) {
   if (p->d3) cudaFree(p->d3);
   if (p->d4) cudaFree(p->d4);
   if (p->d5) cudaFree(p->d5);
+  if (p->d6) cudaFree(p->d6);
   delete p;
   return EHMC_OK;
 }

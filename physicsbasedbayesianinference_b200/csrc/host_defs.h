@@ -74,6 +74,10 @@ struct ehmc_potential {
   int tc_nch = 0;      // 16-column chunks of the tensor-core path (0 = not eligible)
   int tc_kp = 0;       // K padded to a multiple of 8
   int TN = 0;          // dense tile selection
+  void* d6 = nullptr;  // logistic tensor-core path: packed bf16 X chunks + y
+  int lt_nc = 0, lt_dp = 0, lt_npad = 0;
+  unsigned lt_chunk_bytes = 0;
+  int use_tc = 0;      // logistic: 1 = bf16 tensor-core gradient (scalars[1])
   int B = 0;           // nbody: bodies per particle
   int N = 0;           // logistic: data rows
 };
@@ -115,6 +119,9 @@ int colstats(ehmc_ctx* c, const T* q, long long q_ld, long long P, int D, double
 template <typename T>
 int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st,
                     int slot);
+// bf16 tensor-core gradient (float32 state only)
+int logistic_grad_tc(ehmc_ctx* c, const ehmc_potential* p, const float* theta, long long t_ld, long long P, float* g,
+                     long long g_ld, float* e, cudaStream_t st);
 template <typename T>
 int eval_logistic(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
                   long long g_ld, cudaStream_t st);

@@ -19,6 +19,9 @@ static LogisticArgs<T> logistic_args(const ehmc_potential* p) {
 template <typename T>
 static int logistic_grad(ehmc_ctx* c, const ehmc_potential* p, const T* theta, long long t_ld, long long P, T* g,
                          long long g_ld, T* e, cudaStream_t st) {
+  if constexpr (sizeof(T) == 4) {
+    if (p->use_tc && p->d6 != nullptr) return logistic_grad_tc(c, p, theta, t_ld, P, g, g_ld, e, st);
+  }
   constexpr int PT = LogiTile<T>::PT;
   const int D = p->D, DS = (D + 3) & ~3;
   if (D > LG_DMAX) return fail(EHMC_ERR_UNSUPPORTED, "logistic: D = %d > %d", D, LG_DMAX);

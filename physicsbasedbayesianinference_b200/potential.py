@@ -162,7 +162,13 @@ class LogisticPotential(Potential):
 
     family = _lib.FAMILY_LOGISTIC
 
-    def __init__(self, X, y, priorScale=1.0):
+    def __init__(self, X, y, priorScale=1.0, precision="fp32"):
+        """precision="fp32": exact CUDA-core gradient (parity path).  precision="bf16": the
+        tcgen05 tensor-core GEMM chain (X and theta rounded to bf16, fp32 accumulation;
+        float32 ensembles only) -- the throughput path of BASELINE config 3."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
         self.X = np.ascontiguousarray(X, dtype=np.float64)
         self.y = np.ascontiguousarray(y, dtype=np.float64)
         if self.X.ndim != 2 or self.y.shape != (self.X.shape[0],):
@@ -174,7 +180,7 @@ class LogisticPotential(Potential):
         return [self.X, self.y]
 
     def _scalars(self):
-        return [self.priorScale]
+        return [self.priorScale, 1.0 if self.precision == "bf16" else 0.0]
 
 
 def _descriptor(potential):

@@ -796,3 +796,61 @@ def test_run_adaptation_and_moments(E):
     assert np.all(np.abs(r2["mean"].numpy()) < 0.05)
     m, scaled = E.diagnostics.ess_min_over_dims(r2["trace"], numParticlesTotal=P)
     assert 0 < m <= 128 * 120 * 3 and scaled == pytest.approx(m * P / 128)
+
+
+# ---------------------------------------------------------------------------
+# logistic regression on the tensor cores (bf16 GEMM chain, tcgen05)
+# ---------------------------------------------------------------------------
+def _bf16_round(a):
+    b = np.asarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    b = (b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000
+    return b.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("N,D,P", [(1000, 256, 300), (128, 16, 128), (700, 40, 77), (5000, 256, 1024)])
+def test_logistic_tensor_core_gradient(E, N, D, P):
+    """k_logistic_tc vs the float64 oracle evaluated on the SAME bf16-rounded X and theta (tight:
+    only fp32 accumulation, tanh.approx and the bf16 rounding of the residual differ) and vs the
+    exact oracle (loose: the bf16 input rounding itself)."""
+    rng = np.random.RandomState(N + D)
+    X = rng.standard_normal((N, D)) / np.sqrt(D)
+    y = (rng.uniform(size=N) < 0.5).astype(np.float64)
+    th = rng.standard_normal((D, P))
+    pe = E.LogisticPotential(X, y, 2.0, precision="bf16")
+    g = pe.gradient(th.astype(np.float32))
+    u = pe(th.astype(np.float32))
+    po_b = O.Logistic(_bf16_round(X), y, 2.0)
+    thb = _bf16_round(th)
+    # prior term uses the unrounded theta in the kernel
+    g_ref = po_b.grad(thb) - thb / 4.0 + th / 4.0
+    u_ref = po_b.energy(thb) - 0.5 * np.sum(thb * thb, 0) / 4.0 + 0.5 * np.sum(th * th, 0) / 4.0
+    assert rel_err(g, g_ref) < 5e-3  # residual rounded to bf16 before the second GEMM
+    assert rel_err(u, u_ref) < 1e-4
+    po = O.Logistic(X, y, 2.0)
+    assert rel_err(g, po.grad(th)) < 2e-2
+    assert rel_err(u, po.energy(th)) < 2e-3
+
+
+def test_logistic_tensor_core_hmc_iteration(E):
+    """A whole HMC iteration driven by the tensor-core gradient stays close to the exact one."""
+    import torch
+
+    N, D, P, L, h = 2048, 256, 256, 10, 0.02
+    rng = np.random.RandomState(9)
+    X = rng.standard_normal((N, D)) / np.sqrt(D)
+    y = (rng.uniform(size=N) < 0.5).astype(np.float64)
+    q0 = rng.standard_normal((D, P))
+    z = rng.standard_normal((D, P))
+    u = rng.uniform(size=P)
+    qr, pr, accr, oh, nh = O.hmc_iter(q0, z, u, np.ones(P), 1 / KB, h, L, O.Logistic(X, y, 1.0))
+    ens = E.Ensemble(D, P, dtype=np.float32, device="cuda")
+    ens.q.copy_(torch.tensor(q0, dtype=torch.float32))
+    hmc = E.HMC(ens, L * h + 1e-9, h, None, potential=E.LogisticPotential(X, y, 1.0, precision="bf16"))
+    acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+    hmc.step(1 / KB, accept=acc, z=torch.tensor(z, dtype=torch.float32, device="cuda"),
+             u=torch.tensor(u, dtype=torch.float32, device="cuda"))
+    torch.cuda.synchronize()
+    a = acc.cpu().numpy().astype(bool)
+    same = a == accr
+    assert same.mean() > 0.9
+    assert rel_err(ens.q.cpu().numpy()[:, same], qr[:, same]) < 2e-3
