@@ -289,7 +289,7 @@ def main():
     hmc = E.HMC(ens, L * h + 1e-9, h, None, potential=pot, seed=SEED, bugCompat=False)
     assert hmc.integrator.numSteps == L
 
-    fp32_peak = ctx.measure_fp32_peak(300.0) if rank == 0 else None
+    fp32_peak = ctx.measure_fp32_peak(60.0) if rank == 0 else None
 
     def barrier():
         if world > 1:
@@ -433,6 +433,16 @@ def main():
             roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                     "bytes_per_unit": bytes_per_particle_iter(D) / L, "units_per_launch": Pl * L}
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.config[:2])
+            if tr and world == 1:
+                roof["traffic"] = tr["dram_bytes_per_launch"]
+                roof["traffic_source"] = tr["source"]
+                roof["ncu_tensor_pipe_active_pct"] = tr.get("tensor_pipe_active_pct")
+                roof["ncu_issue_active_pct"] = tr.get("issue_active_pct")
+        except (OSError, ValueError):
+            pass
+        roof["algorithmic_bytes_per_launch"] = by
         roof["kernel_ms"] = kern_ms
         roof["other"] = {"hbm_GBps": ach_gbs, "hbm_frac": ach_gbs / hbm_peak, "fp32_TFLOPs": ach_tf,
                          "fp32_frac": ach_tf / fp32_peak}

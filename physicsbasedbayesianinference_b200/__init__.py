@@ -16,7 +16,7 @@ from .ensemble import Ensemble, boltzmannConst  # noqa: F401
 from .integrator import Integrator, Leapfrog, StormerVerlet  # noqa: F401
 from .HMC import HMC, GaussianDensity  # noqa: F401
 from . import potential  # noqa: F401
-from . import diagnostics, parallel  # noqa: F401
+from . import diagnostics, io, numpyro_adapter, parallel  # noqa: F401
 from .potential import (  # noqa: F401
     FunnelPotential,
     GaussianPotential,

@@ -55,6 +55,24 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// NW independent Philox blocks advanced in lock step: the rounds of different blocks interleave,
+// which hides the multiply latency of the (strictly serial) rounds of one block.
+template <int NW>
+__device__ __forceinline__ void philox4x32_10_multi(uint4 (&c)[NW], uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const uint32_t hi0 = __umulhi(M0, c[w].x), lo0 = M0 * c[w].x;
+      const uint32_t hi1 = __umulhi(M1, c[w].z), lo1 = M1 * c[w].z;
+      c[w] = make_uint4(hi1 ^ c[w].y ^ k.x, lo1, hi0 ^ c[w].w ^ k.y, lo0);
+    }
+    k.x += W0;
+    k.y += W1;
+  }
+}
+
 #define EHMC_UNIFORM_BLOCK 0xFFFFFFFFu
 
 struct PhiloxKey {
@@ -78,7 +96,19 @@ template <>
 struct NormalBlock<float> {
   static constexpr int N = 4;
   static __device__ __forceinline__ void draw(const PhiloxKey& K, u64 pid, uint32_t blk, float* z) {
-    const uint4 r = K.block(pid, blk);
+    transform(K.block(pid, blk), z);
+  }
+  // NW consecutive blocks blk .. blk+NW-1 -> z[4*NW]
+  template <int NW>
+  static __device__ __forceinline__ void draw_multi(const PhiloxKey& K, u64 pid, uint32_t blk, float* z) {
+    uint4 c[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) c[w] = make_uint4((uint32_t)pid, (uint32_t)(pid >> 32), blk + w, K.it);
+    philox4x32_10_multi<NW>(c, K.key);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) transform(c[w], z + 4 * w);
+  }
+  static __device__ __forceinline__ void transform(const uint4 r, float* z) {
     const float s = 5.9604644775390625e-8f;  // 2^-24
     const float u1a = (float)((r.x >> 8) + 1u) * s, u2a = (float)(r.y >> 8) * s;
     const float u1b = (float)((r.z >> 8) + 1u) * s, u2b = (float)(r.w >> 8) * s;

@@ -71,7 +71,7 @@ template <int K8>
 struct Tc2Shape {
   static constexpr int KP = 8 * K8, K4 = 2 * K8;
   static constexpr int NP = (KP + 15) / 16 * 16;
-  static constexpr size_t smem_bytes() { return (size_t)K4 * (2 * TC_M + 2 * NP) * 16 + 64; }
+  static constexpr size_t smem_bytes() { return (size_t)K4 * (2 * TC_M + 2 * NP) * 16 + (size_t)KP * 4 + 64; }
 };
 
 // ---- software-pipelined epilogue ---------------------------------------------------------
@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_dense_tc2(const IterArgs<flo
   float4* Alo_all = reinterpret_cast<float4*>(tc2_smem_raw);      // [2][K4][128]
   float4* Bhi = Alo_all + (size_t)2 * K4 * TC_M;                  // [K4][NP]
   float4* Blo = Bhi + (size_t)K4 * NP;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(Blo + (size_t)K4 * NP);  // [2]
+  float* mus = reinterpret_cast<float*>(Blo + (size_t)K4 * NP);           // [KP] mean
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(mus + KP);                 // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -202,10 +203,18 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_dense_tc2(const IterArgs<flo
       Bhi[i] = s0[i];
       Blo[i] = s1[i];
     }
+    if (tid < KP) mus[tid] = pa.mu[tid];
   }
+  const bool prof = pa.prof != nullptr && blockIdx.x == 0 && tid == 0;
+  int pi = 0;
+  auto stamp = [&]() {
+    if (prof && pi < 62) pa.prof[pi++] = clock64();
+  };
+  stamp();  // after TMEM alloc issue + Lambda copy issue
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  stamp();  // after the first CTA barrier
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
   const uint32_t t_d = tmem_base + (uint32_t)(tile * 256) + lane_off;        // this row's accumulator
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_dense_tc2(const IterArgs<flo
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int d = 8 * c + 4 * t + e;
-          const float x = (d < D && valid) ? v[d] - pa.mu[d] : 0.f;
+          const float x = (d < D && valid) ? v[d] - mus[d] : 0.f;
           hh[4 * t + e] = __float_as_uint(x);
           lo4[e] = x - tf32_trunc(x);
         }
@@ -237,6 +246,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_dense_tc2(const IterArgs<flo
       }
       tmem_st8(t_a + (uint32_t)(8 * c), hh);
     }
+    stamp();  // positions loaded, x operands stored
     // momenta
     if (!hmc) {
 #pragma unroll
@@ -245,13 +255,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_dense_tc2(const IterArgs<flo
 #pragma unroll
       for (int d = 0; d < KP; ++d) v[d] = (d < D && valid) ? A.z[d * A.z_ld + pc] * pstd : 0.f;
     } else {
+      // 4 Philox blocks (16 normals) at a time so their serial rounds interleave; K4 = 2*K8 blocks
       const PhiloxKey K(A.seed, A.iter);
+      constexpr int NW = 4;
 #pragma unroll
-      for (int k4 = 0; k4 < K4; ++k4) {
-        float zz[4] = {0.f, 0.f, 0.f, 0.f};
-        if (k4 * 4 < D) NormalBlock<float>::draw(K, A.offset + (u64)pc, (uint32_t)k4, zz);
+      for (int k4 = 0; k4 < K4; k4 += NW) {
+        float zz[4 * NW];
+        if (k4 + NW <= K4) {
+          NormalBlock<float>::draw_multi<NW>(K, A.offset + (u64)pc, (uint32_t)k4, zz);
+        } else {
+          NormalBlock<float>::draw_multi<2>(K, A.offset + (u64)pc, (uint32_t)k4, zz);  // K4 is even
+        }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[4 * k4 + e] = (4 * k4 + e < D && valid) ? zz[e] * pstd : 0.f;
+        for (int e = 0; e < 4 * NW; ++e)
+          if (4 * k4 + e < KP) v[4 * k4 + e] = (4 * k4 + e < D && valid) ? zz[e] * pstd : 0.f;
       }
     }
 #pragma unroll
@@ -261,6 +278,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_dense_tc2(const IterArgs<flo
     }
     tmem_wait_st();
     K0 *= 0.5f * inv_m;
+    stamp();  // momenta drawn
   }
 
   const int L = A.L;
@@ -273,11 +291,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_dense_tc2(const IterArgs<flo
   const float ckh = 0.5f * h * inv_m, ckf = h * inv_m;
   float U0 = 0.f, U1 = 0.f;
 
-  const bool prof = pa.prof != nullptr && blockIdx.x == 0 && tid == 0;
-  int pi = 0;
-  auto stamp = [&]() {
-    if (prof && pi < 64) pa.prof[pi++] = clock64();
-  };
   stamp();
   for (int ev = 0; ev <= L; ++ev) {
     // the tile's operands (x_hi in TMEM, x_lo in smem) are complete once all 128 rows arrive
@@ -341,7 +354,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_dense_tc2(const IterArgs<flo
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int d = 16 * b + e;
-        if (d < D && wr) A.q[d * A.q_ld + pc] = __uint_as_float(hh[e]) + pa.mu[d];
+        if (d < D && wr) A.q[d * A.q_ld + pc] = __uint_as_float(hh[e]) + mus[d];
       }
     }
     if constexpr (K8 % 2 == 1) {
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) k_dense_tc2(const IterArgs<flo
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int d = 8 * (K8 - 1) + e;
-        if (d < D && wr) A.q[d * A.q_ld + pc] = __uint_as_float(hh[e]) + pa.mu[d];
+        if (d < D && wr) A.q[d * A.q_ld + pc] = __uint_as_float(hh[e]) + mus[d];
       }
     }
     if (hmc && valid && A.accept != nullptr) A.accept[pc] = rej ? 0 : 1;

@@ -149,3 +149,55 @@ def test_flat_module_shims():
     out = subprocess.run(["python", "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0, out.stderr
     assert "(2, 3) 0" in out.stdout
+
+
+# ---- section 8f rows: input files, checkpoints, model adapter (host logic) -------------------
+def test_read_nbody_input_reference_files(tmp_path):
+    """ReadInput format of samples/NBody/MiscFunctions.py:8-43 (copy of pl3.txt's numbers)."""
+    from physicsbasedbayesianinference_b200 import io
+
+    txt = (" 3  220.0       0.1     \n0.99990\n0.00001\n0.00009\n0.0      0.0       0.0\n1.0      0.0       0.0\n"
+           "-2.25    0.0       0.0\n0.0      0.0       0.0     \n0.0     -1.0       0.0\n0.0      0.6666666    0.0\n")
+    f = tmp_path / "pl3.txt"
+    f.write_text(txt)
+    N, tmax, dt, M, PS = io.readNBodyInput(str(f))
+    assert (N, tmax, dt) == (3, 220.0, 0.1)
+    assert np.allclose(M, [0.9999, 0.00001, 0.00009])
+    assert np.allclose(PS[:, 0, 0], [0.0, 1.0, -2.25]) and np.allclose(PS[:, 1, 1], [0.0, -1.0, 0.6666666])
+    q, p = io.nbodyInputToEnsembleColumn(M, PS)
+    assert q.shape == (9,) and np.allclose(q[:3], [0.0, 1.0, -2.25]) and np.allclose(p[3:6], M * PS[:, 1, 1])
+    f.write_text(" 3 1.0 0.1\n1\n2\n")
+    with pytest.raises(ValueError):
+        io.readNBodyInput(str(f))
+
+
+def test_checkpoint_roundtrip_host(tmp_path):
+    from physicsbasedbayesianinference_b200 import io
+
+    ens = E.Ensemble(2, 5)
+    ens.q[:] = np.arange(10).reshape(2, 5)
+    ens.mass = np.linspace(1, 2, 5)
+    hmc = E.HMC(ens, 1.0, 0.1, None, potential=E.HarmonicPotential([1.0, 2.0]), rng="philox", seed=77)
+    hmc.iteration = 41
+    io.saveCheckpoint(str(tmp_path / "ck"), hmc)
+    ens2 = E.Ensemble(2, 5)
+    hmc2 = E.HMC(ens2, 1.0, 0.25, None, potential=E.HarmonicPotential([1.0, 2.0]), rng="philox", seed=1)
+    io.loadCheckpoint(str(tmp_path / "ck"), hmc2)
+    assert np.array_equal(ens2.q, ens.q) and np.array_equal(ens2.mass, ens.mass)
+    assert (hmc2.seed, hmc2.iteration, hmc2.stepSize, hmc2.integrator.numSteps) == (77, 41, 0.1, 10)
+
+
+def test_model_spec_adapter():
+    from physicsbasedbayesianinference_b200 import numpyro_adapter as A
+
+    p = A.potentialFromSpec(dict(family="normal_iid", scale=[1.0, 0.5]))
+    assert isinstance(p, E.HarmonicPotential) and np.allclose(p.springConsts, [1.0, 4.0])
+    p = A.potentialFromSpec(dict(family="mvn", mean=[5, 5], cov=[[4, -3], [-3, 4]]))
+    assert isinstance(p, E.GaussianPotential) and np.allclose(p.precision @ [[4, -3], [-3, 4]], np.eye(2))
+    assert isinstance(A.potentialFromSpec(dict(family="funnel", numDimensions=10)), E.FunnelPotential)
+    X = np.ones((4, 3))
+    assert A.potentialFromSpec(dict(family="logistic_regression", X=X, y=np.ones(4))).numDimensions == 3
+    with pytest.raises(NotImplementedError):
+        A.potentialFromSpec(dict(family="eight_schools"))
+    with pytest.raises((ImportError, NotImplementedError)):
+        A.potentialFromNumpyroModel(lambda: None)

@@ -854,3 +854,26 @@ def test_logistic_tensor_core_hmc_iteration(E):
     same = a == accr
     assert same.mean() > 0.9
     assert rel_err(ens.q.cpu().numpy()[:, same], qr[:, same]) < 2e-3
+
+
+def test_checkpoint_resume_is_bit_exact(E, tmp_path):
+    """Philox is counter based: a run resumed from a checkpoint equals the uninterrupted run."""
+    import torch
+
+    D, P = 10, 4096
+
+    def make():
+        ens = E.Ensemble(D, P, dtype=np.float32, device="cuda", seed=3)
+        ens.setPosition(1.0)
+        return ens, E.HMC(ens, 0.4, 0.05, None, potential=E.FunnelPotential(D, 3.0), seed=3)
+
+    ens_a, hmc_a = make()
+    hmc_a.run(6, 1 / KB, collectStats=False)
+    E.io.saveCheckpoint(str(tmp_path / "ck"), hmc_a)
+    hmc_a.run(5, 1 / KB, collectStats=False)
+    ens_b, hmc_b = make()
+    ens_b.q.zero_()
+    E.io.loadCheckpoint(str(tmp_path / "ck"), hmc_b)
+    hmc_b.run(5, 1 / KB, collectStats=False)
+    torch.cuda.synchronize()
+    assert torch.equal(ens_a.q, ens_b.q)
