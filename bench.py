@@ -401,21 +401,27 @@ def main():
         logi_tc = args.config == "c3" and os.environ.get("EHMC_LOGISTIC_PRECISION", "bf16") == "bf16"
         compute_bound = ach_tf / fp32_peak > ach_gbs / hbm_peak
         if dense_tc:
-            # the gradient GEMM runs on tcgen05 (kind::tf32, 3 split passes): tensor-pipe roofline against
-            # the measured dense bf16 peak.  Executed tensor flops per algorithmic flop:
-            # 3 passes x (104*112)/(100*100) padding; tf32 runs at half the bf16 rate, so the ceiling of
-            # this formulation is peak / (2*3*1.165) in algorithmic TFLOP/s.
+            # the gradient GEMM runs on tcgen05 as a 3-pass split (float32 accuracy from 11-bit operands):
+            # tensor-pipe roofline against the measured dense bf16 peak.  Executed tensor flops per
+            # algorithmic flop = 3 passes x padding; kind::f16 (default kernel k_dense_tc3) runs at the
+            # bf16 rate, kind::tf32 (k_dense_tc2, EHMC_DENSE_PATH=3) at half of it.
             tpeak = peaks.get("bf16_tflops", 1590.0)
-            exec_factor = 3.0 * (104.0 * 112.0) / (D * D) if D == 100 else 3.0
+            tf32 = os.environ.get("EHMC_DENSE_PATH", "0") in ("2", "3")
+            kp = (D + 7) // 8 * 8 if tf32 else (D + 15) // 16 * 16
+            npad = (D + 15) // 16 * 16
+            exec_factor = 3.0 * kp * npad / (D * D)
+            rate = 0.5 if tf32 else 1.0
             roof = {"bound": "tensor", "achieved": ach_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_tf / tpeak,
                     "traffic": None,
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback"),
                     "flops_per_unit": fl, "units_per_launch": Pl * L,
-                    "executed_tensor_tflops_tf32": ach_tf * exec_factor,
-                    "formulation_ceiling_frac": 1.0 / (2.0 * exec_factor),
-                    "note": "algorithmic fp32 flops (2 D^2 + 7 D per particle-step) over the measured bf16 peak; "
-                            "3xTF32 executes 3.49x those flops at the tf32 (half) rate, i.e. the tensor pipe is "
-                            "busy ~frac*2*3.49 of the time"}
+                    "executed_tensor_tflops": ach_tf * exec_factor,
+                    "tensor_pipe_busy_frac_est": ach_tf * exec_factor / (rate * tpeak),
+                    "formulation_ceiling_frac": rate / exec_factor,
+                    "note": "algorithmic fp32 flops (2 D^2 + 7 D per particle-step) over the measured bf16 peak; the "
+                            f"{'3xTF32' if tf32 else '3xFP16'} split executes {exec_factor:.2f}x those flops (3 passes x "
+                            f"padding to K={kp}, N={npad}) at {'half the' if tf32 else 'the'} bf16 rate, so `frac` cannot "
+                            "exceed formulation_ceiling_frac; tensor_pipe_busy_frac_est = frac / ceiling"}
         elif logi_tc:
             tpeak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
             roof = {"bound": "tensor", "achieved": ach_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_tf / tpeak,
@@ -456,7 +462,9 @@ def main():
         line = {
             "metric": "particle-leapfrog-steps/sec", "value": value, "unit": "particle-leapfrog-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": ("f32 (3xTF32 tensor-core split, fp32 accumulate)" if (args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1")
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": (("f32 (3xTF32 tensor-core split, fp32 accumulate)" if os.environ.get("EHMC_DENSE_PATH", "0") in ("2", "3")
+                       else "f32 (3xFP16 tensor-core split, fp32 accumulate)")
+                      if (args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1")
                       else "f32 state, bf16 tensor-core gradient GEMMs (fp32 accumulate)" if (args.config == "c3" and os.environ.get("EHMC_LOGISTIC_PRECISION", "bf16") == "bf16") else "f32"),
             "data": "synthetic",
             "config": {"workload": cfg["desc"], "D": D, "P": P, "L": L, "h": h, "particles_per_gpu": Pl,

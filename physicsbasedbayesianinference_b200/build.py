@@ -27,18 +27,29 @@ def _sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def _stale():
-    if not os.path.isfile(OUT):
+def _deps(path, seen=None):
+    """The file plus every header it includes with quotes, recursively."""
+    import re
+
+    seen = set() if seen is None else seen
+    if path in seen or not os.path.isfile(path):
+        return seen
+    seen.add(path)
+    with open(path) as f:
+        for inc in re.findall(r'^\s*#include\s+"([^"]+)"', f.read(), flags=re.M):
+            _deps(os.path.normpath(os.path.join(os.path.dirname(path), inc)), seen)
+    return seen
+
+
+def _newer(target, sources):
+    if not os.path.isfile(target):
         return True
-    t = os.path.getmtime(OUT)
-    deps = glob.glob(os.path.join(CSRC, "*")) + glob.glob(os.path.join(INCLUDE, "*.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
 
 
 def build_library(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library (parallel per file)."""
-    if not force and not _stale():
-        return OUT
+    """Compile the .cu files under csrc/ that changed (parallel per file) and link one shared library."""
     nvcc = os.environ.get("NVCC", "nvcc")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -47,6 +58,8 @@ def build_library(force=False, verbose=False):
     for src in _sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
+        if not force and not _newer(obj, _deps(src) | {os.path.abspath(__file__)}):
+            continue
         cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -57,8 +70,9 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs]
-    subprocess.run(cmd, check=True)
+    if procs or force or _newer(OUT, objs):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs]
+        subprocess.run(cmd, check=True)
     return OUT
 
 

@@ -1,5 +1,6 @@
 // C-ABI of the ehmc engine (include/ehmc.h): argument validation, potential
 // packing, kernel dispatch, host-buffer staging.  No torch types, no exceptions.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -180,7 +181,7 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
     if (value != 1 && value != 2) return fail(EHMC_ERR_INVALID, "dense_occupancy must be 1 or 2");
     c->dense_occupancy = (int)value;
   } else if (!strcmp(name, "dense_path")) {
-    if (value != 0 && value != 1 && value != 2 && value != 3) return fail(EHMC_ERR_INVALID, "dense_path must be 0..3");
+    if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4) return fail(EHMC_ERR_INVALID, "dense_path must be 0..4");
     c->dense_path = (int)value;
   } else if (!strcmp(name, "tc_prof")) {
     c->tc_prof = (int)value;
@@ -266,6 +267,13 @@ static int upload(const std::vector<double>& h, void** dptr) {
   if (h.empty()) return EHMC_OK;
   CUDA_TRY(cudaMalloc(dptr, sizeof(T) * t.size()));
   CUDA_TRY(cudaMemcpy(*dptr, t.data(), sizeof(T) * t.size(), cudaMemcpyHostToDevice));
+  return EHMC_OK;
+}
+
+static int upload_raw(const void* src, size_t bytes, void** dptr) {
+  *dptr = nullptr;
+  CUDA_TRY(cudaMalloc(dptr, bytes));
+  CUDA_TRY(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
   return EHMC_OK;
 }
 
@@ -433,6 +441,34 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
         p->tc_nch = NCH;
         p->tc_kp = KP;
       }
+      if (rc == EHMC_OK && p->bits == 32 && D <= 128) {
+        // 3xFP16 tensor-core operands (k_dense_tc3): Lambda scaled by a power of two so that max |Lambda| lands in
+        // [2^13, 2^14), hi = rn16, lo = rn16(remainder); canonical K-major no-swizzle layout [KP/8][NP][8].
+        const int C8 = (D + 7) / 8, KP = (C8 + 1) / 2 * 16, NP = KP, KCH = KP / 8;
+        double amax = 0.0;
+        for (size_t i = 0; i < (size_t)D * D; ++i) amax = std::max(amax, std::fabs((double)(float)p->hp0[i]));
+        int ex = 0;
+        if (amax > 0 && std::isfinite(amax)) std::frexp(amax, &ex);  // amax = f * 2^ex, f in [0.5, 1)
+        const int sh = std::max(-100, std::min(100, 14 - ex));
+        const double lscale = std::ldexp(1.0, sh);
+        std::vector<__half> bhi((size_t)KCH * NP * 8, __float2half_rn(0.f)), blo(bhi.size(), __float2half_rn(0.f));
+        for (int n = 0; n < D; ++n)
+          for (int k = 0; k < D; ++k) {
+            const float x = (float)((double)(float)p->hp0[(size_t)n * D + k] * lscale);
+            const __half hi = __float2half_rn(x);
+            const __half lo = __float2half_rn(x - __half2float(hi));
+            const size_t o = ((size_t)(k / 8) * NP + n) * 8 + (k % 8);
+            bhi[o] = hi;
+            blo[o] = lo;
+          }
+        std::vector<float> mu3(128, 0.f);
+        for (int d = 0; d < D; ++d) mu3[d] = (float)p->hp1[d];
+        rc = upload_raw(bhi.data(), sizeof(__half) * bhi.size(), &p->d7);
+        if (rc == EHMC_OK) rc = upload_raw(blo.data(), sizeof(__half) * blo.size(), &p->d8);
+        if (rc == EHMC_OK) rc = upload_raw(mu3.data(), sizeof(float) * mu3.size(), &p->d9);
+        p->tc3_c8 = C8;
+        p->tc3_inv_lscale = (float)std::ldexp(1.0, -sh);
+      }
     } else if (rc == EHMC_OK) {
       rc = upload_bits(p->bits, p->hp1, &p->d1);
     }
@@ -455,6 +491,9 @@ extern "C" int ehmc_potential_destroy(ehmc_potential* p) {
   if (p->d4) cudaFree(p->d4);
   if (p->d5) cudaFree(p->d5);
   if (p->d6) cudaFree(p->d6);
+  if (p->d7) cudaFree(p->d7);
+  if (p->d8) cudaFree(p->d8);
+  if (p->d9) cudaFree(p->d9);
   delete p;
   return EHMC_OK;
 }
@@ -467,14 +506,20 @@ static bool per_particle_stats(const ehmc_potential* p) {
 
 // the float32 dense family runs on the tensor cores (3xTF32) unless told otherwise
 static bool use_dense_tc(const ehmc_ctx* c, const ehmc_potential* p, int integ) {
-  return p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->bits == 32 && p->tc_nch >= 2 && integ == INTEG_LEAPFROG &&
-         c->dense_path != 1;
+  if (!(p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->bits == 32 && integ == INTEG_LEAPFROG) || c->dense_path == 1)
+    return false;
+  if (c->dense_path == 2 || c->dense_path == 3) return p->tc_nch >= 2;  // the 3xTF32 kernels (D <= 104)
+  return p->tc3_c8 >= 3;                                                // 0 (auto), 4: 3xFP16 persistent kernel
 }
 
 template <typename T>
 static long long traj_blocks(const ehmc_ctx* c, const ehmc_potential* p, long long P, int integ) {
   if (per_particle_stats(p)) return P;
-  if (use_dense_tc(c, p, integ)) return c->dense_path == 2 ? 8 * ((P + 127) / 128) : 8 * ((P + 255) / 256);
+  if (use_dense_tc(c, p, integ)) {
+    if (c->dense_path == 2) return 8 * ((P + 127) / 128);
+    if (c->dense_path == 3) return 8 * ((P + 255) / 256);
+    return 4 * ((P + 127) / 128);  // k_dense_tc3: one row per warp and 128-particle tile
+  }
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) {
     const int PT = dense_particles_per_cta<T>();
     return (P + PT - 1) / PT;
@@ -492,7 +537,7 @@ static int launch_traj(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& 
     if (use_dense_tc(c, p, integ)) return launch_dense_tc(c, p, A, hmc, st);
   }
   if (c->dense_path >= 2 && p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16 && sizeof(T) == 4)
-    return fail(EHMC_ERR_UNSUPPORTED, "dense_path = 2 (tensor cores) but this call is not eligible (D = %d, integrator %d)", p->D, integ);
+    return fail(EHMC_ERR_UNSUPPORTED, "dense_path >= 2 (tensor cores) but this call is not eligible (D = %d, integrator %d)", p->D, integ);
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) return launch_dense<T>(c, p, A, integ, hmc, st);
   return launch_small<T>(c, p, A, integ, hmc, st);
 }

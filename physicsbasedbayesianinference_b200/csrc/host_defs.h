@@ -51,7 +51,8 @@ struct ehmc_ctx {
   cudaStream_t streams[N_STAGE] = {nullptr, nullptr, nullptr};
   // tuning options (ehmc_ctx_set_option)
   int dense_occupancy = 2;        // CTAs/SM the float32 dense kernel is compiled for (1 or 2)
-  int dense_path = 0;             // 0 auto (tensor cores when eligible), 1 CUDA cores (exact fp32 FMA), 2 force TC
+  int dense_path = 0;             // 0 auto (3xFP16 tensor cores when eligible), 1 CUDA cores (exact fp32 FMA),
+                                  // 2 / 3 the 3xTF32 kernels (one tile SS / two tiles TS), 4 force 3xFP16
   long long host_chunk_bytes = 32LL << 20;
   int tc_prof = 0;                // 1: record a clock64 trace of CTA 0 into tc_prof_buf (64 x int64)
   DevBuf tc_prof_buf;
@@ -77,6 +78,11 @@ struct ehmc_potential {
   void* d6 = nullptr;  // logistic tensor-core path: packed bf16 X chunks + y
   int lt_nc = 0, lt_dp = 0, lt_npad = 0;
   unsigned lt_chunk_bytes = 0;
+  void* d7 = nullptr;  // dense float32 3xFP16 tensor-core path: Lambda_hi fp16 [KP/8][NP][8]
+  void* d8 = nullptr;  //                                       Lambda_lo
+  void* d9 = nullptr;  //                                       mu [128]
+  int tc3_c8 = 0;      // ceil(D / 8) (0 = not eligible)
+  float tc3_inv_lscale = 1.f;
   int use_tc = 0;      // logistic: 1 = bf16 tensor-core gradient (scalars[1])
   int B = 0;           // nbody: bodies per particle
   int N = 0;           // logistic: data rows
@@ -96,6 +102,8 @@ template <typename T>
 int launch_dense(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);
 // float32 3xTF32 tensor-core variant (leapfrog only)
 int launch_dense_tc(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, bool hmc, cudaStream_t st);
+// float32 3xFP16 persistent tensor-core variant (leapfrog only; the default)
+int launch_dense_tc3(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, bool hmc, cudaStream_t st);
 template <typename T>
 int dense_particles_per_cta();
 int dense_tn(int D);

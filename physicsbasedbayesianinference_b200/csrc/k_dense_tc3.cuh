@@ -1,0 +1,557 @@
+// K2-TC3: dense-precision Gaussian trajectory kernel, tensor cores, fp16 split operands,
+// persistent CTAs.
+//
+// Same trajectory as k_dense_tc2.cuh (kick-drift-kick with G = X Lambda^T re-issued L+1 times on
+// on-chip state), with two changes that together halve the time per evaluation:
+//
+//  * 3xFP16 split instead of 3xTF32.  tf32 and fp16 carry the same 11 significant bits, but
+//    tcgen05.mma kind::f16 consumes K = 16 per instruction where kind::tf32 consumes K = 8, at the
+//    same M*N/256 cycles per instruction: 3*K16 = 21 MMAs per evaluation at D = 100 instead of 39.
+//    The split is round-to-nearest:  hi = rn16(x), lo = rn16(x - hi)  ->  |x - hi - lo| <= 2^-24 |x|,
+//    i.e. the (hi, lo) pair is as accurate as the float32 it came from, so the pair IS the master
+//    copy of the row's position (no separate fp32 x anywhere).  fp16's narrow exponent range is
+//    handled by exact power-of-two scalings: Lambda by `lscale` on the host (max |Lambda| -> 2^13),
+//    each particle row by 2^e chosen in the prologue from max(|x|, h L |v|) (-> 2^7, 256x headroom);
+//    both are undone in the kick coefficient.  G ~= hi L_hi + lo L_hi + hi L_lo, fp32 accumulate.
+//  * every operand of the tile lives in TENSOR MEMORY (all three products are TS-mode MMAs):
+//        per tile (256 columns):  [0, NP) D fp32 | [NP, NP + KP/2) hi (fp16 pairs) | [.., NP + KP) lo
+//    shared memory only holds Lambda_hi / Lambda_lo (fp16, canonical K-major no-swizzle layout
+//    [KP/8][NP][8]), loaded ONCE per CTA: the kernel is persistent (grid = #SMs), each of the two
+//    4-warp groups of a CTA walks its own list of 128-particle tiles.  Tiles are dealt to CTAs in
+//    contiguous ranges and alternately to the two groups, so when the tile count per SM is odd the
+//    last tile runs alone at full tensor-pipe rate (tail = ~0.6 of a paired round, not a full one).
+//
+// Thread <-> particle row <-> TMEM lane; the row's D velocities stay in registers for the whole
+// trajectory.  One group's epilogue (tcgen05.ld G/hi/lo -> kick, drift, re-split -> tcgen05.st)
+// overlaps the other group's MMAs.
+//
+// Reference arithmetic replaced: src/integrator.py:105-120 with gradient = Lambda (q - mu),
+// src/HMC.py:106-116,168-176, src/ensemble.py:88-91.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "k_dense_tc2.cuh"
+
+namespace ehmc {
+
+constexpr int TC3_THREADS = 256;  // 2 groups x 4 warps
+
+// C8 = ceil(D / 8): 8-dim chunks the epilogue touches.  MMA K = N = KP = C8 rounded up to 16 dims.
+template <int C8>
+struct Tc3Shape {
+  static constexpr int K16 = (C8 + 1) / 2;
+  static constexpr int KP = 16 * K16;
+  static constexpr int NP = KP;
+  static constexpr int DC = 8 * C8;
+  static constexpr int KCH = KP / 8;  // 16-byte chunks along K
+  static constexpr int HI_COL = NP, LO_COL = NP + KP / 2;
+  static_assert(NP + KP <= 256, "tile does not fit 256 TMEM columns");
+  static constexpr size_t smem_bytes() { return (size_t)2 * KCH * NP * 16 + (size_t)KP * 4 + 64; }
+};
+
+struct DenseTc3Args {
+  const __half* Bhi;  // [KP/8][NP][8]  rn16(lscale * Lambda)
+  const __half* Blo;  //                rn16(lscale * Lambda - hi)
+  const float* mu;    // [128] zero padded
+  float inv_lscale;   // 1 / lscale (power of two)
+  int dbg;            // 1: issue no MMAs (commit only); 2: skip the epilogue arithmetic
+};
+
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4)                      // D format F32; A, B format F16 (0); K-major A, B
+         | ((uint32_t)(N >> 3) << 17)   // N / 8
+         | ((uint32_t)(M >> 4) << 24);  // M / 16
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&u)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld4(uint32_t (&u)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]) : : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&u)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(u[0]), "r"(u[1]),
+               "r"(u[2]), "r"(u[3])
+               : "memory");
+}
+
+// generic N-column wrappers (N = 16: G batch; N = 8 / 4: packed hi / lo of 16 / 8 dims)
+template <int N>
+__device__ __forceinline__ void tm_ld(uint32_t taddr, uint32_t* u) {
+  if constexpr (N == 16) tmem_ld16_issue(taddr, *reinterpret_cast<uint32_t(*)[16]>(u));
+  else if constexpr (N == 8) tmem_ld8_issue2(taddr, *reinterpret_cast<uint32_t(*)[8]>(u));
+  else tmem_ld4_issue(taddr, *reinterpret_cast<uint32_t(*)[4]>(u));
+}
+template <int N>
+__device__ __forceinline__ void tm_wait(uint32_t* u) {
+  if constexpr (N == 16) tmem_wait_ld16(*reinterpret_cast<uint32_t(*)[16]>(u));
+  else if constexpr (N == 8) tmem_wait_ld8(*reinterpret_cast<uint32_t(*)[8]>(u));
+  else tmem_wait_ld4(*reinterpret_cast<uint32_t(*)[4]>(u));
+}
+template <int N>
+__device__ __forceinline__ void tm_st(uint32_t taddr, const uint32_t* u) {
+  if constexpr (N == 16) tmem_st16(taddr, *reinterpret_cast<const uint32_t(*)[16]>(u));
+  else if constexpr (N == 8) tmem_st8(taddr, *reinterpret_cast<const uint32_t(*)[8]>(u));
+  else tmem_st4(taddr, *reinterpret_cast<const uint32_t(*)[4]>(u));
+}
+
+__device__ __forceinline__ float2 h2_unpack(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+__device__ __forceinline__ uint32_t h2_pack(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// sm_100 mixed-precision FADD / FFMA (SASS FHADD / FHFMA): an fp16 operand is widened inside the
+// instruction, so "float + half" and "float - half" cost one issue slot instead of two.
+__device__ __forceinline__ float add_h(unsigned short a, float c) {
+  float d;
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(a), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float sub_h(float c, unsigned short a) {  // c - a
+  float d;
+  const unsigned short m1 = 0xBC00;  // -1.0
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(m1), "f"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned short h_lo(uint32_t w) { return (unsigned short)(w & 0xffffu); }
+__device__ __forceinline__ unsigned short h_hi(uint32_t w) { return (unsigned short)(w >> 16); }
+// (hi, lo) fp16 pair words of two consecutive dims: hi = rn16(x), lo = rn16(x - hi)
+__device__ __forceinline__ void split16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = h2_pack(x0, x1);
+  lo = h2_pack(sub_h(x0, h_lo(hi)), sub_h(x1, h_hi(hi)));
+}
+
+// ---- software-pipelined epilogue: batches of 16 dims (a trailing batch of 8 when C8 is odd) ----
+struct Tc3Batch {
+  uint32_t g[16], hi[8], lo[8];
+};
+
+template <int NCOL>
+__device__ __forceinline__ void tc3_issue(Tc3Batch& b, uint32_t t_d, uint32_t t_hi, uint32_t t_lo, int col0) {
+  tm_ld<NCOL>(t_d + (uint32_t)col0, b.g);
+  tm_ld<NCOL / 2>(t_hi + (uint32_t)(col0 / 2), b.hi);
+  tm_ld<NCOL / 2>(t_lo + (uint32_t)(col0 / 2), b.lo);
+}
+template <int NCOL>
+__device__ __forceinline__ void tc3_wait(Tc3Batch& b) {
+  tm_wait<NCOL>(b.g);
+  tm_wait<NCOL / 2>(b.hi);
+  tm_wait<NCOL / 2>(b.lo);
+}
+
+// One code path for every evaluation (first / middle / last differ only in ck and `store`).
+// w = (h 2^e) v is the row's velocity in drift units, so the drift is two additions:
+//   kick  w -= ck G            (ck carries h 2^e * h/m * 2^-e / lscale)
+//   drift x' = hi + (lo + w)   (5 issue slots per dim including the re-split)
+template <int NCOL>
+__device__ __forceinline__ void tc3_compute(float* w, Tc3Batch& b, uint32_t t_hi, uint32_t t_lo, int col0, float ck,
+                                            bool store) {
+#pragma unroll
+  for (int i = 0; i < NCOL / 2; ++i) {
+    w[2 * i] = fmaf(-ck, __uint_as_float(b.g[2 * i]), w[2 * i]);
+    w[2 * i + 1] = fmaf(-ck, __uint_as_float(b.g[2 * i + 1]), w[2 * i + 1]);
+    const float x0 = add_h(h_lo(b.hi[i]), add_h(h_lo(b.lo[i]), w[2 * i]));
+    const float x1 = add_h(h_hi(b.hi[i]), add_h(h_hi(b.lo[i]), w[2 * i + 1]));
+    split16(x0, x1, b.hi[i], b.lo[i]);
+  }
+  if (store) {
+    tm_st<NCOL / 2>(t_hi + (uint32_t)(col0 / 2), b.hi);
+    tm_st<NCOL / 2>(t_lo + (uint32_t)(col0 / 2), b.lo);
+  }
+}
+
+template <int C8, int B>
+__device__ __forceinline__ void tc3_pipe(float (&w)[8 * C8], Tc3Batch (&bb)[2], uint32_t t_d, uint32_t t_hi,
+                                         uint32_t t_lo, float ck, bool store) {
+  constexpr int NB = (C8 + 1) / 2;
+  constexpr int NCOL = (B == NB - 1 && (C8 % 2) == 1) ? 8 : 16;
+  constexpr int cur = B & 1;
+  tc3_wait<NCOL>(bb[cur]);
+  if constexpr (B + 1 < NB) {
+    constexpr int NCOL_N = (B + 1 == NB - 1 && (C8 % 2) == 1) ? 8 : 16;
+    tc3_issue<NCOL_N>(bb[cur ^ 1], t_d, t_hi, t_lo, 16 * (B + 1));
+  }
+  tc3_compute<NCOL>(&w[16 * B], bb[cur], t_hi, t_lo, 16 * B, ck, store);
+  if constexpr (B + 1 < NB) tc3_pipe<C8, B + 1>(w, bb, t_d, t_hi, t_lo, ck, store);
+}
+
+template <int C8>
+__device__ __forceinline__ void tc3_epilogue(float (&w)[8 * C8], uint32_t t_d, uint32_t t_hi, uint32_t t_lo, float ck,
+                                             bool store) {
+  Tc3Batch bb[2];
+  constexpr int NCOL0 = (C8 == 1) ? 8 : 16;
+  tc3_issue<NCOL0>(bb[0], t_d, t_hi, t_lo, 0);
+  tc3_pipe<C8, 0>(w, bb, t_d, t_hi, t_lo, ck, store);
+  if (store) tmem_wait_st();
+}
+
+// sum_d xs_d G_d of this row (first and last evaluation only: a rolled loop, kept out of the
+// unrolled epilogue so that the 49 middle evaluations do not pay for it)
+template <int C8>
+__device__ __noinline__ float tc3_energy(uint32_t t_d, uint32_t t_hi, uint32_t t_lo) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int c = 0; c < C8; ++c) {
+    uint32_t g[8], hh[4], ll[4];
+    tmem_ld8_issue2(t_d + (uint32_t)(8 * c), g);
+    tmem_ld4_issue(t_hi + (uint32_t)(4 * c), hh);
+    tmem_ld4_issue(t_lo + (uint32_t)(4 * c), ll);
+    tmem_wait_ld8(g);
+    tmem_wait_ld4(hh);
+    tmem_wait_ld4(ll);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 xh = h2_unpack(hh[i]);
+      acc.x = fmaf(add_h(h_lo(ll[i]), xh.x), __uint_as_float(g[2 * i]), acc.x);
+      acc.y = fmaf(add_h(h_hi(ll[i]), xh.y), __uint_as_float(g[2 * i + 1]), acc.y);
+    }
+  }
+  return acc.x + acc.y;
+}
+
+template <int C8>
+__global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<float> A, const DenseTc3Args pa,
+                                                              const int hmc) {
+  typedef Tc3Shape<C8> S;
+  constexpr int NP = S::NP, KP = S::KP, K16 = S::K16, DC = S::DC, KCH = S::KCH;
+  extern __shared__ __align__(128) unsigned char tc3_smem_raw[];
+  const int D = A.D;
+  uint4* Bhi = reinterpret_cast<uint4*>(tc3_smem_raw);  // [KCH][NP] x 16 bytes
+  uint4* Blo = Bhi + (size_t)KCH * NP;
+  float* mus = reinterpret_cast<float*>(Blo + (size_t)KCH * NP);  // [KP]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(mus + KP);         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
+  const int grp = warp >> 2, quarter = warp & 3;
+  const int row = quarter * 32 + lane;
+
+  // ---- CTA setup (once) ------------------------------------------------------------------
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    if (lane == 0) {
+      mbar_init(&mbar[0], 1);
+      mbar_init(&mbar[1], 1);
+      fence_barrier_init();
+    }
+  }
+  {
+    const uint4* s0 = reinterpret_cast<const uint4*>(pa.Bhi);
+    const uint4* s1 = reinterpret_cast<const uint4*>(pa.Blo);
+    for (int i = tid; i < KCH * NP; i += TC3_THREADS) {
+      Bhi[i] = s0[i];
+      Blo[i] = s1[i];
+    }
+    if (tid < KP) mus[tid] = pa.mu[tid];
+  }
+  fence_proxy_async();  // Lambda written through the generic proxy, read by the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+  const uint32_t t_d = tmem_base + (uint32_t)(grp * 256) + lane_off;  // this row's accumulator
+  const uint32_t t_hi = t_d + (uint32_t)S::HI_COL, t_lo = t_d + (uint32_t)S::LO_COL;
+  const uint32_t idesc = umma_idesc_f16(TC_M, NP);
+  const uint64_t db_hi = umma_desc(smem_u32(Bhi), NP), db_lo = umma_desc(smem_u32(Blo), NP);
+  constexpr uint64_t b_step = (2u * NP * 16u) >> 4;
+  const uint32_t mma_d = tmem_base + (uint32_t)(grp * 256);
+  const uint32_t mma_hi = mma_d + (uint32_t)S::HI_COL, mma_lo = mma_d + (uint32_t)S::LO_COL;
+
+  // h == 0 is a fixed point (q, p, H unchanged): run it as L = 0 so that 1 / h never appears
+  const int L = A.h == 0.f ? 0 : A.L;
+  const float h = A.h == 0.f ? 1.f : A.h;
+  const long long ntiles = (A.P + TC_M - 1) / TC_M;
+  const long long tile0 = ntiles * blockIdx.x / gridDim.x, tile1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+  uint32_t phase = 0;
+
+  for (long long tile = tile0 + grp; tile < tile1; tile += 2) {
+    const long long prow = tile * TC_M + row;
+    const bool valid = prow < A.P;
+    const long long pc = valid ? prow : 0;
+
+    float v[DC];
+    const float m = valid ? A.mass[pc] : 1.f;
+    const float inv_m = 1.f / m;
+    const float pstd = hmc ? momentum_std<float>(m, A.kB, A.temp, A.pscale) : 0.f;
+    float K0 = 0.f, amax = 0.f, vmax = 0.f;
+    // The per-tile prologue runs once per L + 1 evaluations but its code must stay SMALL: straight-line
+    // code executed once per tile is fetched from L2 every time.  (Measured at config 2: with the 26
+    // Philox blocks and the general write-back unrolled the kernel was 390 KB of SASS and an L = 0
+    // iteration took 1.06 ms; with the rolled loops below, 84 KB and 0.47 ms.)  Everything that can be
+    // indexed dynamically (tensor-memory columns) runs in rolled loops; only register-array traffic
+    // is unrolled.
+    // ---- positions: all loads in flight (v[] doubles as the staging array) ----------------------
+    // (rows past the end of the ensemble replay row 0 and are never written; only the last 8-dim
+    // chunk can hold dims >= D, so every other load is unconditional)
+    auto col = [&](const float* base, long long ld, int d) -> float {
+      return (d < DC - 8 || d < D) ? base[(long long)d * ld] : 0.f;
+    };
+    const float* qcol = A.q + pc;
+#pragma unroll
+    for (int d = 0; d < DC; ++d) v[d] = col(qcol, A.q_ld, d);
+    const bool philox = hmc && A.z == nullptr;
+    if (philox) {
+      // momenta: Philox blocks 2c, 2c+1 -> dims 8c .. 8c+7, parked as v = p / m in the operand
+      // columns [NP, NP + DC) (free until the split below) while the position loads land
+      const PhiloxKey K(A.seed, A.iter);
+#pragma unroll 1
+      for (int c = 0; c < C8; ++c) {
+        float zz[8];
+        NormalBlock<float>::draw_multi<2>(K, A.offset + (u64)pc, (uint32_t)(2 * c), zz);
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float pp = (8 * c + e < D) ? zz[e] * pstd : 0.f;
+          K0 = fmaf(pp, pp, K0);
+          const float vv = pp * inv_m;
+          vmax = fmaxf(vmax, fabsf(vv));
+          pk[e] = __float_as_uint(vv);
+        }
+        tmem_st8(t_hi + (uint32_t)(8 * c), pk);
+      }
+    }
+    // x = q - mu parked in the (idle) accumulator columns
+#pragma unroll
+    for (int c = 0; c < C8; ++c) {
+      uint32_t xx[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = v[8 * c + e] - mus[8 * c + e];  // dims >= D: 0 - 0
+        amax = fmaxf(amax, fabsf(x));
+        xx[e] = __float_as_uint(x);
+      }
+      tmem_st8(t_d + (uint32_t)(8 * c), xx);
+    }
+    if (philox) {
+      tmem_wait_st();
+#pragma unroll
+      for (int c = 0; c < C8; c += 2) {
+        if (c + 1 < C8) {
+          uint32_t t[16];
+          tmem_ld16_issue(t_hi + (uint32_t)(8 * c), t);
+          tmem_wait_ld16(t);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[8 * c + e] = __uint_as_float(t[e]);
+        } else {
+          uint32_t t[8];
+          tmem_ld8_issue2(t_hi + (uint32_t)(8 * c), t);
+          tmem_wait_ld8(t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[8 * c + e] = __uint_as_float(t[e]);
+        }
+      }
+    } else {
+      // fed momenta (parity mode) or integrate(): straight into the registers
+      const float* mcol = (hmc ? A.z : A.p) + pc;
+      const long long mld = hmc ? A.z_ld : A.p_ld;
+      const float msc = hmc ? pstd : 1.f;
+#pragma unroll
+      for (int d = 0; d < DC; ++d) v[d] = col(mcol, mld, d) * msc;
+#pragma unroll
+      for (int d = 0; d < DC; ++d) {
+        K0 = fmaf(v[d], v[d], K0);
+        v[d] *= inv_m;
+        vmax = fmaxf(vmax, fabsf(v[d]));
+      }
+    }
+    K0 *= 0.5f * inv_m;
+    // ---- row scale 2^e: max(|x|, reach of the ballistic drift) -> [2^7, 2^8) ----------------------
+    amax = fmaxf(amax, fabsf(h) * (float)L * vmax);
+    uint32_t eb = (__float_as_uint(amax) >> 23) & 0xffu;
+    eb = eb < 16u ? 134u : eb;  // zero / tiny rows: no scaling
+    const float sc = __uint_as_float((261u - eb) << 23);   // 2^(7 - (eb - 127))
+    const float isc = __uint_as_float((eb - 7u) << 23);    // 1 / sc
+    tmem_wait_st();
+#pragma unroll 1
+    for (int c = 0; c < C8; ++c) {
+      uint32_t xx[8], hh[4], ll[4];
+      tmem_ld8_issue2(t_d + (uint32_t)(8 * c), xx);
+      tmem_wait_ld8(xx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        split16(__uint_as_float(xx[2 * i]) * sc, __uint_as_float(xx[2 * i + 1]) * sc, hh[i], ll[i]);
+      tmem_st4(t_hi + (uint32_t)(4 * c), hh);
+      tmem_st4(t_lo + (uint32_t)(4 * c), ll);
+    }
+    if constexpr (DC < KP) {
+      // operand columns of the padded dims [DC, KP) (the momentum parking overwrote them): finite zeros
+      uint32_t zero[4] = {0u, 0u, 0u, 0u};
+      tmem_st4(t_hi + (uint32_t)(DC / 2), zero);
+      tmem_st4(t_lo + (uint32_t)(DC / 2), zero);
+    }
+    tmem_wait_st();
+
+    // velocities in drift units: w = (h 2^e) v;  g_true = G * isc * inv_lscale
+    const float hs = h * sc, gs = isc * pa.inv_lscale;
+#pragma unroll
+    for (int d = 0; d < DC; ++d) v[d] *= hs;
+    const float ckf = (h * inv_m) * (h * pa.inv_lscale), ckh = 0.5f * ckf;  // hs * (h / m) * gs
+    float U0 = 0.f, U1 = 0.f;
+
+    for (int ev = 0; ev <= L; ++ev) {
+      // the tile's operands are complete once all 128 rows arrive
+      tc_fence_before();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      if (quarter == 0 && elect_one()) {
+        tc_fence_after();
+        if (!(pa.dbg & 1)) {
+#pragma unroll
+          for (int j = 0; j < K16; ++j) umma_f16_ts(mma_d, mma_hi + 8u * j, db_hi + j * b_step, idesc, j > 0);
+#pragma unroll
+          for (int j = 0; j < K16; ++j) umma_f16_ts(mma_d, mma_lo + 8u * j, db_hi + j * b_step, idesc, 1);
+#pragma unroll
+          for (int j = 0; j < K16; ++j) umma_f16_ts(mma_d, mma_hi + 8u * j, db_lo + j * b_step, idesc, 1);
+        }
+        umma_commit(&mbar[grp]);
+      }
+      mbar_wait(&mbar[grp], phase);
+      phase ^= 1u;
+      tc_fence_after();
+      const bool first = ev == 0, last = ev == L;
+      if (hmc && (first || last)) {
+        const float Uev = tc3_energy<C8>(t_d, t_hi, t_lo);
+        if (first) U0 = Uev;
+        if (last) U1 = Uev;
+      }
+      const float ck = L == 0 ? 0.f : ((first || last) ? ckh : ckf);
+      if (!(pa.dbg & 2)) tc3_epilogue<C8>(v, t_d, t_hi, t_lo, ck, !last);
+    }
+    // U = 1/2 x . g_true = 1/2 (xs isc) . (G gs)
+    U0 = (U0 * isc) * (0.5f * gs);
+    U1 = (U1 * isc) * (0.5f * gs);
+
+    // ---- Metropolis + write back -------------------------------------------------------------
+    float K1 = 0.f;
+    const float w2p = m / hs;  // p = v * m = w * m / (h 2^e)
+#pragma unroll
+    for (int d = 0; d < DC; ++d) {
+      v[d] *= w2p;
+      K1 = fmaf(v[d], v[d], K1);
+    }
+    bool rej = false;
+    float accp = 1.f, oldH = 0.f, newH = 0.f;
+    if (hmc) {
+      oldH = K0 + U0;
+      newH = 0.5f * K1 * inv_m + U1;
+      float u = 0.f;
+      if (valid)
+        u = A.u != nullptr ? A.u[pc] : NormalBlock<float>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)pc);
+      rej = metropolis_reject<float>(oldH, newH, u, A.flags, &accp);
+    }
+    const bool fast = A.p == nullptr && A.partials == nullptr;
+    const bool wr = valid && !rej;  // HMC.py:175: rejected rows keep the value in HBM
+    // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only accepted rows store.
+    // Rolled loops (see the prologue note on code size).
+    if (fast) {
+#pragma unroll 1
+      for (int c = 0; c < C8; ++c) {
+        uint32_t hh[4], ll[4];
+        tmem_ld4_issue(t_hi + (uint32_t)(4 * c), hh);
+        tmem_ld4_issue(t_lo + (uint32_t)(4 * c), ll);
+        tmem_wait_ld4(hh);
+        tmem_wait_ld4(ll);
+        float* qd = A.q + (long long)(8 * c) * A.q_ld + pc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 xh = h2_unpack(hh[i]);
+          const float q0 = fmaf(add_h(h_lo(ll[i]), xh.x), isc, mus[8 * c + 2 * i]);
+          const float q1 = fmaf(add_h(h_hi(ll[i]), xh.y), isc, mus[8 * c + 2 * i + 1]);
+          if (8 * c + 2 * i < D && wr) qd[(long long)(2 * i) * A.q_ld] = q0;
+          if (8 * c + 2 * i + 1 < D && wr) qd[(long long)(2 * i + 1) * A.q_ld] = q1;
+        }
+      }
+    } else {
+      // general path (momentum output and / or statistics): park p in the accumulator columns so that
+      // the rolled loop can index it
+#pragma unroll
+      for (int c = 0; c < C8; ++c) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pk[e] = __float_as_uint(v[8 * c + e]);
+        tmem_st8(t_d + (uint32_t)(8 * c), pk);
+      }
+      tmem_wait_st();
+      const bool need_old = rej && (A.partials != nullptr || (A.flags & FLAG_BUGCOMPAT));
+      double* prow_out = A.partials ? A.partials + ((size_t)tile * 4 + quarter) * (2 * D + 3) : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < C8; ++c) {
+        uint32_t hh[4], ll[4], pk[8];
+        tmem_ld4_issue(t_hi + (uint32_t)(4 * c), hh);
+        tmem_ld4_issue(t_lo + (uint32_t)(4 * c), ll);
+        tmem_ld8_issue2(t_d + (uint32_t)(8 * c), pk);
+        tmem_wait_ld4(hh);
+        tmem_wait_ld4(ll);
+        tmem_wait_ld8(pk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int d = 8 * c + e;
+          if (d >= D) continue;  // uniform
+          const float xh = (e & 1) ? h2_unpack(hh[e / 2]).y : h2_unpack(hh[e / 2]).x;
+          const float xl = (e & 1) ? h2_unpack(ll[e / 2]).y : h2_unpack(ll[e / 2]).x;
+          const float qn = fmaf(xl + xh, isc, mus[d]);
+          float qold = 0.f;
+          if (valid && need_old) qold = A.q[d * A.q_ld + pc];
+          if (wr) A.q[d * A.q_ld + pc] = qn;
+          if (A.p != nullptr && valid) {
+            float pv = __uint_as_float(pk[e]);
+            if (rej) {
+              if (A.flags & FLAG_BUGCOMPAT)
+                pv = qold;  // HMC.py:176 (sic)
+              else if (A.z != nullptr)
+                pv = A.z[d * A.z_ld + pc] * pstd;
+              else
+                pv = one_normal<float>(A.seed, A.iter, A.offset + (u64)pc, d) * pstd;
+            }
+            A.p[d * A.p_ld + pc] = pv;
+          }
+          if (prow_out != nullptr) {
+            const double qk = valid ? (double)(rej ? qold : qn) : 0.0;
+            const double s1 = warp_sum(qk), s2 = warp_sum(qk * qk);
+            if (lane == 0) {
+              prow_out[3 + d] = s1;
+              prow_out[3 + D + d] = s2;
+            }
+          }
+        }
+      }
+      if (prow_out != nullptr) {
+        double s_acc = valid ? (rej ? 0.0 : 1.0) : 0.0, s_accp = valid ? (double)accp : 0.0;
+        double s_h = valid ? (double)(rej ? oldH : newH) : 0.0;
+        s_acc = warp_sum(s_acc);
+        s_accp = warp_sum(s_accp);
+        s_h = warp_sum(s_h);
+        if (lane == 0) {
+          prow_out[0] = s_acc;
+          prow_out[1] = s_accp;
+          prow_out[2] = s_h;
+        }
+      }
+    }
+    if (hmc && valid && A.accept != nullptr) A.accept[pc] = rej ? 0 : 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace ehmc

@@ -1,0 +1,90 @@
+// Issue-rate microbenchmark for the conversion / mixed-precision instructions the fp16-split
+// epilogue of k_dense_tc3 depends on (sm_100a).  Each thread runs 8 independent dependency chains
+// of one instruction; 1024 threads per CTA, one CTA per SM.  Prints warp-instructions per clock
+// per SM sub-partition (1.0 = full issue rate).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o op_rates op_rates.cu && ./op_rates
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define ITER 4096
+
+template <int OP>
+__global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, float seed) {
+  float a[8];
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = seed + threadIdx.x * 1e-3f + i;
+    u[i] = 0x3c003c00u + threadIdx.x + i;
+  }
+  const unsigned short one = 0x3c00, m1 = 0xbc00;
+  long long t0 = clock64();
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (OP == 0) asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(a[i]) : "f"(seed));
+      if (OP == 1) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(seed));
+      if (OP == 2) asm volatile("add.rn.f32.f16 %0, %1, %0;" : "+f"(a[i]) : "h"(one));                 // FHADD
+      if (OP == 3) asm volatile("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(a[i]) : "h"(one), "h"(m1));   // FHFMA
+      if (OP == 4) asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %0; cvt.f32.f16 %1, lo;}" : "+r"(u[i]), "+f"(a[i]));  // HADD2.F32 unpack
+      if (OP == 5) asm volatile("cvt.rn.f16x2.f32 %0, %1, %1;" : "=r"(u[i]) : "f"(a[i]));             // F2FP pack (independent)
+      if (OP == 6) asm volatile("{.reg .b32 t; cvt.rn.f16x2.f32 t, %0, %0; mov.b32 %0, t;}" : "+f"(a[i]));  // F2FP chain
+      if (OP == 7) asm volatile("lop3.b32 %0, %0, %1, %0, 0x96;" : "+r"(u[i]) : "r"(0x1234567u));
+      if (OP == 8) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(u[i]) : "r"(0x1234567u));
+      if (OP == 9) asm volatile("shf.l.wrap.b32 %0, %0, %0, 3;" : "+r"(u[i]));
+      if (OP == 10) asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(0x1234567u));
+      if (OP == 11) asm volatile("fma.rn.f16x2 %0, %0, %1, %0;" : "+r"(u[i]) : "r"(0x3c003c00u));    // HFMA2
+      if (OP == 12) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(seed));
+      if (OP == 13) asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(u[i]) : "f"(a[i]));
+      if (OP == 14) asm volatile("{.reg .b64 t; mov.b64 t, {%0, %1}; fma.rn.f32x2 t, t, t, t; mov.b64 {%0, %1}, t;}" : "+f"(a[i]), "+f"(a[(i + 1) & 7]));  // FFMA2
+      if (OP == 15) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(seed));
+    }
+  }
+  long long t1 = clock64();
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i] + __uint_as_float(u[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+void run(const char* name, float* out, long long* cyc) {
+  k<OP><<<148, 1024>>>(out, cyc, 1.0f);
+  cudaDeviceSynchronize();
+  k<OP><<<148, 1024>>>(out, cyc, 1.0f);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h[148];
+  cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+  double c = 0;
+  for (int i = 0; i < 148; ++i) c += h[i];
+  c /= 148;
+  // 32 warps per SM = 8 per sub-partition, each issuing 8 * ITER instructions
+  const double per_smsp = 8.0 * 8 * ITER / c;
+  printf("%-28s %8.3f warp-instr/clk/SMSP  (%.0f cycles)  %s\n", name, per_smsp, c, cudaGetErrorString(e));
+}
+
+int main() {
+  float* out;
+  long long* cyc;
+  cudaMalloc(&out, 148 * 1024 * 4);
+  cudaMalloc(&cyc, 148 * 8);
+  run<0>("FFMA", out, cyc);
+  run<1>("FADD", out, cyc);
+  run<12>("FMUL", out, cyc);
+  run<15>("FMNMX", out, cyc);
+  run<2>("FHADD (add.f32.f16)", out, cyc);
+  run<3>("FHFMA (fma.f32.f16)", out, cyc);
+  run<4>("HADD2.F32 (cvt.f32.f16)", out, cyc);
+  run<5>("F2FP.F16.F32.PACK_AB", out, cyc);
+  run<6>("F2FP chain", out, cyc);
+  run<11>("HFMA2", out, cyc);
+  run<14>("FFMA2 (fma.f32x2)", out, cyc);
+  run<13>("cvt.rna.tf32", out, cyc);
+  run<7>("LOP3", out, cyc);
+  run<8>("PRMT", out, cyc);
+  run<9>("SHF", out, cyc);
+  run<10>("IADD", out, cyc);
+  return 0;
+}

@@ -705,7 +705,8 @@ def test_config3_shape_logistic_reduced(E):
 # ---------------------------------------------------------------------------
 # dense Gaussian: tensor-core (3xTF32, tcgen05) path vs CUDA-core FP32 path vs oracle
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("D,P,L", [(20, 300, 7), (40, 129, 9), (100, 1000, 50), (104, 257, 12), (17, 64, 0), (56, 200, 3)])
+@pytest.mark.parametrize("D,P,L", [(20, 300, 7), (40, 129, 9), (100, 1000, 50), (104, 257, 12), (17, 64, 0), (56, 200, 3),
+                                   (112, 300, 10), (128, 513, 25), (100, 40000, 5)])
 def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
     import torch
 
@@ -725,7 +726,10 @@ def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
     args = E._lib.make_args(h, h**2, L, KB, 1 / KB, flags=1)
     out = {}
     try:
-        for path in (1, 2, 3):  # 1 = CUDA cores, 2 = tensor cores (one tile, SS), 3 = tensor cores (two tiles, TS)
+        # 1 = CUDA cores, 2 / 3 = 3xTF32 tensor cores (one tile SS / two tiles TS, D <= 104),
+        # 4 = 3xFP16 persistent tensor-core kernel (the default path, D <= 128)
+        paths = (1, 2, 3, 4) if D <= 104 else (1, 4)
+        for path in paths:
             ctx.set_option("dense_path", path)
             q = torch.tensor(q0, dtype=torch.float32, device="cuda")
             p = torch.empty_like(q)
@@ -740,7 +744,7 @@ def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
         ctx.set_option("dense_path", 0)
     with np.errstate(over="ignore"):
         clear = np.abs(u - np.minimum(1, np.exp(oh - nh))) > TIE[np.float32]
-    for path in (1, 2, 3):
+    for path in paths:
         q, p, a, st = out[path]
         assert np.array_equal(a[clear], accr[clear]), f"path {path}"
         same = a == accr
@@ -748,8 +752,7 @@ def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
         assert rel_err(p[:, same], pr[:, same]) < 1e-5, f"path {path}"
         assert st[0] == a.sum()
         np.testing.assert_allclose(st[3:3 + D], q.astype(np.float64).sum(1), rtol=1e-9, atol=1e-9)
-    print("D", D, "tc2-vs-oracle", rel_err(out[3][0], qr), "tc-vs-oracle", rel_err(out[2][0], qr), "cc-vs-oracle",
-          rel_err(out[1][0], qr))
+    print("D", D, {f"path{k}-vs-oracle": float(rel_err(out[k][0], qr)) for k in paths})
 
 
 def test_dense_tensor_core_integrate_only(E):
@@ -770,6 +773,54 @@ def test_dense_tensor_core_integrate_only(E):
     ens.mass = torch.tensor(mass, dtype=torch.float32, device="cuda")
     q, p = E.Leapfrog(ens, h, L * h + 1e-9, E.GaussianPotential(precision=prec)).integrate()
     assert rel_err(q.cpu().numpy(), qr) < 1e-5 and rel_err(p.cpu().numpy(), pr) < 1e-5
+
+
+@pytest.mark.parametrize("scale", [1e-6, 1.0, 3e4])
+def test_dense_tensor_core_scale_robustness(E, scale):
+    """The fp16 split operands of k_dense_tc3 are rescaled per particle row by a power of two, so a
+    trajectory in tiny or huge units (far outside fp16's exponent range) keeps float32 accuracy.
+    The dynamics are linear: scaling q and p by s scales the trajectory by s."""
+    import torch
+
+    D, P, L, h = 100, 300, 30, 0.05
+    rng = np.random.RandomState(11)
+    A = rng.standard_normal((D, D))
+    prec = A @ A.T / D + np.eye(D)
+    mu = rng.standard_normal(D) * scale
+    q0 = rng.standard_normal((D, P)) * scale + mu[:, None]
+    q0[:, 0] = mu  # a row that starts exactly at the mean (x = 0)
+    p0 = rng.standard_normal((D, P)) * scale
+    p0[:, 1] = 0.0  # and one at rest
+    mass = rng.uniform(0.5, 2.0, P)
+    qr, pr = O.leapfrog(q0, p0, mass, h, L, O.DenseGaussian(prec, mu).grad)
+    ens = E.Ensemble(D, P, dtype=np.float32, device="cuda")
+    ens.q.copy_(torch.tensor(q0, dtype=torch.float32))
+    ens.p.copy_(torch.tensor(p0, dtype=torch.float32))
+    ens.mass = torch.tensor(mass, dtype=torch.float32, device="cuda")
+    q, p = E.Leapfrog(ens, h, L * h + 1e-9, E.GaussianPotential(precision=prec, mean=mu)).integrate()
+    # positions relative to the spread around the mean (q - mu), not to |mu|
+    assert rel_err(q.cpu().numpy() - mu[:, None], qr - mu[:, None]) < 1e-5
+    assert rel_err(p.cpu().numpy(), pr) < 1e-5
+
+
+def test_dense_tensor_core_zero_step(E):
+    """h = 0 is a fixed point of the trajectory (q, p unchanged, every proposal accepted)."""
+    import torch
+
+    D, P = 64, 200
+    rng = np.random.RandomState(12)
+    A = rng.standard_normal((D, D))
+    prec = A @ A.T / D + np.eye(D)
+    q0 = rng.standard_normal((D, P)).astype(np.float32)
+    ctx = E._lib.Context.get()
+    hd = E.GaussianPotential(precision=prec).handle(32, ctx)
+    args = E._lib.make_args(0.0, 0.0, 5, KB, 1 / KB, flags=0)
+    q = torch.tensor(q0, device="cuda")
+    acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+    E._lib.hmc_iter(ctx, hd, q, torch.ones(P, dtype=torch.float32, device="cuda"), args, accept=acc)
+    torch.cuda.synchronize()
+    assert acc.cpu().numpy().all()
+    np.testing.assert_allclose(q.cpu().numpy(), q0, rtol=3e-7, atol=1e-7)
 
 
 # ---------------------------------------------------------------------------
