@@ -330,6 +330,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
+    # leapfrog steps actually executed per iteration: with step-size adaptation the trajectory LENGTH
+    # (simulTime) is fixed and numSteps = int(simulTime / stepSize) follows the step size
+    # (src/integrator.py:51), so the units of work are counted, not assumed
+    L_cfg = L
+    if adaptive:
+        L = float(np.mean(run_out["numSteps"]))
     value = P * L * args.steps / (total_ms * 1e-3)
 
     # ---- ESS/s: min over dimensions of the ESS of traced chains, scaled to the ensemble ------
@@ -377,7 +383,7 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
-        e2e = {"value": P * L * args.e2e_steps / e2e_s, "unit": "particle-leapfrog-steps/s",
+        e2e = {"value": P * L_cfg * args.e2e_steps / e2e_s, "unit": "particle-leapfrog-steps/s",
                "h2d_bytes_per_step": int(D * Pl * 4 + Pl * 4), "d2h_bytes_per_step": int(D * Pl * 4 + Pl),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
                "api": "HMC.step on a host-backed Ensemble -> ehmc_hmc_iter (host path, pinned buffers)"}
@@ -467,7 +473,7 @@ def main():
                       if (args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1")
                       else "f32 state, bf16 tensor-core gradient GEMMs (fp32 accumulate)" if (args.config == "c3" and os.environ.get("EHMC_LOGISTIC_PRECISION", "bf16") == "bf16") else "f32"),
             "data": "synthetic",
-            "config": {"workload": cfg["desc"], "D": D, "P": P, "L": L, "h": h, "particles_per_gpu": Pl,
+            "config": {"workload": cfg["desc"], "D": D, "P": P, "L": L_cfg, "L_executed_mean": L, "h": h, "particles_per_gpu": Pl,
                        "rng": "philox in-kernel", "l2": "inputs_exceed_l2" if D * Pl * 4 > 126e6 else "resident",
                        "parallelism": f"particle-shard x{world}, no data-path collective"},
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,

@@ -218,46 +218,62 @@ class HMC:
             Ptot = float(t.item())
         adapter = StepSizeAdapter(self.stepSize, targetAccept) if adapt else None
         adaptIterations = numIterations if adaptIterations is None else adaptIterations
+        # Two statistics slots (device vector + pinned host copy + "copy done" event).  Iteration k
+        # writes slot k & 1; a side stream all-reduces it and copies it to the host behind an event,
+        # so the host only ever waits for iteration k - 1 while iteration k is already running:
+        # the GPU never idles on the statistics (they are consumed one iteration late).
         stats = [torch.zeros(2 * D + 3, dtype=torch.float64, device=dev) for _ in range(2)]
-        host = torch.zeros(2 * D + 3, dtype=torch.float64).pin_memory()
-        out = dict(acceptRate=[], meanAcceptProb=[], meanH=[], stepSize=[])
-        sum1 = torch.zeros(D, dtype=torch.float64)
-        sum2 = torch.zeros(D, dtype=torch.float64)
+        hosts = [torch.zeros(2 * D + 3, dtype=torch.float64).pin_memory() for _ in range(2)]
+        hosts_np = [h.numpy() for h in hosts]
+        done = [torch.cuda.Event() for _ in range(2)]
+        main = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        out = dict(acceptRate=[], meanAcceptProb=[], meanH=[], stepSize=[], numSteps=[])
+        sum1 = np.zeros(D)
+        sum2 = np.zeros(D)
         nstat = 0
         trace = (torch.empty((D, traceParticles, numIterations), dtype=ens.dtype, device=dev)
                  if traceParticles else None)
         self.integrator.q = ens.q
-        pending = None  # statistics tensor whose all-reduce is in flight
+        pending = None  # slot whose statistics are in flight
 
-        def consume(buf, it):
+        def consume(slot, it):
             nonlocal nstat
-            reducer.wait()
-            host.copy_(buf)  # sync D2H of 2D+3 doubles
-            u = unpack_stats(host, D, Ptot)
-            out["acceptRate"].append(u["acceptRate"])
-            out["meanAcceptProb"].append(u["meanAcceptProb"])
-            out["meanH"].append(u["meanH"])
-            sum1.add_(host[3:3 + D])
-            sum2.add_(host[3 + D:3 + 2 * D])
+            done[slot].synchronize()  # host wait: kernel `it` + all-reduce + D2H of 2D+3 doubles
+            h = hosts_np[slot]
+            acc_prob = float(h[1]) / Ptot
+            out["acceptRate"].append(float(h[0]) / Ptot)
+            out["meanAcceptProb"].append(acc_prob)
+            out["meanH"].append(float(h[2]) / Ptot)
+            sum1[:] += h[3:3 + D]
+            sum2[:] += h[3 + D:3 + 2 * D]
             nstat += 1
             if adapter is not None and it < adaptIterations:
-                self.stepSize = adapter.update(u["meanAcceptProb"])
+                self.stepSize = adapter.update(acc_prob)
                 self.integrator.stepSize = self.stepSize
                 self.integrator.numSteps = int(self.simulTime / self.stepSize)  # src/integrator.py:51
 
         for it in range(numIterations):
-            buf = stats[it & 1]
+            slot = it & 1
             out["stepSize"].append(self.stepSize)
-            self.step(temperature, stats=buf if collectStats else None)
+            out["numSteps"].append(self.integrator.numSteps)
+            self.step(temperature, stats=stats[slot] if collectStats else None)
             if trace is not None:
                 trace[:, :, it] = ens.q[:, :traceParticles]
             if collectStats:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    reducer.reduce(stats[slot])
+                    hosts[slot].copy_(stats[slot], non_blocking=True)
+                    done[slot].record(side)
                 if pending is not None:
                     consume(*pending)  # statistics of the PREVIOUS iteration (one iteration stale)
-                reducer.reduce_async(buf)
-                pending = (buf, it)
+                pending = (slot, it)
         if pending is not None:
             consume(*pending)
+        main.wait_stream(side)
+        sum1 = torch.from_numpy(sum1)
+        sum2 = torch.from_numpy(sum2)
         n = max(nstat, 1) * Ptot
         mean = sum1 / n
         out.update(mean=mean, var=sum2 / n - mean * mean, trace=trace, worldSize=world)

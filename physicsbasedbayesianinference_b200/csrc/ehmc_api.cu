@@ -198,6 +198,9 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
       for (int i = 0; i < 62 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[63]);
       fprintf(stderr, "\n");
     }
+  } else if (!strcmp(name, "small_waves")) {
+    if (!(value >= 1 && value <= 1e6)) return fail(EHMC_ERR_INVALID, "small_waves must be in [1, 1e6]");
+    c->small_waves = (int)value;
   } else if (!strcmp(name, "tc_debug")) {
     c->tc_debug = (int)value;
   } else if (!strcmp(name, "host_chunk_mb")) {
@@ -530,7 +533,9 @@ static long long traj_blocks(const ehmc_ctx* c, const ehmc_potential* p, long lo
 template <typename T>
 static int launch_traj(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc,
                        cudaStream_t st, int slot = 0) {
+  c->last_rows = 0;
   if (A.P == 0) return EHMC_OK;
+  c->last_rows = traj_blocks<T>(c, p, A.P, integ);  // upper bound == exact for every kernel but the persistent k_small
   if (p->family == EHMC_FAMILY_NBODY) return launch_nbody<T>(c, p, A, integ, hmc, st);
   if (p->family == EHMC_FAMILY_LOGISTIC) return launch_logistic<T>(c, p, A, integ, hmc, st, slot);
   if constexpr (sizeof(T) == 4) {
@@ -597,6 +602,7 @@ static int run_device(ehmc_ctx* c, const ehmc_potential* pot, IterArgs<T> A, int
   }
   TRY(launch_traj<T>(c, pot, A, integ, hmc, st));
   if (stats_dev != nullptr && A.P > 0) {
+    if (!pps) nblk = c->last_rows;
     k_stats_finalize<<<NS, 256, 0, st>>>(A.partials, (int)nblk, NS, stats_dev);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -625,13 +631,8 @@ static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, 
   const size_t slab_elems = 3 * arr + 2 * (size_t)chunk;
   const size_t slab_bytes = slab_elems * sizeof(T) + (size_t)chunk + 64;
   for (int i = 0; i < N_STAGE; ++i) TRY(c->stage[i].ensure(slab_bytes));
-  long long blocks_total = 0;
-  std::vector<long long> blk_off((size_t)nchunks + 1, 0);
-  for (long long k = 0; k < nchunks; ++k) {
-    const long long n = std::min(chunk, P - k * chunk);
-    blk_off[k] = blocks_total;
-    blocks_total += traj_blocks<T>(c, pot, n, integ);
-  }
+  long long blocks_total = 0;  // upper bound of the statistics rows (exact count: rows_done below)
+  for (long long k = 0; k < nchunks; ++k) blocks_total += traj_blocks<T>(c, pot, std::min(chunk, P - k * chunk), integ);
   const bool pps = per_particle_stats(pot);
   if (v.has_stats) {
     // fused families: one row of NS sums per CTA.  per-particle families: [P][3] rows in pstats plus
@@ -641,6 +642,7 @@ static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, 
     TRY(c->stage_stats.ensure(sizeof(double) * NS));
   }
   const size_t es = sizeof(T);
+  long long rows_done = 0;  // statistics rows written so far (fused families)
   for (long long k = 0; k < nchunks; ++k) {
     const int s = (int)(k % N_STAGE);
     cudaStream_t st = c->streams[s];
@@ -677,8 +679,9 @@ static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, 
     else if (pps)
       A.partials = static_cast<double*>(c->pstats.ptr) + (size_t)c0 * 3;
     else
-      A.partials = static_cast<double*>(c->partials.ptr) + (size_t)blk_off[k] * NS;
+      A.partials = static_cast<double*>(c->partials.ptr) + (size_t)rows_done * NS;
     TRY(launch_traj<T>(c, pot, A, integ, hmc, st, s));
+    rows_done += c->last_rows;
     if (v.has_stats && pps) {
       double* row = static_cast<double*>(c->partials.ptr) + (size_t)k * NS;
       CUDA_TRY(cudaMemsetAsync(row, 0, sizeof(double) * 3, st));
@@ -692,7 +695,7 @@ static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, 
   for (int i = 0; i < N_STAGE; ++i) CUDA_TRY(cudaStreamSynchronize(c->streams[i]));
   if (v.has_stats) {
     cudaStream_t st = c->streams[0];
-    k_stats_finalize<<<NS, 256, 0, st>>>(static_cast<double*>(c->partials.ptr), (int)(pps ? nchunks : blocks_total), NS,
+    k_stats_finalize<<<NS, 256, 0, st>>>(static_cast<double*>(c->partials.ptr), (int)(pps ? nchunks : rows_done), NS,
                                          static_cast<double*>(c->stage_stats.ptr));
     c->launches++;
     if (pps) {

@@ -43,6 +43,7 @@ struct ehmc_ctx {
   int device = 0;
   cudaDeviceProp prop;
   uint64_t launches = 0;
+  long long last_rows = 0;  // rows of statistics partials the last trajectory launch wrote
   DevBuf partials;        // block partial sums for the statistics
   DevBuf stage[N_STAGE];  // host path staging (one slab per in-flight chunk)
   DevBuf stage_stats;
@@ -50,6 +51,7 @@ struct ehmc_ctx {
   DevBuf uf[N_STAGE];     // scratch of the unfused path: w, v, g [D][P] + K0, U0, U1 [P]
   cudaStream_t streams[N_STAGE] = {nullptr, nullptr, nullptr};
   // tuning options (ehmc_ctx_set_option)
+  int small_waves = 8;            // k_small grid = this many resident waves of CTAs (grid-stride over particles)
   int dense_occupancy = 2;        // CTAs/SM the float32 dense kernel is compiled for (1 or 2)
   int dense_path = 0;             // 0 auto (3xFP16 tensor cores when eligible), 1 CUDA cores (exact fp32 FMA),
                                   // 2 / 3 the 3xTF32 kernels (one tile SS / two tiles TS), 4 force 3xFP16

@@ -1,6 +1,8 @@
 // Instantiations of the small-D fused kernels for one dtype (included by inst_small_f32/f64.cu).
 #pragma once
 
+#include <algorithm>
+
 #include "host_defs.h"
 #include "k_misc.cuh"
 #include "k_small.cuh"
@@ -30,23 +32,46 @@ static FunnelPot<T, DT> make_funnel(const ehmc_potential* p) {
   return f;
 }
 
+// `small_waves` resident waves of CTAs (the kernel walks the particles with a grid-stride loop)
+template <class K>
+static int small_grid(ehmc_ctx* c, K kernel, size_t sm, long long P, unsigned* grid) {
+  int occ = 0;
+  if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, K1_THREADS, sm));
+  const long long need = (P + K1_THREADS - 1) / K1_THREADS;
+  const long long wave = (long long)std::max(occ, 1) * c->prop.multiProcessorCount;
+  // measured at config 5 (profiles/k1_probe.py): without statistics 4+ waves are ~8 % faster than one
+  // (CTAs drift out of lockstep); with statistics the per-CTA reduction favours few, long-lived CTAs
+  const int waves = sm > 0 ? std::min(2, c->small_waves) : c->small_waves;
+  *grid = (unsigned)std::max<long long>(1, std::min<long long>(need, wave * std::max(1, waves)));
+  return EHMC_OK;
+}
+
 template <typename T, int DT, class Pot>
 static int launch_small_pot(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, int integ, bool hmc, cudaStream_t st) {
   static_assert(K1_THREADS == K1_THREADS_HOST, "K1 block size");
-  const unsigned grid = (unsigned)((A.P + K1_THREADS - 1) / K1_THREADS);
-  const size_t sm = A.partials != nullptr ? sizeof(double) * (K1_THREADS / 32) * (2 * A.D + 3) : 0;
+  // statistics: per-thread accumulators [2DT+3][128] + per-warp rows [4][2DT+3] (doubles)
+  const size_t sm = A.partials != nullptr ? sizeof(double) * (K1_THREADS + K1_THREADS / 32) * (2 * DT + 3) : 0;
+  unsigned grid = 1;
   if (hmc) {
-    if (integ == INTEG_LEAPFROG)
+    if (integ == INTEG_LEAPFROG) {
+      TRY(small_grid(c, k_small<T, DT, Pot, INTEG_LEAPFROG, true>, sm, A.P, &grid));
       k_small<T, DT, Pot, INTEG_LEAPFROG, true><<<grid, K1_THREADS, sm, st>>>(A, pot);
-    else
+    } else {
+      TRY(small_grid(c, k_small<T, DT, Pot, INTEG_STORMER, true>, sm, A.P, &grid));
       k_small<T, DT, Pot, INTEG_STORMER, true><<<grid, K1_THREADS, sm, st>>>(A, pot);
+    }
   } else {
-    if (integ == INTEG_LEAPFROG)
+    if (integ == INTEG_LEAPFROG) {
+      TRY(small_grid(c, k_small<T, DT, Pot, INTEG_LEAPFROG, false>, sm, A.P, &grid));
       k_small<T, DT, Pot, INTEG_LEAPFROG, false><<<grid, K1_THREADS, sm, st>>>(A, pot);
-    else
+    } else {
+      TRY(small_grid(c, k_small<T, DT, Pot, INTEG_STORMER, false>, sm, A.P, &grid));
       k_small<T, DT, Pot, INTEG_STORMER, false><<<grid, K1_THREADS, sm, st>>>(A, pot);
+    }
   }
   c->launches++;
+  c->last_rows = grid;  // statistics partials: one row per CTA actually launched
   CUDA_TRY(cudaGetLastError());
   return EHMC_OK;
 }

@@ -110,6 +110,35 @@ __device__ __forceinline__ T integrate_regs(const Pot& pot, T (&q)[DT], T (&p)[D
                                             bool wantE, T* U0) {
   typedef Ar<T> R;
   const T inv_m = T(1) / m;
+  if constexpr (sizeof(T) == 4 && INTEG == INTEG_LEAPFROG) {
+    // float32: the same recurrence in kick-drift-kick form (v_half = v + a h / 2 ; q += h v_half ;
+    // v = v_half + a' h / 2, consecutive half kicks merged): 2 FFMA per dimension and step instead of
+    // the 8 operations of the reference's expression order, which only the float64 mode reproduces
+    // bit for bit.  Differs from it by rounding only (tolerance 1e-5, north_star).
+    T g[DT];
+    T (&v)[DT] = p;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) v[d] *= inv_m;
+    *U0 = pot.grad(q, g, wantE);
+    T Uend = *U0;
+    const T hm = h * inv_m, hmh = T(0.5) * hm;
+    if (L > 0) {
+#pragma unroll
+      for (int d = 0; d < DT; ++d) v[d] = fmaf(-hmh, g[d], v[d]);
+    }
+    for (int j = 0; j < L; ++j) {
+#pragma unroll
+      for (int d = 0; d < DT; ++d) q[d] = fmaf(h, v[d], q[d]);
+      const bool last = j == L - 1;
+      Uend = pot.grad(q, g, wantE && last);
+      const T ck = last ? hmh : hm;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) v[d] = fmaf(-ck, g[d], v[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < DT; ++d) p[d] = v[d] * m;
+    return Uend;
+  }
   T a[DT], g[DT];
   T Uend;
   // v = p / m                                   integrator.py:106 / :143
@@ -175,120 +204,145 @@ __device__ __forceinline__ T kinetic(const T (&p)[DT], T m, T inv_m) {
   return Ar<T>::divm(Ar<T>::mul(T(0.5), s), m, inv_m);
 }
 
-// Block-level partial sums of NS values -> partials[blockIdx.x * NS + j].
-// Each thread contributes vals via the callback `get(j)`.
-template <int NTHREADS, class F>
-__device__ __forceinline__ void block_partials(double* out, int NS, double* smem /*[NTHREADS/32][NS]*/, F get) {
+// Block-level reduction of the per-thread statistics accumulators -> one row of partials.
+// Accumulators live in shared memory, sacc[j][thread] (registers are better spent on occupancy):
+// j in [0..2] scalars, [3 .. 3+DT) sum q_d, [3+DT .. 3+2DT) sum q_d^2 (DT = padded D);
+// output row layout uses the true D: [0..2], [3 .. 3+D), [3+D .. 3+2D).
+template <int NTHREADS, int DT>
+__device__ __forceinline__ void block_partials(double* out_row, int D, const double* sacc /*[2DT+3][NTHREADS]*/,
+                                               double* sred /*[NTHREADS/32][2DT+3]*/) {
+  constexpr int NA = 2 * DT + 3;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int j = 0; j < NS; ++j) {
-    const double s = warp_sum(get(j));
-    if (lane == 0) smem[w * NS + j] = s;
+#pragma unroll 1
+  for (int j = 0; j < NA; ++j) {
+    const double s = warp_sum(sacc[j * NTHREADS + threadIdx.x]);
+    if (lane == 0) sred[w * NA + j] = s;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < NS; j += NTHREADS) {
+  for (int j = threadIdx.x; j < NA; j += NTHREADS) {
     double s = 0.0;
 #pragma unroll
-    for (int ww = 0; ww < NTHREADS / 32; ++ww) s += smem[ww * NS + j];
-    out[(size_t)blockIdx.x * NS + j] = s;
+    for (int ww = 0; ww < NTHREADS / 32; ++ww) s += sred[ww * NA + j];
+    int o = j;
+    if (j >= 3 + DT) {
+      const int d = j - 3 - DT;
+      o = d < D ? 3 + D + d : -1;
+    } else if (j >= 3) {
+      o = (j - 3) < D ? j : -1;
+    }
+    if (o >= 0) out_row[o] = s;
   }
 }
 
 // ---------------------------------------------------------------------------
 // Kernel.  HMC = false: Leapfrog/StormerVerlet.integrate on (q, p) in place.
 //          HMC = true : one full iteration of HMC.getSamples' loop body.
+// Persistent: the grid is one resident wave of CTAs and every thread walks particles
+// i, i + gridDim * 128, ...  so that the ensemble statistics (2D+3 sums) are accumulated per
+// thread (in shared memory) and reduced across the block ONCE per launch (a per-particle block reduction of 23
+// doubles cost 3x the trajectory itself at config 5).
 // ---------------------------------------------------------------------------
 template <typename T, int DT, class Pot, int INTEG, bool HMC>
 __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> A, const Pot pot) {
   extern __shared__ double k1_smem[];
-  const long long i = (long long)blockIdx.x * K1_THREADS + threadIdx.x;
-  const bool active = i < A.P;
-  const long long ic = active ? i : 0;  // inactive threads shadow particle 0, never store
-
-  T q[DT], p[DT];
-  const T m = A.mass[ic];
-#pragma unroll
-  for (int d = 0; d < DT; ++d) q[d] = d < A.D ? A.q[d * A.q_ld + ic] : T(0);
-
-  T pstd = T(0);
-  if (HMC) {
-    pstd = momentum_std<T>(m, A.kB, A.temp, A.pscale);
-    draw_momentum<T, DT>(A, ic, pstd, p);
-  } else {
-#pragma unroll
-    for (int d = 0; d < DT; ++d) p[d] = d < A.D ? A.p[d * A.p_ld + ic] : T(0);
+  constexpr int NA = 2 * DT + 3;
+  const bool want_stats = HMC && A.partials != nullptr;
+  double* sacc = k1_smem + threadIdx.x;          // [NA][K1_THREADS], this thread's column
+  double* sred = k1_smem + NA * K1_THREADS;      // [K1_THREADS / 32][NA]
+  if (want_stats) {
+#pragma unroll 1
+    for (int j = 0; j < NA; ++j) sacc[j * K1_THREADS] = 0.0;
   }
+  const long long stride = (long long)gridDim.x * K1_THREADS;
 
-  T K0 = T(0);
-  const T inv_m = T(1) / m;
-  if (HMC) K0 = kinetic<T, DT>(p, m, inv_m);
-  T U0;
-  const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, A.h, A.h2, A.L, HMC, &U0);
+  for (long long base = (long long)blockIdx.x * K1_THREADS; base < A.P; base += stride) {
+    const long long i = base + threadIdx.x;
+    const bool active = i < A.P;
+    const long long ic = active ? i : 0;  // inactive threads shadow particle 0, never store
 
-  if (!HMC) {
-    if (active) {
+    T q[DT], p[DT];
+    const T m = A.mass[ic];
 #pragma unroll
-      for (int d = 0; d < DT; ++d)
-        if (d < A.D) {
-          A.q[d * A.q_ld + i] = q[d];
-          A.p[d * A.p_ld + i] = p[d];
-        }
+    for (int d = 0; d < DT; ++d) q[d] = d < A.D ? A.q[d * A.q_ld + ic] : T(0);
+
+    T pstd = T(0);
+    if (HMC) {
+      pstd = momentum_std<T>(m, A.kB, A.temp, A.pscale);
+      draw_momentum<T, DT>(A, ic, pstd, p);
+    } else {
+#pragma unroll
+      for (int d = 0; d < DT; ++d) p[d] = d < A.D ? A.p[d * A.p_ld + ic] : T(0);
     }
-    return;
-  }
 
-  const T oldH = Ar<T>::add(K0, U0);
-  const T newH = Ar<T>::add(kinetic<T, DT>(p, m, inv_m), U1);  // dot(-p,-p) == dot(p,p), HMC.py:164
-  T u;
-  if (A.u != nullptr)
-    u = A.u[ic];
-  else
-    u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)ic);
-  T accp;
-  const bool rej = metropolis_reject<T>(oldH, newH, u, A.flags, &accp);
+    T K0 = T(0);
+    const T inv_m = T(1) / m;
+    if (HMC) K0 = kinetic<T, DT>(p, m, inv_m);
+    T U0;
+    const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, A.h, A.h2, A.L, HMC, &U0);
 
-  if (active) {
-    if (!rej) {
+    if (!HMC) {
+      if (active) {
 #pragma unroll
-      for (int d = 0; d < DT; ++d)
-        if (d < A.D) A.q[d * A.q_ld + i] = q[d];  // HMC.py:175 (rejected: q in HBM is still oldQ)
-    }
-    if (A.p != nullptr) {
-      if (rej) {
-        if (A.flags & FLAG_BUGCOMPAT) {
-#pragma unroll
-          for (int d = 0; d < DT; ++d) p[d] = d < A.D ? A.q[d * A.q_ld + i] : T(0);  // HMC.py:176 (sic)
-        } else {
-          draw_momentum<T, DT>(A, i, pstd, p);  // oldP
-        }
+        for (int d = 0; d < DT; ++d)
+          if (d < A.D) {
+            A.q[d * A.q_ld + i] = q[d];
+            A.p[d * A.p_ld + i] = p[d];
+          }
       }
-#pragma unroll
-      for (int d = 0; d < DT; ++d)
-        if (d < A.D) A.p[d * A.p_ld + i] = p[d];  // un-flipped, HMC.py:164,179
+      continue;
     }
-    if (A.accept != nullptr) A.accept[i] = rej ? 0 : 1;
-  }
 
-  if (A.partials != nullptr) {
-    // kept state for the statistics
-    if (rej) {
+    const T oldH = Ar<T>::add(K0, U0);
+    const T newH = Ar<T>::add(kinetic<T, DT>(p, m, inv_m), U1);  // dot(-p,-p) == dot(p,p), HMC.py:164
+    T u;
+    if (A.u != nullptr)
+      u = A.u[ic];
+    else
+      u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)ic);
+    T accp;
+    const bool rej = metropolis_reject<T>(oldH, newH, u, A.flags, &accp);
+
+    if (active) {
+      if (!rej) {
 #pragma unroll
-      for (int d = 0; d < DT; ++d) q[d] = d < A.D ? A.q[d * A.q_ld + ic] : T(0);
+        for (int d = 0; d < DT; ++d)
+          if (d < A.D) A.q[d * A.q_ld + i] = q[d];  // HMC.py:175 (rejected: q in HBM is still oldQ)
+      }
+      if (A.p != nullptr) {
+        if (rej) {
+          if (A.flags & FLAG_BUGCOMPAT) {
+#pragma unroll
+            for (int d = 0; d < DT; ++d) p[d] = d < A.D ? A.q[d * A.q_ld + i] : T(0);  // HMC.py:176 (sic)
+          } else {
+            draw_momentum<T, DT>(A, i, pstd, p);  // oldP
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < DT; ++d)
+          if (d < A.D) A.p[d * A.p_ld + i] = p[d];  // un-flipped, HMC.py:164,179
+      }
+      if (A.accept != nullptr) A.accept[i] = rej ? 0 : 1;
     }
-    const double w = active ? 1.0 : 0.0;
-    const double hk = (double)(rej ? oldH : newH);
-    const int D = A.D;
-    block_partials<K1_THREADS>(A.partials, 2 * D + 3, k1_smem, [&](int j) -> double {
-      if (j == 0) return w * (rej ? 0.0 : 1.0);
-      if (j == 1) return w * (double)accp;
-      if (j == 2) return w * hk;
-      const int d = (j - 3) % D;
-      double qd = 0.0;
+
+    if (want_stats && active) {
+      // kept state for the statistics
+      if (rej) {
 #pragma unroll
-      for (int dd = 0; dd < DT; ++dd)
-        if (dd == d) qd = (double)q[dd];
-      return w * ((j - 3) < D ? qd : qd * qd);
-    });
+        for (int d = 0; d < DT; ++d) q[d] = d < A.D ? A.q[d * A.q_ld + i] : T(0);
+      }
+      sacc[0 * K1_THREADS] += rej ? 0.0 : 1.0;
+      sacc[1 * K1_THREADS] += (double)accp;
+      sacc[2 * K1_THREADS] += (double)(rej ? oldH : newH);
+#pragma unroll
+      for (int d = 0; d < DT; ++d) {
+        const double qd = (double)q[d];
+        sacc[(3 + d) * K1_THREADS] += qd;
+        sacc[(3 + DT + d) * K1_THREADS] = fma(qd, qd, sacc[(3 + DT + d) * K1_THREADS]);
+      }
+    }
   }
+  if (want_stats)
+    block_partials<K1_THREADS, DT>(A.partials + (size_t)blockIdx.x * (2 * A.D + 3), A.D, k1_smem, sred);
 }
 
 }  // namespace ehmc

@@ -5,8 +5,8 @@ Particles are independent (src/integrator.py:105-120 reads only column i; the ac
 src/HMC.py:173-176 is per particle), so the data path needs NO collective.  Only the
 per-iteration ensemble statistics vector of ehmc_hmc_iter (2D+3 float64 sums: n_accept,
 sum acceptance probability, sum H, sum q_d, sum q_d^2) crosses GPUs, through one all-reduce
-that is issued asynchronously and consumed one iteration late, so its ~10-20 us latency is
-off the critical path.
+that is issued on a side stream and consumed one iteration late, so its ~10-20 us latency (and the
+device-to-host copy of the reduced vector) is off the critical path.
 """
 from __future__ import annotations
 
@@ -38,6 +38,12 @@ class StatsReducer:
     def reduce_async(self, stats):
         if self.enabled:
             self.work = self.dist.all_reduce(stats, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return stats
+
+    def reduce(self, stats):
+        """In-place all-reduce ordered on the CURRENT stream (the host does not block with NCCL)."""
+        if self.enabled:
+            self.dist.all_reduce(stats, op=self.dist.ReduceOp.SUM, group=self.group)
         return stats
 
     def wait(self):
