@@ -299,7 +299,7 @@ def main():
     adaptive = args.config.startswith("c5")  # config 5: ensemble statistics all-reduced every iteration
     group = dist.group.WORLD if world > 1 else None
     if adaptive:
-        hmc.run(args.warmup, 1 / KB, adapt=True, group=group)
+        hmc.run(args.warmup, 1 / KB, adapt=True, group=group, keepNumSteps=True)
     else:
         for _ in range(args.warmup):
             hmc.step(1 / KB)
@@ -311,7 +311,7 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
     if adaptive:
-        run_out = hmc.run(args.steps, 1 / KB, adapt=True, group=group)
+        run_out = hmc.run(args.steps, 1 / KB, adapt=True, group=group, keepNumSteps=True)
         for i in range(args.steps):
             ev[i + 1] = ev[0]
         ev[-1] = torch.cuda.Event(enable_timing=True)

@@ -187,7 +187,7 @@ class HMC:
 
     # ------------------------------------------------------------------------------------
     def run(self, numIterations, temperature, *, adapt=False, targetAccept=0.8, adaptIterations=None,
-            traceParticles=0, group=None, collectStats=True):
+            traceParticles=0, group=None, collectStats=True, keepNumSteps=False):
         """Production loop for device ensembles (build-defined; scales where getSamples'
         (D, P, S) arrays cannot, SURVEY.md section 7 hard part 7).
 
@@ -196,6 +196,10 @@ class HMC:
         same launch, all-reduced across the ranks of `group` asynchronously and consumed one
         iteration late (step-size adaptation, running moments).  Positions of the first
         `traceParticles` local particles are kept for ESS estimation.
+
+        Adaptation changes the step size; by default the trajectory LENGTH simulTime stays fixed and
+        numSteps = int(simulTime / stepSize) follows (src/integrator.py:51).  keepNumSteps=True keeps
+        the number of leapfrog steps instead (simulTime = numSteps * stepSize follows).
 
         Returns dict(acceptRate[S], meanAcceptProb[S], meanH[S], stepSize[S], mean[D], var[D],
         trace (D, traceParticles, S) or None).
@@ -251,7 +255,10 @@ class HMC:
             if adapter is not None and it < adaptIterations:
                 self.stepSize = adapter.update(acc_prob)
                 self.integrator.stepSize = self.stepSize
-                self.integrator.numSteps = int(self.simulTime / self.stepSize)  # src/integrator.py:51
+                if keepNumSteps:
+                    self.simulTime = self.integrator.finalTime = self.integrator.numSteps * self.stepSize
+                else:
+                    self.integrator.numSteps = int(self.simulTime / self.stepSize)  # src/integrator.py:51
 
         for it in range(numIterations):
             slot = it & 1

@@ -201,6 +201,9 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
   } else if (!strcmp(name, "small_waves")) {
     if (!(value >= 1 && value <= 1e6)) return fail(EHMC_ERR_INVALID, "small_waves must be in [1, 1e6]");
     c->small_waves = (int)value;
+  } else if (!strcmp(name, "nbody_ti")) {
+    if (value != 0 && value != 4 && value != 8) return fail(EHMC_ERR_INVALID, "nbody_ti must be 0, 4 or 8");
+    c->nbody_ti = (int)value;
   } else if (!strcmp(name, "tc_debug")) {
     c->tc_debug = (int)value;
   } else if (!strcmp(name, "host_chunk_mb")) {

@@ -52,6 +52,7 @@ struct ehmc_ctx {
   cudaStream_t streams[N_STAGE] = {nullptr, nullptr, nullptr};
   // tuning options (ehmc_ctx_set_option)
   int small_waves = 8;            // k_small grid = this many resident waves of CTAs (grid-stride over particles)
+  int nbody_ti = 0;               // bodies per thread of k_nbody: 0 auto, 4 or 8
   int dense_occupancy = 2;        // CTAs/SM the float32 dense kernel is compiled for (1 or 2)
   int dense_path = 0;             // 0 auto (3xFP16 tensor cores when eligible), 1 CUDA cores (exact fp32 FMA),
                                   // 2 / 3 the 3xTF32 kernels (one tile SS / two tiles TS), 4 force 3xFP16

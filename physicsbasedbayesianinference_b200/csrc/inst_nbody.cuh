@@ -5,9 +5,9 @@
 
 namespace ehmc {
 
-static int nbody_threads(int B) {
+static int nbody_threads(int B, int ti) {
   int nt = 32;
-  while (nt * NB_TI < B && nt < 1024) nt <<= 1;
+  while (nt * ti < B && nt < 1024) nt <<= 1;
   return nt;
 }
 
@@ -21,26 +21,35 @@ static NBodyArgs<T> nbody_args(const ehmc_potential* p) {
   return pa;
 }
 
-template <typename T>
-int launch_nbody(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st) {
-  const int B = p->B, nt = nbody_threads(B);
-  if (nt * NB_TI < B) return fail(EHMC_ERR_UNSUPPORTED, "nbody: B = %d > %d bodies", B, 1024 * NB_TI);
-  const size_t sm = (size_t)B * 4 * sizeof(T) + 40 * sizeof(T);
+template <typename T, int TI>
+static int launch_nbody_ti(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc,
+                           cudaStream_t st) {
+  const int B = p->B, nt = nbody_threads(B, TI);
+  if (nt * TI < B) return fail(EHMC_ERR_UNSUPPORTED, "nbody: B = %d > %d bodies", B, 1024 * TI);
+  const size_t sm = (size_t)B * BodyRec<T>::VECS * 4 * sizeof(T) + 40 * sizeof(T);
   if (sm > 227 * 1024) return fail(EHMC_ERR_UNSUPPORTED, "nbody: B = %d needs %zu B shared memory", B, sm);
   const NBodyArgs<T> pa = nbody_args<T>(p);
   const bool eps0 = p->scalars[1] == 0.0;
   void (*k)(const IterArgs<T>, const NBodyArgs<T>, const int, const int);
   if (nt <= 128)
-    k = eps0 ? k_nbody<T, true, 128> : k_nbody<T, false, 128>;
+    k = eps0 ? k_nbody<T, true, 128, TI> : k_nbody<T, false, 128, TI>;
   else if (nt <= 512)
-    k = eps0 ? k_nbody<T, true, 512> : k_nbody<T, false, 512>;
+    k = eps0 ? k_nbody<T, true, 512, TI> : k_nbody<T, false, 512, TI>;
   else
-    k = eps0 ? k_nbody<T, true, 1024> : k_nbody<T, false, 1024>;
+    k = eps0 ? k_nbody<T, true, 1024, TI> : k_nbody<T, false, 1024, TI>;
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   k<<<(unsigned)A.P, nt, sm, st>>>(A, pa, integ, hmc ? 1 : 0);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return EHMC_OK;
+}
+
+template <typename T>
+int launch_nbody(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st) {
+  // 4 bodies per thread (twice the warps per SM) while that covers B, else 8
+  const int ti = c->nbody_ti ? c->nbody_ti : (p->B <= 4096 ? 4 : 8);
+  if (ti == 4 && p->B <= 4096) return launch_nbody_ti<T, 4>(c, p, A, integ, hmc, st);
+  return launch_nbody_ti<T, 8>(c, p, A, integ, hmc, st);
 }
 
 template <typename T>

@@ -7,7 +7,7 @@
 //    potential sign as samples/NBody/MiscFunctions.py:163-169)
 //
 // One CTA per ensemble particle.  The B bodies' positions (x, y, z, m) live in shared
-// memory as 16/32-byte vectors; every thread owns up to 8 bodies (positions, velocities
+// memory as 16/32-byte vectors; every thread owns 4 or 8 bodies (positions, velocities
 // and force accumulators in registers) and sweeps all j through shared-memory
 // broadcasts: one LDS.128 feeds 8 pair interactions (~13 issue slots each, one MUFU.RSQ).
 // Per trajectory the all-pairs sweep runs L+1 times without touching HBM; HBM traffic is
@@ -15,12 +15,14 @@
 // Coordinates are flattened component-major, d = c*B + b (src/potential.py:83-84).
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "k_dense.cuh"  // one_normal
 
 namespace ehmc {
 
-constexpr int NB_TI = 8;  // bodies per thread
+constexpr int NB_TI_MAX = 8;  // bodies per thread: 8, or 4 when that still covers B with <= 1024 threads
 
 template <typename T>
 struct NBodyArgs {
@@ -45,6 +47,61 @@ struct V4<double> {
   }
 };
 
+// ---- packed float32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: two lanes of work per issue slot) ----
+// Measured (profiles/microbench/op_rates.cu): the packed instructions issue at 0.5 / clk / SM
+// sub-partition, i.e. the same flop rate as the scalar ones for HALF the issue slots -- the
+// all-pairs loop is issue bound in scalar form (13 slots + loop overhead per interaction against
+// 12 cycles of FMA pipe), so packing two of a thread's bodies per instruction makes it pipe bound.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  return ((f32x2)__float_as_uint(hi) << 32) | (f32x2)__float_as_uint(lo);
+}
+__device__ __forceinline__ float pk_lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float pk_hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// bare MUFU.RSQ: rsqrtf() wraps it in a denormal-input rescue (FSETP + two predicated FMULs per call),
+// which squared distances never need
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// shared-memory record of one body: double (x, y, z, m); float (x, x, y, y)(z, z, m, m) -- every
+// component duplicated so that one LDS.128 delivers two ready-made packed operands
+template <typename T>
+struct BodyRec;
+template <>
+struct BodyRec<double> {
+  static constexpr int VECS = 1;
+  static __device__ __forceinline__ void store(double4* pos, int b, double x, double y, double z, double m) {
+    pos[b] = make_double4(x, y, z, m);
+  }
+};
+template <>
+struct BodyRec<float> {
+  static constexpr int VECS = 2;
+  static __device__ __forceinline__ void store(float4* pos, int b, float x, float y, float z, float m) {
+    pos[2 * b] = make_float4(x, x, y, y);
+    pos[2 * b + 1] = make_float4(z, z, m, m);
+  }
+};
+
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* red, int nwarps) {
 #pragma unroll
@@ -57,14 +114,14 @@ __device__ __forceinline__ T block_sum(T v, T* red, int nwarps) {
   return s;
 }
 
-template <typename T, bool EPS0, int NTMAX>
+template <typename T, bool EPS0, int NTMAX, int NB_TI>
 __global__ void __launch_bounds__(NTMAX) k_nbody(const IterArgs<T> A, const NBodyArgs<T> pa, const int integ,
                                                 const int hmc) {
   typedef typename V4<T>::type Vec;
   extern __shared__ __align__(32) unsigned char k3_smem_raw[];
   const int B = pa.B, NT = blockDim.x, tid = threadIdx.x, nwarps = NT >> 5;
-  Vec* pos = reinterpret_cast<Vec*>(k3_smem_raw);  // [B] (x, y, z, m)
-  T* red = reinterpret_cast<T*>(pos + B);          // [32] + 2 broadcast slots
+  Vec* pos = reinterpret_cast<Vec*>(k3_smem_raw);                 // [B] body records (BodyRec)
+  T* red = reinterpret_cast<T*>(pos + BodyRec<T>::VECS * B);      // [32] + 2 broadcast slots
   const long long part = blockIdx.x;
   const T M = A.mass[part], inv_M = T(1) / M;
   const T G = pa.G, eps2 = pa.eps2;
@@ -83,7 +140,7 @@ __global__ void __launch_bounds__(NTMAX) k_nbody(const IterArgs<T> A, const NBod
     bm[s] = own[s] ? pa.bmass[body[s]] : T(0);
 #pragma unroll
     for (int c = 0; c < 3; ++c) x[s][c] = own[s] ? A.q[((long long)c * B + body[s]) * A.q_ld + part] : T(0);
-    if (own[s]) pos[body[s]] = V4<T>::make(x[s][0], x[s][1], x[s][2], bm[s]);
+    if (own[s]) BodyRec<T>::store(pos, body[s], x[s][0], x[s][1], x[s][2], bm[s]);
   }
 
   // ---- momentum ---------------------------------------------------------------------
@@ -141,28 +198,90 @@ __global__ void __launch_bounds__(NTMAX) k_nbody(const IterArgs<T> A, const NBod
 
   // ---- all-pairs sweep: f[s] = sum_j m_j (r_j - r_i) / r^3 ; pot[s] = sum_j m_j / r -------
   T f[NB_TI][3], pot[NB_TI];
-  auto sweep = [&](bool wantE) {
+  auto sweep_scalar = [&](bool wantE) {
 #pragma unroll
     for (int s = 0; s < NB_TI; ++s) {
       f[s][0] = f[s][1] = f[s][2] = T(0);
       pot[s] = T(0);
     }
+    if constexpr (sizeof(T) == 8) {
 #pragma unroll 2
-    for (int j = 0; j < B; ++j) {
-      const Vec pj = pos[j];
+      for (int j = 0; j < B; ++j) {
+        const Vec pj = pos[j];
 #pragma unroll
-      for (int s = 0; s < NB_TI; ++s) {
-        const T dx = pj.x - x[s][0], dy = pj.y - x[s][1], dz = pj.z - x[s][2];
-        const T r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
-        T inv = Ar<T>::rsqrt_(r2);
-        if (EPS0) inv = r2 > T(0) ? inv : T(0);  // self pair / coincident bodies contribute nothing
-        const T mi = pj.w * inv;
-        const T w3 = mi * inv * inv;
-        f[s][0] = fma(dx, w3, f[s][0]);
-        f[s][1] = fma(dy, w3, f[s][1]);
-        f[s][2] = fma(dz, w3, f[s][2]);
-        if (wantE) pot[s] += mi;
+        for (int s = 0; s < NB_TI; ++s) {
+          const T dx = pj.x - x[s][0], dy = pj.y - x[s][1], dz = pj.z - x[s][2];
+          const T r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, eps2)));
+          T inv = Ar<T>::rsqrt_(r2);
+          if (EPS0) inv = r2 > T(0) ? inv : T(0);  // self pair / coincident bodies contribute nothing
+          const T mi = pj.w * inv;
+          const T w3 = mi * inv * inv;
+          f[s][0] = fma(dx, w3, f[s][0]);
+          f[s][1] = fma(dy, w3, f[s][1]);
+          f[s][2] = fma(dz, w3, f[s][2]);
+          if (wantE) pot[s] += mi;
+        }
       }
+    }
+  };
+  // float32: slots (2k, 2k+1) of a thread ride in one packed register pair
+  auto sweep_packed = [&](auto wantE_tag) {
+    constexpr bool wantE = decltype(wantE_tag)::value;
+    if constexpr (sizeof(T) == 4) {
+      constexpr int NP2 = NB_TI / 2;
+      f32x2 X[NP2][3], F[NP2][3], PT[NP2];
+      const f32x2 m1 = pk2(-1.f, -1.f), e2 = pk2(eps2, eps2);
+#pragma unroll
+      for (int k = 0; k < NP2; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          X[k][c] = pk2(x[2 * k][c], x[2 * k + 1][c]);
+          F[k][c] = 0ull;
+        }
+        PT[k] = 0ull;
+      }
+      const ulonglong2* rec = reinterpret_cast<const ulonglong2*>(pos);
+#pragma unroll 2
+      for (int j = 0; j < B; ++j) {
+        const ulonglong2 a = rec[2 * j], b = rec[2 * j + 1];  // (xx, yy), (zz, mm)
+#pragma unroll
+        for (int k = 0; k < NP2; ++k) {
+          const f32x2 dx = fma2(X[k][0], m1, a.x), dy = fma2(X[k][1], m1, a.y), dz = fma2(X[k][2], m1, b.x);
+          const f32x2 r2 = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, e2)));
+          float i0 = rsqrt_ftz(pk_lo(r2)), i1 = rsqrt_ftz(pk_hi(r2));
+          if (EPS0) {  // self pair / coincident bodies contribute nothing
+            i0 = pk_lo(r2) > 0.f ? i0 : 0.f;
+            i1 = pk_hi(r2) > 0.f ? i1 : 0.f;
+          }
+          const f32x2 inv = pk2(i0, i1);
+          const f32x2 mi = mul2(b.y, inv);
+          const f32x2 w3 = mul2(mul2(mi, inv), inv);
+          F[k][0] = fma2(dx, w3, F[k][0]);
+          F[k][1] = fma2(dy, w3, F[k][1]);
+          F[k][2] = fma2(dz, w3, F[k][2]);
+          if (wantE) PT[k] = add2(PT[k], mi);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NP2; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          f[2 * k][c] = pk_lo(F[k][c]);
+          f[2 * k + 1][c] = pk_hi(F[k][c]);
+        }
+        pot[2 * k] = pk_lo(PT[k]);
+        pot[2 * k + 1] = pk_hi(PT[k]);
+      }
+    }
+  };
+  auto sweep = [&](bool wantE) {
+    if constexpr (sizeof(T) == 4) {
+      if (wantE)
+        sweep_packed(std::true_type{});
+      else
+        sweep_packed(std::false_type{});
+    } else {
+      sweep_scalar(wantE);
     }
   };
   // U = -0.5 G sum_i m_i (pot_i - self term)
@@ -178,7 +297,7 @@ __global__ void __launch_bounds__(NTMAX) k_nbody(const IterArgs<T> A, const NBod
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < NB_TI; ++s)
-      if (own[s]) pos[body[s]] = V4<T>::make(x[s][0], x[s][1], x[s][2], bm[s]);
+      if (own[s]) BodyRec<T>::store(pos, body[s], x[s][0], x[s][1], x[s][2], bm[s]);
     __syncthreads();
   };
 

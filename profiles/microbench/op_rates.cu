@@ -19,6 +19,10 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, float s
     u[i] = 0x3c003c00u + threadIdx.x + i;
   }
   const unsigned short one = 0x3c00, m1 = 0xbc00;
+  unsigned long long w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = ((unsigned long long)__float_as_uint(a[i]) << 32) | __float_as_uint(a[i] + 0.5f);
+  const unsigned long long wseed = ((unsigned long long)__float_as_uint(seed) << 32) | __float_as_uint(seed);
   long long t0 = clock64();
   for (int it = 0; it < ITER; ++it) {
 #pragma unroll
@@ -37,14 +41,18 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, float s
       if (OP == 11) asm volatile("fma.rn.f16x2 %0, %0, %1, %0;" : "+r"(u[i]) : "r"(0x3c003c00u));    // HFMA2
       if (OP == 12) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(seed));
       if (OP == 13) asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(u[i]) : "f"(a[i]));
-      if (OP == 14) asm volatile("{.reg .b64 t; mov.b64 t, {%0, %1}; fma.rn.f32x2 t, t, t, t; mov.b64 {%0, %1}, t;}" : "+f"(a[i]), "+f"(a[(i + 1) & 7]));  // FFMA2
+      if (OP == 14) asm volatile("fma.rn.f32x2 %0, %0, %1, %0;" : "+l"(w[i]) : "l"(wseed));  // FFMA2 (two FMAs per lane)
+      if (OP == 16) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[i]) : "l"(wseed));           // FADD2
+      if (OP == 17) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(w[i]) : "l"(wseed));           // FMUL2
+      if (OP == 18) asm volatile("rsqrt.approx.f32 %0, %0;" : "+f"(a[i]));                         // MUFU.RSQ
+      if (OP == 19) { asm volatile("rsqrt.approx.f32 %0, %0;" : "+f"(a[i])); asm volatile("fma.rn.f32x2 %0, %0, %1, %0;" : "+l"(w[i]) : "l"(wseed)); asm volatile("fma.rn.f32x2 %0, %0, %1, %0;" : "+l"(w[(i + 4) & 7]) : "l"(wseed)); }
       if (OP == 15) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(seed));
     }
   }
   long long t1 = clock64();
   float s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s += a[i] + __uint_as_float(u[i]);
+  for (int i = 0; i < 8; ++i) s += a[i] + __uint_as_float(u[i]) + __uint_as_float((uint32_t)w[i]) + __uint_as_float((uint32_t)(w[i] >> 32));
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -81,6 +89,10 @@ int main() {
   run<6>("F2FP chain", out, cyc);
   run<11>("HFMA2", out, cyc);
   run<14>("FFMA2 (fma.f32x2)", out, cyc);
+  run<16>("FADD2 (add.f32x2)", out, cyc);
+  run<17>("FMUL2 (mul.f32x2)", out, cyc);
+  run<18>("MUFU.RSQ", out, cyc);
+  run<19>("MUFU.RSQ + 2 FFMA2 (per 3 instr)", out, cyc);
   run<13>("cvt.rna.tf32", out, cyc);
   run<7>("LOP3", out, cyc);
   run<8>("PRMT", out, cyc);
