@@ -373,8 +373,8 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       p->use_tc = (nscalars == 2 && scalars[1] != 0.0) ? 1 : 0;
       if (rc == EHMC_OK && p->use_tc) {
         if (p->bits != 32) { rc = fail(EHMC_ERR_INVALID, "logistic: the tensor-core path needs float32 state"); break; }
-        // bf16 chunks of 128 data rows in the canonical UMMA layout [DP/8][128][8] + y[128] (float)
-        const int D = p->D, N = p->N, DP = (D + 15) / 16 * 16, NB = 128, NC = (N + NB - 1) / NB;
+        // bf16 chunks of 64 data rows in the canonical UMMA layout [DP/8][64][8] + y[64] (float); LT_NB
+        const int D = p->D, N = p->N, DP = (D + 15) / 16 * 16, NB = 64, NC = (N + NB - 1) / NB;
         const size_t cb = (size_t)DP * NB * 2 + NB * 4;
         std::vector<unsigned char> buf(cb * NC, 0);
         auto bf16 = [](float f) -> uint16_t {

@@ -1,20 +1,29 @@
 // K4-TC: Bayesian logistic-regression gradient (and energy) on the tensor cores -- BASELINE
 // config 3 (X 100k x 256, 65 536 particles).  Flash-attention-shaped GEMM chain; the N x P
-// logits never leave the SM:
+// logits never leave the SM and BOTH GEMMs take their A operand from tensor memory, so shared
+// memory carries nothing but a deep ring of X chunks:
 //
-//   per CTA: 128 particles (Theta tile, bf16, shared memory, resident)
-//   per chunk of 128 data rows (X chunk bf16 + y, ONE TMA bulk copy into a 2-stage ring):
-//     GEMM1  S[128 x 128]  = Theta_tile . X_chunk^T        tcgen05.mma kind::f16, K = D, D in TMEM
-//     epilogue             r = sigmoid(S) - y  (tanh.approx: one MUFU), energy terms, bf16 -> smem
-//     GEMM2  G[128 x D]   += R . X_chunk                   A = R (smem), B = the SAME smem chunk
-//                                                          read MN-major, accumulator in TMEM
-//   TMEM columns: S0 [0,128) | S1 [128,256) | G [256, 256+D)     (S double-buffered)
+//   per CTA: 128 particles.  Theta tile -> bf16 pairs in TMEM (A of GEMM1, resident).
+//   per chunk of 64 data rows (X chunk bf16 + y, ONE TMA bulk copy into an NS-stage ring):
+//     GEMM1  S[128 x 64]   = Theta_tile . X_chunk^T       tcgen05.mma kind::f16, A = Theta (TMEM)
+//     epilogue             r = sigmoid(S) - y  (tanh.approx: one MUFU), energy terms; r (bf16
+//                          pairs) is written back INTO the S columns it came from (tcgen05.st)
+//     GEMM2  G[128 x D]   += R . X_chunk                   A = R (TMEM, aliasing S), B = the SAME
+//                                                          smem chunk read MN-major
+//   TMEM columns: Theta [0, DP/2) | S0 [128,192) | S1 [192,256) | G [256, 256+DP)
+//
+// Why this shape (measured on the first version, which kept Theta and R in shared memory with a
+// 2-stage ring of 128-row chunks: 43 % tensor-pipe active): (1) with A and B both in shared memory
+// GEMM1 alone needs 128 B/clk, the whole shared-memory bandwidth, before TMA writes and the R
+// round trip; (2) two stages leave no prefetch distance -- a stage is refilled only when GEMM2 of
+// its chunk retires and is needed again by the very next GEMM1, so every chunk exposed the TMA
+// latency.  Here shared-memory traffic is ~1/2 of its bandwidth and 6 stages are in flight.
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
-// (thread <-> particle row and one half of the 128 logit columns).
-// Shared-memory operand layout everywhere: canonical K-major no-swizzle UMMA layout
-// [K/8][128 rows][8 bf16]; an X chunk stored that way is simultaneously the K-major B operand
-// of GEMM1 (rows = data rows, K = d) and the MN-major B operand of GEMM2 (N = d, K = data rows).
+// (thread <-> particle row and one half of the 64 logit columns).
+// Shared-memory operand layout: canonical K-major no-swizzle UMMA layout [K/8][64 rows][8 bf16];
+// an X chunk stored that way is simultaneously the K-major B operand of GEMM1 (rows = data rows,
+// K = d) and the MN-major B operand of GEMM2 (N = d, K = data rows).
 //
 // Inputs are rounded to bf16 (fp32 accumulation): this is the throughput path; the exact
 // fp32 / fp64 path is k_logistic.cuh.  A trajectory driven by this gradient is still reversible
@@ -26,21 +35,26 @@
 #include "common.cuh"
 #include "k_dense_tc.cuh"
 #include "k_dense_tc2.cuh"
+#include "k_dense_tc3.cuh"  // tmem_st4
 
 namespace ehmc {
 
 constexpr int LT_M = 128;    // particles per CTA
-constexpr int LT_NB = 128;   // data rows per chunk
+constexpr int LT_NB = 64;    // data rows per chunk
+constexpr int LT_MAX_STAGES = 8;
 constexpr int LT_EPI_WARPS = 8;
 constexpr int LT_THREADS = 32 * (2 + LT_EPI_WARPS);
 
 struct LogisticTcArgs {
-  const unsigned char* chunks;  // [NC] blocks of chunk_bytes: X part [DP/8][128][8] bf16, then y[128] float
+  const unsigned char* chunks;  // [NC] blocks of chunk_bytes: X part [DP/8][64][8] bf16, then y[64] float
   int NC;                       // number of chunks
   int DP;                       // D rounded up to 16
   int D;
   int n_pad;                    // zero rows appended to the last chunk (y = 0.5 there)
   unsigned chunk_bytes;
+  int stages;                   // ring depth (shared memory permitting, <= LT_MAX_STAGES)
+  int split;                    // 1, or 2: two CTAs per particle tile, each over half of the data rows,
+                                // results combined with atomicAdd into zeroed outputs (0 + a + b is order independent)
   float inv_s2;
 };
 
@@ -97,79 +111,97 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+// D[tmem] (+)= A[tmem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // grad[D,P] (and energy[P] when WITH_E) at theta[D,P]
 template <bool WITH_E>
 __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __restrict__ theta, long long t_ld,
                                                                long long P, float* __restrict__ grad, long long g_ld,
                                                                float* __restrict__ energy, const LogisticTcArgs pa) {
   extern __shared__ __align__(128) unsigned char lt_smem[];
-  const int DP = pa.DP, D = pa.D, NC = pa.NC;
-  const uint32_t a_bytes = (uint32_t)DP * LT_M * 2;             // Theta tile, [DP/8][128][16 B]
-  unsigned char* As = lt_smem;
-  unsigned char* Xs0 = As + a_bytes;                            // 2 stages of chunk_bytes
-  unsigned char* Rs = Xs0 + 2 * (size_t)pa.chunk_bytes;         // [NB/8][128][16 B]
-  float* xch = reinterpret_cast<float*>(Rs + LT_NB * LT_M * 2);  // [2][128] energy exchange
+  const int DP = pa.DP, D = pa.D, NS = pa.stages;
+  const int part = (int)(blockIdx.x % (unsigned)pa.split);
+  const int cbeg = (int)((long long)pa.NC * part / pa.split);
+  const int NC = (int)((long long)pa.NC * (part + 1) / pa.split) - cbeg;  // chunks of this CTA: cbeg .. cbeg + NC
+  unsigned char* Xs0 = lt_smem;                                                     // NS stages of chunk_bytes
+  float* xch = reinterpret_cast<float*>(Xs0 + (size_t)NS * pa.chunk_bytes);         // [2][128] energy exchange
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * LT_M);
-  uint64_t* x_full = bars;        // [2]
-  uint64_t* x_empty = bars + 2;   // [2]
-  uint64_t* s_full = bars + 4;    // [2]
-  uint64_t* s_empty = bars + 6;   // [2]
-  uint64_t* r_full = bars + 8;
-  uint64_t* r_empty = bars + 9;
-  uint64_t* g_done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* x_full = bars;                      // [LT_MAX_STAGES]
+  uint64_t* x_empty = bars + LT_MAX_STAGES;     // [LT_MAX_STAGES]
+  uint64_t* s_full = bars + 2 * LT_MAX_STAGES;  // [2]
+  uint64_t* r_full = s_full + 2;                // [2]
+  uint64_t* g_done = r_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_done + 1);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const long long p0 = (long long)blockIdx.x * LT_M;
+  const long long p0 = (long long)(blockIdx.x / (unsigned)pa.split) * LT_M;
 
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NS; ++i) {
         mbar_init(&x_full[i], 1);
         mbar_init(&x_empty[i], 1);
-        mbar_init(&s_full[i], 1);
-        mbar_init(&s_empty[i], LT_EPI_WARPS);
       }
-      mbar_init(r_full, LT_EPI_WARPS);
-      mbar_init(r_empty, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&r_full[i], LT_EPI_WARPS);
+      }
       mbar_init(g_done, 1);
       fence_barrier_init();
     }
   }
-  // Theta tile -> bf16 canonical layout: thread (row, dk) builds 16-byte units
-  for (int i = tid; i < (DP / 8) * LT_M; i += LT_THREADS) {
-    const int dk = i / LT_M, row = i % LT_M;
-    const long long pi = p0 + row;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int d = 8 * dk + e;
-      v[e] = (d < D && pi < P) ? theta[d * t_ld + pi] : 0.f;
-    }
-    uint4 u;
-    u.x = pack_bf16x2(v[0], v[1]);
-    u.y = pack_bf16x2(v[2], v[3]);
-    u.z = pack_bf16x2(v[4], v[5]);
-    u.w = pack_bf16x2(v[6], v[7]);
-    reinterpret_cast<uint4*>(As)[i] = u;
-  }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const uint32_t t_g = tmem_base + 256u;
+  const uint32_t t_s = tmem_base + 128u, t_g = tmem_base + 256u;
+  // a warp can only touch the TMEM lanes of ITS hardware quarter (warp index % 4)
+  const int quarter = warp & 3, half = (warp - 2) >> 2;
+  const int row = quarter * 32 + lane;
+  const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+
+  if (warp >= 2) {
+    // Theta tile -> bf16 pairs in TMEM: this thread's particle row, dims [half * DP/2, (half + 1) * DP/2)
+    const long long pi = p0 + row;
+    const int d0 = half * (DP / 2);
+    for (int b = 0; b < DP / 16; ++b) {  // 8 dims = 4 packed columns per batch (DP / 2 is a multiple of 8)
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = d0 + 8 * b + 2 * e;
+        const float v0 = (d < D && pi < P) ? theta[d * t_ld + pi] : 0.f;
+        const float v1 = (d + 1 < D && pi < P) ? theta[(d + 1) * t_ld + pi] : 0.f;
+        w[e] = pack_bf16x2(v0, v1);
+      }
+      tmem_st4(tmem_base + lane_off + (uint32_t)(d0 / 2 + 4 * b), w);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
       for (int c = 0; c < NC; ++c) {
-        const int s = c & 1;
-        mbar_wait(&x_empty[s], (uint32_t)(((c >> 1) & 1) ^ 1));
+        const int s = c % NS;
+        mbar_wait(&x_empty[s], (uint32_t)(((c / NS) & 1) ^ 1));
         mbar_expect_tx(&x_full[s], pa.chunk_bytes);
-        tma_bulk_g2s(Xs0 + (size_t)s * pa.chunk_bytes, pa.chunks + (size_t)c * pa.chunk_bytes, pa.chunk_bytes,
+        tma_bulk_g2s(Xs0 + (size_t)s * pa.chunk_bytes, pa.chunks + (size_t)(cbeg + c) * pa.chunk_bytes, pa.chunk_bytes,
                      &x_full[s]);
       }
     }
@@ -178,30 +210,32 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
     if (elect_one()) {
       const uint32_t idesc1 = umma_idesc_bf16(LT_M, LT_NB, 0);
       const uint32_t idesc2 = umma_idesc_bf16(LT_M, DP, 1);
-      const uint64_t dA = umma_desc2(smem_u32(As), LT_M * 16, 128);       // K-major: LBO = next K chunk, SBO = 8 rows
-      const uint64_t dR = umma_desc2(smem_u32(Rs), LT_M * 16, 128);
-      const uint64_t k_step = (2u * LT_M * 16u) >> 4;                     // two 16-byte K chunks per MMA (K = 16)
+      const uint64_t k_step = (2u * LT_NB * 16u) >> 4;  // GEMM1: two 16-byte K chunks (of 64 rows) per MMA
       auto gemm2 = [&](int cc) {
-        const int s = cc & 1;
-        mbar_wait(r_full, (uint32_t)(cc & 1));
+        const int s = cc % NS, b = cc & 1;
+        mbar_wait(&r_full[b], (uint32_t)((cc >> 1) & 1));
         tc_fence_after();
-        // B = X chunk read MN-major: N = d (unit stride LT_NB*16 B between 8-d groups = SBO),
+        // B = X chunk read MN-major: N = d (LT_NB*16 B between 8-d groups = SBO),
         // K = data rows (16 B apart, groups of 8 rows 128 B apart = LBO)
         const uint64_t dB2 = umma_desc2(smem_u32(Xs0 + (size_t)s * pa.chunk_bytes), 128, LT_NB * 16);
+        // A = R: bf16 pairs of data rows (2k, 2k+1); half h of the epilogue wrote its 32 rows into the
+        // first 16 columns of ITS 32-column half of the S buffer
+#pragma unroll
         for (int j = 0; j < LT_NB / 16; ++j)
-          umma_bf16_ss(t_g, dR + j * k_step, dB2 + j * ((16u * 16u) >> 4), idesc2, (cc > 0 || j > 0) ? 1u : 0u);
-        umma_commit(&x_empty[s]);  // the X stage and R are free once these MMAs have executed
-        umma_commit(r_empty);
+          umma_bf16_ts(t_g, t_s + (uint32_t)(b * 64 + (j >> 1) * 32 + (j & 1) * 8), dB2 + j * ((16u * 16u) >> 4), idesc2,
+                       (cc > 0 || j > 0) ? 1u : 0u);
+        umma_commit(&x_empty[s]);  // the X stage is free once these MMAs have executed
       };
       for (int c = 0; c < NC; ++c) {
-        const int s = c & 1;
-        mbar_wait(&x_full[s], (uint32_t)((c >> 1) & 1));
-        mbar_wait(&s_empty[s], (uint32_t)(((c >> 1) & 1) ^ 1));
+        const int s = c % NS;
+        mbar_wait(&x_full[s], (uint32_t)((c / NS) & 1));
         tc_fence_after();
+        // S buffer c & 1 was last read (as R) by GEMM2 of chunk c - 2, issued before this point: the
+        // tensor pipe executes one thread's MMAs in order, no barrier needed
         const uint64_t dB1 = umma_desc2(smem_u32(Xs0 + (size_t)s * pa.chunk_bytes), LT_NB * 16, 128);
         for (int j = 0; j < DP / 16; ++j)
-          umma_bf16_ss(tmem_base + (uint32_t)(s * 128), dA + j * k_step, dB1 + j * k_step, idesc1, j > 0 ? 1u : 0u);
-        umma_commit(&s_full[s]);
+          umma_bf16_ts(t_s + (uint32_t)((c & 1) * 64), tmem_base + 8u * j, dB1 + j * k_step, idesc1, j > 0 ? 1u : 0u);
+        umma_commit(&s_full[c & 1]);
         if (c >= 1) gemm2(c - 1);
       }
       gemm2(NC - 1);
@@ -209,48 +243,39 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
     }
   } else {
     // ===== epilogue warps: sigmoid-residual between the two GEMMs =====
-    // a warp can only touch the TMEM lanes of ITS hardware quarter (warp index % 4)
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     float Uacc = 0.f;
+    const uint32_t t_mine = t_s + lane_off + (uint32_t)(half * 32);
     for (int c = 0; c < NC; ++c) {
-      const int s = c & 1;
-      mbar_wait(&s_full[s], (uint32_t)((c >> 1) & 1));
+      const int s = c % NS, b = c & 1;
+      mbar_wait(&s_full[b], (uint32_t)((c >> 1) & 1));
       tc_fence_after();
-      uint32_t sv[4][16];
+      uint32_t sv[2][16];
+      tmem_ld16_issue(t_mine + (uint32_t)(b * 64), sv[0]);
+      tmem_ld16_issue(t_mine + (uint32_t)(b * 64 + 16), sv[1]);
+      tmem_wait_ld16(sv[0]);
+      tmem_wait_ld16(sv[1]);
+      const float* yv = reinterpret_cast<const float*>(Xs0 + (size_t)s * pa.chunk_bytes + (size_t)DP * LT_NB * 2) + half * 32;
+      uint32_t rp[16];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) tmem_ld16_issue(tmem_base + lane_off + (uint32_t)(s * 128 + half * 64 + 16 * b), sv[b]);
-#pragma unroll
-      for (int b = 0; b < 4; ++b) tmem_wait_ld16(sv[b]);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[s]);  // S buffer may be overwritten by GEMM1 of chunk c + 2
-      const float* yv = reinterpret_cast<const float*>(Xs0 + (size_t)s * pa.chunk_bytes + (size_t)DP * LT_NB * 2);
-      uint32_t rp[32];
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
+      for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           float r2[2];
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            const float sgm = __uint_as_float(sv[b][i + t]);
-            const float yn = yv[half * 64 + 16 * b + i + t];
+            const float sgm = __uint_as_float(sv[bb][i + t]);
+            const float yn = yv[16 * bb + i + t];
             const float sig = fmaf(0.5f, tanh_approx(0.5f * sgm), 0.5f);
             r2[t] = sig - yn;
             if (WITH_E) Uacc += fmaxf(sgm, 0.f) + __logf(1.f + __expf(-fabsf(sgm))) - yn * sgm;
           }
-          rp[(16 * b + i) / 2] = pack_bf16x2(r2[0], r2[1]);
+          rp[(16 * bb + i) / 2] = pack_bf16x2(r2[0], r2[1]);
         }
-      mbar_wait(r_empty, (uint32_t)((c & 1) ^ 1));  // GEMM2 of the previous chunk has consumed R
-#pragma unroll
-      for (int u8 = 0; u8 < 8; ++u8)
-        reinterpret_cast<uint4*>(Rs)[(half * 8 + u8) * LT_M + row] =
-            make_uint4(rp[4 * u8], rp[4 * u8 + 1], rp[4 * u8 + 2], rp[4 * u8 + 3]);
-      fence_proxy_async();
+      tmem_st16(t_mine + (uint32_t)(b * 64), rp);  // R over the first 16 of my 32 S columns
+      tmem_wait_st();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(r_full);
+      if (lane == 0) mbar_arrive(&r_full[b]);
     }
     // ---- final: G from TMEM, prior term, stores --------------------------------------------------
     mbar_wait(g_done, 0u);
@@ -266,9 +291,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
       for (int i = 0; i < 16; ++i) {
         const int d = half * dh + 16 * b + i;
         if (d < D && pi < P) {
-          const float th = theta[d * t_ld + pi];
+          const float th = part == 0 ? theta[d * t_ld + pi] : 0.f;  // prior term: once per particle
           t2 = fmaf(th, th, t2);
-          if (grad) grad[d * g_ld + pi] = __uint_as_float(gv[i]) + th * pa.inv_s2;
+          const float gd = __uint_as_float(gv[i]) + th * pa.inv_s2;
+          if (grad) {
+            if (pa.split == 1)
+              grad[d * g_ld + pi] = gd;
+            else
+              atomicAdd(&grad[d * g_ld + pi], gd);
+          }
         }
       }
     }
@@ -280,9 +311,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
       for (int i = 0; i < 8; ++i) {
         const int d = half * dh + (dh / 16) * 16 + i;
         if (d < D && pi < P) {
-          const float th = theta[d * t_ld + pi];
+          const float th = part == 0 ? theta[d * t_ld + pi] : 0.f;
           t2 = fmaf(th, th, t2);
-          if (grad) grad[d * g_ld + pi] = __uint_as_float(gv[i]) + th * pa.inv_s2;
+          const float gd = __uint_as_float(gv[i]) + th * pa.inv_s2;
+          if (grad) {
+            if (pa.split == 1)
+              grad[d * g_ld + pi] = gd;
+            else
+              atomicAdd(&grad[d * g_ld + pi], gd);
+          }
         }
       }
     }
@@ -290,8 +327,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
   }
   tc_fence_before();
   __syncthreads();
-  if (WITH_E && tid < LT_M && p0 + tid < P)
-    energy[p0 + tid] = xch[tid] + xch[LT_M + tid] - (float)pa.n_pad * 0.6931471805599453f;
+  if (WITH_E && tid < LT_M && p0 + tid < P) {
+    // the zero rows padding the LAST chunk each contributed softplus(0) = ln 2
+    const float pad = part == pa.split - 1 ? (float)pa.n_pad * 0.6931471805599453f : 0.f;
+    const float ev = xch[tid] + xch[LT_M + tid] - pad;
+    if (pa.split == 1)
+      energy[p0 + tid] = ev;
+    else
+      atomicAdd(&energy[p0 + tid], ev);
+  }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
