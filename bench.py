@@ -452,6 +452,7 @@ def main():
                 roof["traffic_source"] = tr["source"]
                 roof["ncu_tensor_pipe_active_pct"] = tr.get("tensor_pipe_active_pct")
                 roof["ncu_issue_active_pct"] = tr.get("issue_active_pct")
+                roof["ncu_fma_pipe_active_pct"] = tr.get("fma_pipe_active_pct")
         except (OSError, ValueError):
             pass
         roof["algorithmic_bytes_per_launch"] = by
