@@ -194,8 +194,11 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
     if (c->tc_prof_buf.ptr) {
       long long h[64];
       CUDA_TRY(cudaMemcpy(h, c->tc_prof_buf.ptr, sizeof(h), cudaMemcpyDeviceToHost));
-      fprintf(stderr, "tc_prof start=%lld:", h[63]);
-      for (int i = 0; i < 62 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[63]);
+      // k_dense_tc3 stores the number of stamps in h[63] (absolute clocks); the older kernels store the start clock
+      const bool counted = h[63] > 0 && h[63] < 63;
+      const long long base = counted ? h[0] : h[63];
+      fprintf(stderr, "tc_prof:");
+      for (int i = 0; i < (counted ? (int)h[63] : 62) && h[i]; ++i) fprintf(stderr, " %lld", h[i] - base);
       fprintf(stderr, "\n");
     }
   } else if (!strcmp(name, "small_waves")) {

@@ -18,6 +18,7 @@ static int launch_tc3_c8(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<fl
   pa.mu = static_cast<const float*>(p->d9);
   pa.inv_lscale = p->tc3_inv_lscale;
   pa.dbg = c->tc_debug;
+  pa.prof = c->tc_prof ? static_cast<long long*>(c->tc_prof_buf.ptr) : nullptr;
   // persistent: one CTA per SM (the CTA takes the whole TMEM), tiles dealt in contiguous ranges
   const long long ntiles = (A.P + TC_M - 1) / TC_M;
   const unsigned grid = (unsigned)std::min<long long>(c->prop.multiProcessorCount, ntiles);

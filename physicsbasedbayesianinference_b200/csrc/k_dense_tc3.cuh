@@ -47,7 +47,10 @@ struct Tc3Shape {
   static constexpr int KCH = KP / 8;  // 16-byte chunks along K
   static constexpr int HI_COL = NP, LO_COL = NP + KP / 2;
   static_assert(NP + KP <= 256, "tile does not fit 256 TMEM columns");
-  static constexpr size_t smem_bytes() { return (size_t)2 * KCH * NP * 16 + (size_t)KP * 4 + 64; }
+  // Lambda hi / lo + mean + barriers + the two groups' stashes of standard normals [DC][128]
+  static constexpr size_t smem_bytes() {
+    return (size_t)2 * KCH * NP * 16 + (size_t)KP * 4 + 64 + (size_t)2 * DC * TC_M * 4;
+  }
 };
 
 struct DenseTc3Args {
@@ -56,6 +59,7 @@ struct DenseTc3Args {
   const float* mu;    // [128] zero padded
   float inv_lscale;   // 1 / lscale (power of two)
   int dbg;            // 1: issue no MMAs (commit only); 2: skip the epilogue arithmetic
+  long long* prof;    // optional clock64() trace of the second tile of CTA 0 / group 0 (ctx option "tc_prof")
 };
 
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
   float* mus = reinterpret_cast<float*>(Blo + (size_t)KCH * NP);  // [KP]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(mus + KP);         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+  float* zstash_all = reinterpret_cast<float*>(tc3_smem_raw + (size_t)2 * KCH * NP * 16 + (size_t)KP * 4 + 64);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
@@ -284,7 +289,31 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
   const long long tile0 = ntiles * blockIdx.x / gridDim.x, tile1 = ntiles * (blockIdx.x + 1) / gridDim.x;
   uint32_t phase = 0;
 
+  // Momentum refresh off the critical path: the standard normals of the group's NEXT tile are drawn
+  // 8 dims at a time in the shadow of the current tile's MMAs (one chunk per evaluation, right after
+  // the MMAs are issued) and kept in shared memory, zst[d][row] -- each thread only ever touches its
+  // own column, so no synchronisation is involved.  Measured before this change: the Philox /
+  // Box-Muller loop at the start of a tile took 11.6k of the tile's 154k cycles with the tensor pipe idle.
+  float* zst = zstash_all + (size_t)grp * DC * TC_M + row;
+  const bool philox = hmc && A.z == nullptr;
+  const PhiloxKey PK(A.seed, A.iter);
+  auto gen_chunk = [&](long long t, int c) {
+    const long long r = t * TC_M + row;
+    float zz[8];
+    NormalBlock<float>::draw_multi<2>(PK, A.offset + (u64)(r < A.P ? r : 0), (uint32_t)(2 * c), zz);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) zst[(8 * c + e) * TC_M] = zz[e];
+  };
+  int ngen = 0;  // chunks of the CURRENT tile's normals already in the stash
+
   for (long long tile = tile0 + grp; tile < tile1; tile += 2) {
+    // phase trace of one steady-state tile (the second of CTA 0 / group 0), thread 0
+    const bool prof = pa.prof != nullptr && blockIdx.x == 0 && tid == 0 && tile == tile0 + 2;
+    int pi = 0;
+    auto stamp = [&]() {
+      if (prof && pi < 62) pa.prof[pi++] = clock64();
+    };
+    stamp();  // 0: tile start
     const long long prow = tile * TC_M + row;
     const bool valid = prow < A.P;
     const long long pc = valid ? prow : 0;
@@ -309,27 +338,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
     const float* qcol = A.q + pc;
 #pragma unroll
     for (int d = 0; d < DC; ++d) v[d] = col(qcol, A.q_ld, d);
-    const bool philox = hmc && A.z == nullptr;
+    stamp();  // 1: position loads issued
     if (philox) {
-      // momenta: Philox blocks 2c, 2c+1 -> dims 8c .. 8c+7, parked as v = p / m in the operand
-      // columns [NP, NP + DC) (free until the split below) while the position loads land
-      const PhiloxKey K(A.seed, A.iter);
+      // first tile of the group (or a trajectory shorter than the chunk count): draw what is missing now,
+      // while the position loads land
 #pragma unroll 1
-      for (int c = 0; c < C8; ++c) {
-        float zz[8];
-        NormalBlock<float>::draw_multi<2>(K, A.offset + (u64)pc, (uint32_t)(2 * c), zz);
-        uint32_t pk[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float pp = (8 * c + e < D) ? zz[e] * pstd : 0.f;
-          K0 = fmaf(pp, pp, K0);
-          const float vv = pp * inv_m;
-          vmax = fmaxf(vmax, fabsf(vv));
-          pk[e] = __float_as_uint(vv);
-        }
-        tmem_st8(t_hi + (uint32_t)(8 * c), pk);
-      }
+      for (int c = ngen; c < C8; ++c) gen_chunk(tile, c);
     }
+    stamp();  // 2: momenta drawn
     // x = q - mu parked in the (idle) accumulator columns
 #pragma unroll
     for (int c = 0; c < C8; ++c) {
@@ -343,38 +359,24 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       tmem_st8(t_d + (uint32_t)(8 * c), xx);
     }
     if (philox) {
-      tmem_wait_st();
 #pragma unroll
-      for (int c = 0; c < C8; c += 2) {
-        if (c + 1 < C8) {
-          uint32_t t[16];
-          tmem_ld16_issue(t_hi + (uint32_t)(8 * c), t);
-          tmem_wait_ld16(t);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[8 * c + e] = __uint_as_float(t[e]);
-        } else {
-          uint32_t t[8];
-          tmem_ld8_issue2(t_hi + (uint32_t)(8 * c), t);
-          tmem_wait_ld8(t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[8 * c + e] = __uint_as_float(t[e]);
-        }
-      }
+      for (int d = 0; d < DC; ++d) v[d] = (d < DC - 8 || d < D) ? zst[d * TC_M] * pstd : 0.f;
     } else {
-      // fed momenta (parity mode) or integrate(): straight into the registers
+      // fed momenta (parity mode) or integrate()
       const float* mcol = (hmc ? A.z : A.p) + pc;
       const long long mld = hmc ? A.z_ld : A.p_ld;
       const float msc = hmc ? pstd : 1.f;
 #pragma unroll
       for (int d = 0; d < DC; ++d) v[d] = col(mcol, mld, d) * msc;
+    }
 #pragma unroll
-      for (int d = 0; d < DC; ++d) {
-        K0 = fmaf(v[d], v[d], K0);
-        v[d] *= inv_m;
-        vmax = fmaxf(vmax, fabsf(v[d]));
-      }
+    for (int d = 0; d < DC; ++d) {
+      K0 = fmaf(v[d], v[d], K0);
+      v[d] *= inv_m;
+      vmax = fmaxf(vmax, fabsf(v[d]));
     }
     K0 *= 0.5f * inv_m;
+    stamp();  // 3: positions landed and parked, momenta in registers
     // ---- row scale 2^e: max(|x|, reach of the ballistic drift) -> [2^7, 2^8) ----------------------
     amax = fmaxf(amax, fabsf(h) * (float)L * vmax);
     uint32_t eb = (__float_as_uint(amax) >> 23) & 0xffu;
@@ -394,13 +396,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       tmem_st4(t_lo + (uint32_t)(4 * c), ll);
     }
     if constexpr (DC < KP) {
-      // operand columns of the padded dims [DC, KP) (the momentum parking overwrote them): finite zeros
+      // operand columns of the padded dims [DC, KP): finite zeros
       uint32_t zero[4] = {0u, 0u, 0u, 0u};
       tmem_st4(t_hi + (uint32_t)(DC / 2), zero);
       tmem_st4(t_lo + (uint32_t)(DC / 2), zero);
     }
     tmem_wait_st();
 
+    stamp();  // 4: operands split and stored
     // velocities in drift units: w = (h 2^e) v;  g_true = G * isc * inv_lscale
     const float hs = h * sc, gs = isc * pa.inv_lscale;
 #pragma unroll
@@ -424,6 +427,18 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
         }
         umma_commit(&mbar[grp]);
       }
+      // in the shadow of the MMAs: one chunk of the next tile's normals, then an L2 prefetch of its positions
+      if (tile + 2 < tile1) {
+        if (philox && ev < C8) {
+          gen_chunk(tile + 2, ev);
+        } else if (ev == C8) {
+          const long long r0 = (tile + 2) * TC_M + quarter * 32;
+          if (r0 < A.P) {
+            for (int d = lane; d < D; d += 32)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(A.q + (long long)d * A.q_ld + r0));
+          }
+        }
+      }
       mbar_wait(&mbar[grp], phase);
       phase ^= 1u;
       tc_fence_after();
@@ -435,7 +450,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       }
       const float ck = L == 0 ? 0.f : ((first || last) ? ckh : ckf);
       if (!(pa.dbg & 2)) tc3_epilogue<C8>(v, t_d, t_hi, t_lo, ck, !last);
+      if (ev < 2 || ev >= L - 1) stamp();  // 5, 6: first two evaluations; then the last two
     }
+    ngen = (philox && tile + 2 < tile1) ? (L + 1 < C8 ? L + 1 : C8) : 0;
     // U = 1/2 x . g_true = 1/2 (xs isc) . (G gs)
     U0 = (U0 * isc) * (0.5f * gs);
     U1 = (U1 * isc) * (0.5f * gs);
@@ -458,6 +475,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
         u = A.u != nullptr ? A.u[pc] : NormalBlock<float>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)pc);
       rej = metropolis_reject<float>(oldH, newH, u, A.flags, &accp);
     }
+    stamp();  // Metropolis decided
     const bool fast = A.p == nullptr && A.partials == nullptr;
     const bool wr = valid && !rej;  // HMC.py:175: rejected rows keep the value in HBM
     // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only accepted rows store.
@@ -548,6 +566,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       }
     }
     if (hmc && valid && A.accept != nullptr) A.accept[pc] = rej ? 0 : 1;
+    stamp();  // write-back issued
+    if (prof) pa.prof[63] = (long long)pi;
   }
   tc_fence_before();
   __syncthreads();
