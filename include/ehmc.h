@@ -93,7 +93,13 @@ typedef enum {
   EHMC_FAMILY_NBODY = 4,
   /* Bayesian logistic regression: U = sum_n softplus(x_n.q) - y_n x_n.q + 0.5 |q|^2 / s^2.
    * params: X[N,D] (row-major), y[N].  scalars: {s}. */
-  EHMC_FAMILY_LOGISTIC = 5
+  EHMC_FAMILY_LOGISTIC = 5,
+  /* Independent coin biases q_d in (0, 1) with a flat prior -- the reference's own NumPyro sample
+   * (samples/NumpyroExamples/CoinToss/CoinToss.py:6-25):
+   * U = -sum_d [ k_d ln q_d + (n_d - k_d) ln(1 - q_d) ],  dU/dq_d = -k_d/q_d + (n_d - k_d)/(1 - q_d)
+   * (references/NotesOnParticleBasedHMC.pdf eq. 22).  Outside (0, 1) U is NaN, as ln of a negative
+   * number is in the reference.  params: successes k[D], trials n[D].  scalars: none.  D <= 32. */
+  EHMC_FAMILY_COIN_TOSS = 6
 } ehmc_family;
 
 typedef enum {

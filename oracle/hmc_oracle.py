@@ -108,6 +108,35 @@ class Funnel:
         return g
 
 
+class CoinToss:
+    """Independent coin biases under a flat prior: the reference's NumPyro sample model
+    (samples/NumpyroExamples/CoinToss/CoinToss.py:21-25, Uniform(0,1) priors and Bernoulli
+    observations), whose potential is -log_density (CoinTossExample.py:75-90):
+
+        U = -sum_d [ k_d ln q_d + (n_d - k_d) ln(1 - q_d) ]
+        dU/dq_d = -k_d / q_d + (n_d - k_d) / (1 - q_d)   (references/NotesOnParticleBasedHMC.pdf eq. 22)
+    """
+
+    family = 6
+
+    def __init__(self, successes, trials):
+        self.k = np.asarray(successes, dtype=np.float64).reshape(-1)
+        self.n = np.asarray(trials, dtype=np.float64).reshape(-1)
+        self.D = self.k.shape[0]
+
+    def energy(self, q):
+        k = self.k.reshape((-1,) + (1,) * (q.ndim - 1))
+        nk = (self.n - self.k).reshape(k.shape)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return -np.sum(k * np.log(q) + nk * np.log(1.0 - q), axis=0)
+
+    def grad(self, q):
+        k = self.k.reshape((-1,) + (1,) * (q.ndim - 1))
+        nk = (self.n - self.k).reshape(k.shape)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return -k / q + nk / (1.0 - q)
+
+
 class NBody:
     """Pairwise gravitational potential with every ensemble particle being a
     whole B-body system.  Coordinates are flattened component-major,

@@ -18,6 +18,7 @@ from .HMC import HMC, GaussianDensity  # noqa: F401
 from . import potential  # noqa: F401
 from . import diagnostics, io, numpyro_adapter, parallel  # noqa: F401
 from .potential import (  # noqa: F401
+    CoinTossPotential,
     FunnelPotential,
     GaussianPotential,
     HarmonicPotential,

@@ -22,6 +22,7 @@ FAMILY_DENSE_GAUSSIAN = 2
 FAMILY_FUNNEL = 3
 FAMILY_NBODY = 4
 FAMILY_LOGISTIC = 5
+FAMILY_COIN_TOSS = 6
 LEAPFROG = 0
 STORMER_VERLET = 1
 FLAG_BUGCOMPAT_MOMENTUM = 1

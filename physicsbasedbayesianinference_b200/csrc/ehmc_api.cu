@@ -348,6 +348,19 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       if (!(scalars[1] > 0)) rc = fail(EHMC_ERR_INVALID, "funnel: sigma_v must be > 0");
       break;
     }
+    case EHMC_FAMILY_COIN_TOSS: {
+      if (nparams != 2) { rc = fail(EHMC_ERR_INVALID, "coin toss: params = {successes[D], trials[D]}"); break; }
+      rc = fetch_param(params[0], "successes", 1, &p->hp0, &v);
+      if (rc) break;
+      rc = fetch_param(params[1], "trials", 1, &p->hp1, &v);
+      if (rc) break;
+      p->D = (int)p->hp0.size();
+      if (p->D < 1 || p->D > 32) { rc = fail(EHMC_ERR_UNSUPPORTED, "coin toss: 1 <= D <= 32 (got %d)", p->D); break; }
+      if ((int)p->hp1.size() != p->D) { rc = fail(EHMC_ERR_INVALID, "coin toss: trials must have D entries"); break; }
+      for (int d = 0; d < p->D && rc == EHMC_OK; ++d)
+        if (!(p->hp0[d] >= 0 && p->hp1[d] >= p->hp0[d])) rc = fail(EHMC_ERR_INVALID, "coin toss: need 0 <= successes <= trials");
+      break;
+    }
     case EHMC_FAMILY_NBODY: {
       if (nparams != 1 || nscalars != 2) { rc = fail(EHMC_ERR_INVALID, "nbody: params = {bodyMass[B]}, scalars = {G, eps}"); break; }
       rc = fetch_param(params[0], "bodyMass", 1, &p->hp0, &v);

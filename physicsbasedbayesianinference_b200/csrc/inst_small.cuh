@@ -47,6 +47,16 @@ static int small_grid(ehmc_ctx* c, K kernel, size_t sm, long long P, unsigned* g
   return EHMC_OK;
 }
 
+template <typename T, int DT>
+static CoinPot<T, DT> make_coin(const ehmc_potential* p) {
+  CoinPot<T, DT> f;
+  for (int d = 0; d < DT; ++d) {
+    f.k[d] = d < p->D ? (T)p->hp0[d] : T(0);
+    f.nk[d] = d < p->D ? (T)(p->hp1[d] - p->hp0[d]) : T(0);
+  }
+  return f;
+}
+
 template <typename T, int DT, class Pot>
 static int launch_small_pot(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, int integ, bool hmc, cudaStream_t st) {
   static_assert(K1_THREADS == K1_THREADS_HOST, "K1 block size");
@@ -84,6 +94,8 @@ static int launch_small_dt(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<
       return launch_small_pot<T, DT>(c, A, make_diag<T, DT>(p), integ, hmc, st);
     case EHMC_FAMILY_FUNNEL:
       return launch_small_pot<T, DT>(c, A, make_funnel<T, DT>(p), integ, hmc, st);
+    case EHMC_FAMILY_COIN_TOSS:
+      return launch_small_pot<T, DT>(c, A, make_coin<T, DT>(p), integ, hmc, st);
     case EHMC_FAMILY_DENSE_GAUSSIAN:
       if constexpr (DT <= 16) return launch_small_pot<T, DT>(c, A, make_dense_small<T, DT>(p), integ, hmc, st);
       break;
@@ -115,6 +127,9 @@ static int eval_small_dt(ehmc_ctx* c, const ehmc_potential* p, const T* q, long 
       break;
     case EHMC_FAMILY_FUNNEL:
       k_eval_small<T, DT><<<grid, 128, 0, st>>>(q, q_ld, P, p->D, e, g, g_ld, make_funnel<T, DT>(p));
+      break;
+    case EHMC_FAMILY_COIN_TOSS:
+      k_eval_small<T, DT><<<grid, 128, 0, st>>>(q, q_ld, P, p->D, e, g, g_ld, make_coin<T, DT>(p));
       break;
     default:
       return fail(EHMC_ERR_UNSUPPORTED, "eval: family %d", p->family);

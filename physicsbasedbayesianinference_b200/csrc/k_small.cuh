@@ -76,6 +76,23 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL)
   }
 };
 
+template <typename T, int DT>
+struct CoinPot {  // EHMC_FAMILY_COIN_TOSS: U = -sum k ln q + (n - k) ln(1 - q)
+  T k[DT];        // successes (0 for padded dims)
+  T nk[DT];       // failures n - k
+  __device__ __forceinline__ T grad(const T (&q)[DT], T (&g)[DT], bool wantE) const {
+    T e = T(0);
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      const T a = q[d], b = T(1) - q[d];
+      // padded dims (k = nk = 0, q = 0) must stay exactly 0, not 0/0
+      g[d] = (k[d] != T(0) ? -k[d] / a : T(0)) + (nk[d] != T(0) ? nk[d] / b : T(0));
+      if (wantE) e -= (k[d] != T(0) ? k[d] * log(a) : T(0)) + (nk[d] != T(0) ? nk[d] * log(b) : T(0));
+    }
+    return e;
+  }
+};
+
 // ---------------------------------------------------------------------------
 // momentum draw: p = z * pstd, z fed or from Philox
 // ---------------------------------------------------------------------------

@@ -11,14 +11,15 @@ from __future__ import annotations
 
 import numpy as np
 
-from .potential import FunnelPotential, GaussianPotential, HarmonicPotential, LogisticPotential
+from .potential import CoinTossPotential, FunnelPotential, GaussianPotential, HarmonicPotential, LogisticPotential
 
 
 def potentialFromSpec(spec):
     """spec: dict(family=..., **parameters) -> potential descriptor.
 
     families: "normal_iid" (scale per dim), "mvn" (mean, cov | precision),
-    "funnel" (numDimensions, sigmaV), "logistic_regression" (X, y, priorScale)."""
+    "funnel" (numDimensions, sigmaV), "coin_toss" (observations | successes, trials),
+    "logistic_regression" (X, y, priorScale)."""
     fam = spec.get("family")
     if fam == "normal_iid":
         scale = np.atleast_1d(np.asarray(spec["scale"], dtype=np.float64))
@@ -29,11 +30,15 @@ def potentialFromSpec(spec):
         return GaussianPotential(cov=spec["cov"], mean=spec.get("mean"))
     if fam == "funnel":
         return FunnelPotential(int(spec["numDimensions"]), float(spec.get("sigmaV", 3.0)))
+    if fam == "coin_toss":  # Uniform(0, 1) priors, Bernoulli observations (CoinToss.py:21-25)
+        if "observations" in spec:
+            return CoinTossPotential.fromObservations(*spec["observations"])
+        return CoinTossPotential(spec["successes"], spec["trials"])
     if fam == "logistic_regression":
         return LogisticPotential(spec["X"], spec["y"], float(spec.get("priorScale", 1.0)),
                                  precision=spec.get("precision", "fp32"))
     raise NotImplementedError(
-        f"model family {fam!r} has no fused CUDA kernel; supported: normal_iid, mvn, funnel, logistic_regression")
+        f"model family {fam!r} has no fused CUDA kernel; supported: normal_iid, mvn, funnel, coin_toss, logistic_regression")
 
 
 def potentialFromNumpyroModel(model, model_args=(), model_kwargs=None):
@@ -50,6 +55,11 @@ def potentialFromNumpyroModel(model, model_args=(), model_kwargs=None):
     tr = handlers.trace(handlers.seed(model, jax.random.PRNGKey(0))).get_trace(*model_args, **(model_kwargs or {}))
     latent = [s for s in tr.values() if s["type"] == "sample" and not s["is_observed"]]
     observed = [s for s in tr.values() if s["type"] == "sample" and s["is_observed"]]
+    if latent and len(latent) == len(observed) and all(
+            isinstance(s["fn"], dist.Uniform) and float(s["fn"].low) == 0.0 and float(s["fn"].high) == 1.0 for s in latent) and all(
+            isinstance(getattr(s["fn"], "base_dist", s["fn"]), (dist.BernoulliProbs,)) for s in observed):
+        # the coin-toss sample: site k observes Bernoulli(latent k)
+        return potentialFromSpec(dict(family="coin_toss", observations=[np.asarray(s["value"]) for s in observed]))
     if len(latent) == 1 and not observed:
         d = latent[0]["fn"]
         if isinstance(d, dist.MultivariateNormal):

@@ -133,6 +133,33 @@ class FunnelPotential(Potential):
         return [self.numDimensions, self.sigmaV]
 
 
+class CoinTossPotential(Potential):
+    """Independent coin biases q_d in (0, 1) under a flat prior -- the model of the reference's
+    NumPyro sample (samples/NumpyroExamples/CoinToss/CoinToss.py:6-25):
+
+        U(q) = -sum_d [ k_d ln q_d + (n_d - k_d) ln(1 - q_d) ]
+
+    successes k_d out of trials n_d per coin.  The gradient -k/q + (n-k)/(1-q) vanishes at
+    q = k/n (references/NotesOnParticleBasedHMC.pdf eq. 22; CoinTossExample.py:102-109)."""
+
+    family = _lib.FAMILY_COIN_TOSS
+
+    def __init__(self, successes, trials):
+        self.successes = np.atleast_1d(np.asarray(successes, dtype=np.float64)).copy()
+        self.trials = np.atleast_1d(np.asarray(trials, dtype=np.float64)).copy()
+        if self.successes.shape != self.trials.shape:
+            raise ValueError("successes and trials must have the same length")
+        super().__init__(self.successes.shape[0])
+
+    @classmethod
+    def fromObservations(cls, *coins):
+        """One 0/1 outcome array per coin, as in CoinToss.data.json (c1, c2)."""
+        return cls([float(np.sum(c)) for c in coins], [float(np.size(c)) for c in coins])
+
+    def _params(self):
+        return [self.successes, self.trials]
+
+
 class NBodyPotential(Potential):
     """Every ensemble particle is a whole B-body system; coordinates are flattened
     component-major, d = c*B + b (the reference's own convention, src/potential.py:83-84).

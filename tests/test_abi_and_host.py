@@ -197,6 +197,9 @@ def test_model_spec_adapter():
     assert isinstance(A.potentialFromSpec(dict(family="funnel", numDimensions=10)), E.FunnelPotential)
     X = np.ones((4, 3))
     assert A.potentialFromSpec(dict(family="logistic_regression", X=X, y=np.ones(4))).numDimensions == 3
+    # the reference's own NumPyro sample model (CoinToss.data.json: c1, c2)
+    p = A.potentialFromSpec(dict(family="coin_toss", observations=[[1, 0] * 10, [1] * 15 + [0] * 5]))
+    assert isinstance(p, E.CoinTossPotential) and list(p.successes) == [10, 15] and list(p.trials) == [20, 20]
     with pytest.raises(NotImplementedError):
         A.potentialFromSpec(dict(family="eight_schools"))
     with pytest.raises((ImportError, NotImplementedError)):

@@ -599,6 +599,47 @@ def test_logistic_eval_matches_oracle(E, N, D):
         assert rel_err(pe.gradient(q.astype(dt)), po.grad(q)) < 20 * RTOL[dt]
 
 
+def test_coin_toss_family_KA6_and_hmc(E):
+    """The reference's NumPyro sample model (samples/NumpyroExamples/CoinToss): gradient zero at the
+    reference biases (KA6), energy/gradient and one HMC iteration against the oracle."""
+    import torch
+
+    c1, c2 = [1, 0] * 10, [1] * 15 + [0] * 5
+    pe = E.CoinTossPotential.fromObservations(c1, c2)
+    po = O.CoinToss([10, 15], [20, 20])
+    assert np.array_equal(pe.gradient(np.array([0.5, 0.75])), np.zeros(2))  # KA6, exact in binary
+    rng = np.random.RandomState(4)
+    P = 500
+    q0 = rng.uniform(0.2, 0.8, (2, P))
+    for dt in (np.float64, np.float32):
+        assert rel_err(pe(q0.astype(dt)), po.energy(q0)) < 20 * RTOL[dt]
+        assert rel_err(pe.gradient(q0.astype(dt)), po.grad(q0)) < 20 * RTOL[dt]
+    z = rng.standard_normal((2, P)) * 0.3
+    u = rng.uniform(size=P)
+    mass = rng.uniform(0.5, 2.0, P)
+    h, L = 0.01, 12
+    qr, pr, accr, oh, nh = O.hmc_iter(q0, z, u, mass, 1 / KB, h, L, po)
+    ctx = E._lib.Context.get()
+    for dt, bits, tol in ((np.float64, 64, 1e-12), (np.float32, 32, 1e-5)):
+        tdt = torch.float64 if bits == 64 else torch.float32
+        q = torch.tensor(q0, dtype=tdt, device="cuda")
+        p = torch.empty_like(q)
+        acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+        args = E._lib.make_args(h, h**2, L, KB, 1 / KB, flags=0)
+        E._lib.hmc_iter(ctx, pe.handle(bits, ctx), q, torch.tensor(mass, dtype=tdt, device="cuda"), args, p_out=p,
+                        z=torch.tensor(z, dtype=tdt, device="cuda"), u=torch.tensor(u, dtype=tdt, device="cuda"),
+                        accept=acc)
+        torch.cuda.synchronize()
+        a = acc.cpu().numpy().astype(bool)
+        with np.errstate(over="ignore", invalid="ignore"):
+            clear = np.abs(u - np.minimum(1, np.exp(oh - nh))) > TIE[dt]
+        clear &= np.isfinite(nh)  # a trajectory that left (0, 1) has H = NaN on both sides
+        assert np.array_equal(a[clear], accr[clear])
+        same = (a == accr) & np.isfinite(nh)
+        assert same.sum() > 0.8 * P
+        assert rel_err(q.cpu().numpy()[:, same], qr[:, same]) < tol
+
+
 @pytest.mark.parametrize("family", ["nbody", "logistic"])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_families_production_equals_fed_and_stats(E, family, dt):

@@ -151,6 +151,27 @@ def test_closed_form_gradients_vs_finite_difference(pot, D):
         np.testing.assert_allclose(g[d], fd, rtol=2e-6, atol=1e-8)
 
 
+def test_coin_toss_known_answer_KA6():
+    """the reference's coin-toss sample (samples/NumpyroExamples/CoinToss/CoinToss.data.json:
+    10 of 20 and 15 of 20 ones, reference biases p1 = 0.5, p2 = 0.75) -- the gradient of the log density
+    vanishes at the reference biases (CoinTossExample.py:102-109; NotesOnParticleBasedHMC.pdf eq. 22)."""
+    c1 = [1, 0] * 10
+    c2 = [1] * 15 + [0] * 5
+    pot = O.CoinToss([sum(c1), sum(c2)], [len(c1), len(c2)])
+    assert np.array_equal(pot.grad(np.array([0.5, 0.75])), np.zeros(2))
+    # and it is the minimum of U = -log density: 20 ln 2 + (-15 ln .75 - 5 ln .25)
+    u_ref = 20 * np.log(2.0) - 15 * np.log(0.75) - 5 * np.log(0.25)
+    assert abs(pot.energy(np.array([0.5, 0.75])) - u_ref) < 1e-12
+    assert pot.energy(np.array([0.45, 0.75])) > u_ref and pot.energy(np.array([0.5, 0.8])) > u_ref
+    # closed-form gradient == central difference inside (0, 1)
+    q = np.array([[0.3, 0.6], [0.7, 0.2]])
+    for d in range(2):
+        e = np.zeros((2, 1))
+        e[d] = 1e-6
+        fd = (pot.energy(q + e) - pot.energy(q - e)) / 2e-6
+        np.testing.assert_allclose(pot.grad(q)[d], fd, rtol=1e-6)
+
+
 def test_philox_known_answer():
     """Random123 known-answer vectors for Philox4x32-10."""
     out = O.philox4x32_10(0, 0, 0, 0, 0, 0)
