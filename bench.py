@@ -297,9 +297,12 @@ def main():
         torch.cuda.synchronize()
 
     adaptive = args.config.startswith("c5")  # config 5: ensemble statistics all-reduced every iteration
+    # EHMC_DEVICE_ADAPT=1: step size / iteration counter in device-resident control blocks (HMC.run(deviceAdapt=True));
+    # default is the host-side adapter fed through a side stream -- measured equally fast (profiles/r01_adapt_probe.txt)
+    dev_adapt = os.environ.get("EHMC_DEVICE_ADAPT", "0") == "1"
     group = dist.group.WORLD if world > 1 else None
     if adaptive:
-        hmc.run(args.warmup, 1 / KB, adapt=True, group=group, keepNumSteps=True)
+        hmc.run(args.warmup, 1 / KB, adapt=True, group=group, keepNumSteps=True, deviceAdapt=dev_adapt)
     else:
         for _ in range(args.warmup):
             hmc.step(1 / KB)
@@ -311,7 +314,7 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
     if adaptive:
-        run_out = hmc.run(args.steps, 1 / KB, adapt=True, group=group, keepNumSteps=True)
+        run_out = hmc.run(args.steps, 1 / KB, adapt=True, group=group, keepNumSteps=True, deviceAdapt=dev_adapt)
         for i in range(args.steps):
             ev[i + 1] = ev[0]
         ev[-1] = torch.cuda.Event(enable_timing=True)
@@ -322,6 +325,7 @@ def main():
             ev[i + 1].record()
     barrier()
     launches = ctx.launch_count() - launches0
+
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step = [total_ms / args.steps] if adaptive else [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]

@@ -126,7 +126,21 @@ typedef struct {
   uint64_t seed;           /* Philox key */
   uint64_t iteration;      /* HMC iteration index (Philox counter word 3) */
   uint64_t particleOffset; /* global index of column 0 (multi-GPU shards) */
+  const void* dynamic;     /* optional DEVICE pointer to an ehmc_dynamic: when set, stepSize (and its
+                              square) and iteration are read from it by the kernel at run time instead of
+                              from this struct (device tensors, small-D and float32 dense families) */
 } ehmc_hmc_args;
+
+/* Device-resident control block of an adaptive run: a whole iteration -- trajectory kernel,
+ * statistics all-reduce, step-size update (ehmc_adapt_step) -- is enqueued, or replayed from a CUDA
+ * graph, without the host reading anything back (build-defined: the reference has no adaptation). */
+typedef struct {
+  double stepSize;     /* h of the next ehmc_hmc_iter handed this block */
+  double logStepSize;
+  uint64_t iteration;  /* Philox iteration word of the next ehmc_hmc_iter */
+  uint64_t updates;    /* Robbins-Monro updates applied so far (k) */
+  uint64_t row;        /* next row of `history` */
+} ehmc_dynamic;
 
 /* ---- library / context ---------------------------------------------------- */
 EHMC_API int ehmc_version(void);
@@ -212,6 +226,22 @@ EHMC_API int ehmc_integrate_nbody_mode(ehmc_ctx* ctx, int integrator, DLTensor* 
 EHMC_API int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p_out,
                   const DLTensor* mass, const ehmc_hmc_args* args, const DLTensor* z,
                   const DLTensor* u, DLTensor* accept_out, DLTensor* stats_out, void* stream);
+
+/* Consumes the (all-reduced) statistics of the iteration that just ran with the block `dynamic`:
+ *   history[dynamic.row] = {acceptRate, meanAcceptProb, meanH, stepSize used}  (optional, float64 [S,4])
+ *   moments[0:D] += sum q_d, moments[D:2D] += sum q_d^2                        (optional, float64 [2D])
+ *   (log h, k) are taken from `state` (NULL: from `dynamic` itself) and, if dynamic.row < adaptRows,
+ *       log h += clip(gain0 / k^kappa * (meanAcceptProb - targetAccept), +-maxMove),
+ *       clipped to [log minStep, log maxStep]                                   (parallel.StepSizeAdapter)
+ *   the result is written to `dynamic`;  dynamic.iteration += stride, dynamic.row += stride.
+ * stride = 1, state = NULL: plain sequential adaptation.  stride = 2 with two blocks used alternately
+ * (state = the other block) gives the one-iteration-stale pipeline of HMC.run: the update computed from
+ * iteration k - 1 is consumed by iteration k + 1 and overlaps iteration k.
+ * One tiny kernel on `stream`; every rank computes the same update from the same reduced numbers. */
+EHMC_API int ehmc_adapt_step(ehmc_ctx* ctx, const DLTensor* stats, double numParticlesTotal, double targetAccept,
+                    double gain0, double kappa, double maxMove, double minStep, double maxStep,
+                    uint64_t adaptRows, void* dynamic, const void* state, uint64_t stride, DLTensor* history,
+                    DLTensor* moments, void* stream);
 
 #ifdef __cplusplus
 }

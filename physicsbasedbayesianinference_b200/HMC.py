@@ -112,12 +112,12 @@ class HMC:
         return (_lib.FLAG_BUGCOMPAT_MOMENTUM if self.bugCompat else 0) | (
             _lib.FLAG_REJECT_NONFINITE if self.rejectNonFinite else 0)
 
-    def _args(self, temperature):
+    def _args(self, temperature, dynamic=None):
         integ = _lib.LEAPFROG if self.method == "Leapfrog" else _lib.STORMER_VERLET
         return _lib.make_args(self.stepSize, self.stepSize**2, self.integrator.numSteps, boltzmannConst, temperature,
-                              integ, self._flags(), self.seed, self.iteration, self.ensemble.particleOffset)
+                              integ, self._flags(), self.seed, self.iteration, self.ensemble.particleOffset, dynamic)
 
-    def step(self, temperature, p_out=None, accept=None, stats=None, z=None, u=None):
+    def step(self, temperature, p_out=None, accept=None, stats=None, z=None, u=None, dynamic=None):
         """One HMC iteration on ``integrator.q`` in place (the body of getSamples' loop)."""
         q = self.integrator.q
         host = isinstance(q, np.ndarray)
@@ -126,7 +126,7 @@ class HMC:
         mass = self.integrator.mass
         if host:
             mass = np.ascontiguousarray(mass, dtype=q.dtype)
-        args = self._args(temperature)
+        args = self._args(temperature, dynamic)
         _lib.hmc_iter(ctx, self.potential.handle(bits, ctx), q, mass, args, p_out=p_out, z=z, u=u, accept=accept,
                       stats=stats, stream=_lib.current_stream_ptr(q))
         self.iteration += 1
@@ -187,7 +187,7 @@ class HMC:
 
     # ------------------------------------------------------------------------------------
     def run(self, numIterations, temperature, *, adapt=False, targetAccept=0.8, adaptIterations=None,
-            traceParticles=0, group=None, collectStats=True, keepNumSteps=False):
+            traceParticles=0, group=None, collectStats=True, keepNumSteps=False, deviceAdapt=False, graph=False):
         """Production loop for device ensembles (build-defined; scales where getSamples'
         (D, P, S) arrays cannot, SURVEY.md section 7 hard part 7).
 
@@ -201,9 +201,21 @@ class HMC:
         numSteps = int(simulTime / stepSize) follows (src/integrator.py:51).  keepNumSteps=True keeps
         the number of leapfrog steps instead (simulTime = numSteps * stepSize follows).
 
+        deviceAdapt=True keeps the step size and the Philox iteration counter in a device-resident
+        control block (ehmc_dynamic): the trajectory kernel reads them at run time and a tiny kernel
+        (ehmc_adapt_step) applies the update after the all-reduce, so the host never waits for a value
+        (same one-iteration-stale pipeline as the host-side loop, same results); graph=True replays
+        blocks of iterations from a CUDA graph.  The number of leapfrog steps stays fixed in this mode.
+        Measured at config 5 (profiles/r01_adapt_probe.txt): host loop 285 us / iteration, device blocks
+        287 us, graph 373 us -- the cross-stream edges a graph needs for the overlap cost more than the
+        Python enqueue they save, so graph replay is off by default.
+
         Returns dict(acceptRate[S], meanAcceptProb[S], meanH[S], stepSize[S], mean[D], var[D],
         trace (D, traceParticles, S) or None).
         """
+        if deviceAdapt:
+            return self._run_device_adapt(numIterations, temperature, adapt, targetAccept, adaptIterations,
+                                          traceParticles, group, graph)
         import torch
 
         from .parallel import StatsReducer, StepSizeAdapter, unpack_stats
@@ -285,6 +297,102 @@ class HMC:
         mean = sum1 / n
         out.update(mean=mean, var=sum2 / n - mean * mean, trace=trace, worldSize=world)
         return out
+
+
+    def _run_device_adapt(self, numIterations, temperature, adapt, targetAccept, adaptIterations, traceParticles,
+                          group, graph, graphIterations=10):
+        """Two control blocks used alternately: iteration k runs with block k & 1; on a side stream the
+        statistics of iteration k are all-reduced and ehmc_adapt_step writes the block iteration k + 2
+        will read, taking the adaptation state from the other block.  Iteration k + 1 therefore only
+        waits for the update computed from iteration k - 1 (the one-iteration-stale pipeline of the
+        host-side loop) and the all-reduce overlaps iteration k + 1."""
+        import torch
+
+        from .parallel import StatsReducer
+
+        ens = self.ensemble
+        if not ens.onDevice:
+            raise TypeError("HMC.run needs a device-backed Ensemble (device='cuda')")
+        if graph and traceParticles:
+            raise ValueError("traceParticles needs graph=False (the trace slot changes every iteration)")
+        D, P, dev = ens.numDimensions, ens.numParticles, ens.device
+        reducer = StatsReducer(group)
+        world = reducer.dist.get_world_size(group) if reducer.enabled else 1
+        Ptot = float(P)
+        if reducer.enabled:
+            t = torch.tensor([P], dtype=torch.float64, device=dev)
+            reducer.dist.all_reduce(t, group=group)
+            Ptot = float(t.item())
+        ctx = _lib.Context.get(dev.index)
+        adaptRows = 0 if not adapt else (numIterations if adaptIterations is None else adaptIterations)
+        it0 = self.iteration
+        blocks = [_lib.dynamic_to_device(self.stepSize, it0 + b, dev, row=b) for b in range(2)]
+        stats = [torch.zeros(2 * D + 3, dtype=torch.float64, device=dev) for _ in range(2)]
+        hist = torch.zeros((numIterations, 4), dtype=torch.float64, device=dev)
+        mom = torch.zeros(2 * D, dtype=torch.float64, device=dev)
+        trace = (torch.empty((D, traceParticles, numIterations), dtype=ens.dtype, device=dev)
+                 if traceParticles else None)
+        self.integrator.q = ens.q
+        numSteps = self.integrator.numSteps
+        # high priority: the 1-block update kernel and the small all-reduce must not queue behind the
+        # thousands of CTAs of the running trajectory kernel
+        side = torch.cuda.Stream(dev, priority=-1)
+
+        def enqueue(k0, n, main):
+            """Iterations k0 .. k0 + n - 1 on `main` + `side`; joins the two streams at the end."""
+            ran = [None, None]      # per parity: event "kernel + statistics of this parity done"
+            adapted = [None, None]  # per parity: event "block of this parity rewritten"
+            for k in range(k0, k0 + n):
+                b = k & 1
+                if adapted[b] is not None:
+                    main.wait_event(adapted[b])  # block b and stats[b] are free / up to date
+                self.step(temperature, stats=stats[b], dynamic=blocks[b].data_ptr())
+                if trace is not None:
+                    trace[:, :, k] = ens.q[:, :traceParticles]
+                ran[b] = torch.cuda.Event()
+                ran[b].record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ran[b])
+                    reducer.reduce(stats[b])
+                    _lib.adapt_step(ctx, stats[b], Ptot, blocks[b].data_ptr(), target=targetAccept,
+                                    adapt_rows=adaptRows, state_ptr=blocks[1 - b].data_ptr(), stride=2, history=hist,
+                                    moments=mom, stream=_lib.current_stream_ptr(stats[b]))
+                    adapted[b] = torch.cuda.Event()
+                    adapted[b].record(side)
+            main.wait_stream(side)
+
+        main = torch.cuda.current_stream(dev)
+        side.wait_stream(main)
+        G = int(graphIterations) & ~1
+        if graph and G >= 2 and numIterations >= 2 + G:
+            # eager head: sizes the library's scratch buffers outside the capture and leaves a multiple of G
+            head = 2 + (numIterations - 2) % G
+            enqueue(0, head, main)
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(dev)
+            cap.wait_stream(main)
+            with torch.cuda.stream(cap):
+                # capture executes nothing; step size / iteration / history row advance on the device at replay
+                with torch.cuda.graph(g, stream=cap):
+                    enqueue(head, G, cap)
+            main.wait_stream(cap)
+            self.iteration = it0 + head  # the captured calls advanced the host counter; it is reset below anyway
+            for _ in range((numIterations - head) // G):
+                g.replay()
+        else:
+            enqueue(0, numIterations, main)
+        self.iteration = it0 + numIterations
+        newest = _lib.dynamic_from_device(blocks[(numIterations - 1) & 1 if numIterations else 0])  # synchronises
+        self.stepSize = float(newest.stepSize)
+        self.integrator.stepSize = self.stepSize
+        self.simulTime = self.integrator.finalTime = numSteps * self.stepSize
+        h = hist.cpu().numpy()
+        m = mom.cpu().numpy()
+        n = float(max(numIterations, 1)) * Ptot
+        mean = torch.from_numpy(m[:D] / n)
+        return dict(acceptRate=list(h[:, 0]), meanAcceptProb=list(h[:, 1]), meanH=list(h[:, 2]), stepSize=list(h[:, 3]),
+                    numSteps=[numSteps] * numIterations, mean=mean, var=torch.from_numpy(m[D:] / n) - mean * mean,
+                    trace=trace, worldSize=world)
 
 
 class GaussianDensity:

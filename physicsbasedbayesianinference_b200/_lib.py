@@ -33,7 +33,7 @@ SYMBOLS = (
     "ehmc_version", "ehmc_last_error", "ehmc_ctx_create", "ehmc_ctx_destroy", "ehmc_ctx_launch_count",
     "ehmc_ctx_device_info", "ehmc_ctx_set_option", "ehmc_measure_fp32_peak", "ehmc_potential_create", "ehmc_potential_destroy",
     "ehmc_potential_eval", "ehmc_set_position", "ehmc_set_momentum", "ehmc_philox_fill", "ehmc_leapfrog",
-    "ehmc_stormer_verlet", "ehmc_integrate_nbody_mode", "ehmc_hmc_iter",
+    "ehmc_stormer_verlet", "ehmc_integrate_nbody_mode", "ehmc_hmc_iter", "ehmc_adapt_step",
 )
 
 
@@ -58,6 +58,19 @@ class HmcArgs(ctypes.Structure):
         ("seed", ctypes.c_uint64),
         ("iteration", ctypes.c_uint64),
         ("particleOffset", ctypes.c_uint64),
+        ("dynamic", ctypes.c_void_p),
+    ]
+
+
+class Dynamic(ctypes.Structure):
+    """struct ehmc_dynamic (include/ehmc.h): device-resident step size / iteration of an adaptive run."""
+
+    _fields_ = [
+        ("stepSize", ctypes.c_double),
+        ("logStepSize", ctypes.c_double),
+        ("iteration", ctypes.c_uint64),
+        ("updates", ctypes.c_uint64),
+        ("row", ctypes.c_uint64),
     ]
 
 
@@ -97,6 +110,7 @@ def load():
             "ehmc_stormer_verlet": [vp, vp, vp, vp, vp, cd, cd, ci, vp],
             "ehmc_integrate_nbody_mode": [vp, ci, vp, vp, vp, cd, cd, cd, ci, vp],
             "ehmc_hmc_iter": [vp, vp, vp, vp, vp, ctypes.POINTER(HmcArgs), vp, vp, vp, vp, vp],
+            "ehmc_adapt_step": [vp, vp, cd, cd, cd, cd, cd, cd, cd, u64, vp, vp, u64, vp, vp, vp],
         }
         for name, args in sigs.items():
             fn = getattr(lib, name)
@@ -264,7 +278,7 @@ def integrate_nbody_mode(ctx, integrator, q, p, mass, grav, step_size, step_size
 
 
 def make_args(step_size, step_size_sq, num_steps, boltzmann, temperature, integrator=LEAPFROG, flags=0, seed=0,
-              iteration=0, particle_offset=0):
+              iteration=0, particle_offset=0, dynamic=None):
     a = HmcArgs()
     a.struct_size = ctypes.sizeof(HmcArgs)
     a.flags = int(flags)
@@ -277,7 +291,32 @@ def make_args(step_size, step_size_sq, num_steps, boltzmann, temperature, integr
     a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     a.iteration = int(iteration) & 0xFFFFFFFFFFFFFFFF
     a.particleOffset = int(particle_offset)
+    a.dynamic = None if dynamic is None else int(dynamic)
     return a
+
+
+def dynamic_to_device(step_size, iteration, device, row=0):
+    """A device copy of ehmc_dynamic (as a uint8 tensor; pass ``.data_ptr()`` as args.dynamic)."""
+    import math
+
+    import torch
+
+    d = Dynamic(float(step_size), math.log(step_size), int(iteration), 0, int(row))
+    return torch.frombuffer(bytearray(bytes(d)), dtype=torch.uint8).to(device)
+
+
+def dynamic_from_device(t):
+    return Dynamic.from_buffer_copy(t.cpu().numpy().tobytes())
+
+
+def adapt_step(ctx, stats, num_particles_total, dynamic_ptr, target=0.8, gain0=1.5, kappa=0.5, max_move=0.7,
+               min_step=1e-6, max_step=1e3, adapt_rows=1 << 62, state_ptr=None, stride=1, history=None, moments=None,
+               stream=None):
+    vs, vh, vm = dl(stats), dl(history), dl(moments)
+    check(ctx.lib.ehmc_adapt_step(ctx.handle, vs.ptr, float(num_particles_total), float(target), float(gain0),
+                                  float(kappa), float(max_move), float(min_step), float(max_step), int(adapt_rows),
+                                  int(dynamic_ptr), None if state_ptr is None else int(state_ptr), int(stride),
+                                  _p(vh), _p(vm), stream))
 
 
 def hmc_iter(ctx, pot, q, mass, args, p_out=None, z=None, u=None, accept=None, stats=None, stream=None):

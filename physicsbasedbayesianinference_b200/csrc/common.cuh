@@ -164,6 +164,11 @@ struct NormalBlock<double> {
 // Kernel argument block shared by every fused trajectory kernel.
 // (D,P) arrays: element [d, i] at base[d * ld + i].
 // ---------------------------------------------------------------------------
+struct DynArgs {  // == ehmc_dynamic (include/ehmc.h)
+  double stepSize, logStepSize;
+  u64 iteration, updates, row;
+};
+
 template <typename T>
 struct IterArgs {
   T* q;
@@ -184,7 +189,20 @@ struct IterArgs {
   double kB, temp;
   double pscale;  // sqrt(kB * temp), host-computed
   u64 seed, iter, offset;
+  const DynArgs* dyn;  // optional device-resident step size / iteration (ehmc_dynamic)
 };
+
+// kernel-side copy of the arguments with the dynamic fields resolved
+template <typename T>
+__device__ __forceinline__ IterArgs<T> resolve_dynamic(const IterArgs<T>& in) {
+  IterArgs<T> A = in;
+  if (in.dyn != nullptr) {
+    A.h = (T)in.dyn->stepSize;
+    A.h2 = A.h * A.h;
+    A.iter = in.dyn->iteration;
+  }
+  return A;
+}
 
 constexpr unsigned FLAG_BUGCOMPAT = 1u;
 constexpr unsigned FLAG_REJECT_NONFINITE = 2u;

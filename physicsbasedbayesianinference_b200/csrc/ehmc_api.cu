@@ -826,7 +826,16 @@ extern "C" int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor*
     A.seed = a->seed;
     A.iter = a->iteration;
     A.offset = a->particleOffset;
+    A.dyn = static_cast<const DynArgs*>(a->dynamic);
   };
+  if (a->dynamic != nullptr) {
+    // only kernels that resolve the block themselves; everything else would silently use the host values
+    const bool small = pot->family == EHMC_FAMILY_DIAG_GAUSSIAN || pot->family == EHMC_FAMILY_FUNNEL ||
+                       pot->family == EHMC_FAMILY_COIN_TOSS || (pot->family == EHMC_FAMILY_DENSE_GAUSSIAN && pot->D <= 16);
+    const bool tc3 = v.bits == 32 && use_dense_tc(ctx, pot, a->integrator) && (ctx->dense_path == 0 || ctx->dense_path == 4);
+    if (v.q.host || !(small || tc3))
+      return fail(EHMC_ERR_UNSUPPORTED, "%s: args.dynamic needs device tensors and a small-D or float32 dense (tensor-core) potential", fn);
+  }
   if (v.bits == 32) {
     IterArgs<float> A = base_args<float>(v, a->stepSize, a->stepSizeSq, a->numSteps);
     fill(A);
@@ -839,6 +848,78 @@ extern "C" int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor*
   if (v.q.host) return run_host<double>(ctx, pot, v, A, a->integrator, true);
   return run_device<double>(ctx, pot, A, a->integrator, true,
                             v.has_stats ? reinterpret_cast<double*>(v.stats.data) : nullptr, st);
+}
+
+// ---------------------------------------------------------------------------
+// device-side step-size adaptation (ehmc_dynamic)
+// ---------------------------------------------------------------------------
+static __global__ void k_adapt_step(const double* __restrict__ stats, int D, double P, double target, double gain0,
+                                    double kappa, double maxMove, double logLo, double logHi, u64 adaptRows,
+                                    DynArgs* dyn, const DynArgs* state, u64 stride, double* history,
+                                    long long hist_rows, double* moments) {
+  const int t = threadIdx.x;
+  if (moments != nullptr)
+    for (int j = t; j < 2 * D; j += blockDim.x) moments[j] += stats[3 + j];
+  if (t != 0) return;
+  const double meanAcc = stats[1] / P;
+  const u64 row = dyn->row;
+  if (history != nullptr && (long long)row < hist_rows) {
+    history[4 * row + 0] = stats[0] / P;
+    history[4 * row + 1] = meanAcc;
+    history[4 * row + 2] = stats[2] / P;
+    history[4 * row + 3] = dyn->stepSize;
+  }
+  double logh = state->logStepSize;
+  u64 k = state->updates;
+  if (row < adaptRows) {
+    k += 1;
+    const double acc = isfinite(meanAcc) ? meanAcc : 0.0;
+    double move = gain0 / pow((double)k, kappa) * (acc - target);
+    move = fmin(fmax(move, -maxMove), maxMove);
+    logh = fmin(fmax(logh + move, logLo), logHi);
+  }
+  dyn->logStepSize = logh;
+  dyn->stepSize = row < adaptRows ? exp(logh) : state->stepSize;
+  dyn->updates = k;
+  dyn->iteration += stride;
+  dyn->row = row + stride;
+}
+
+extern "C" int ehmc_adapt_step(ehmc_ctx* ctx, const DLTensor* stats, double numParticlesTotal, double targetAccept,
+                               double gain0, double kappa, double maxMove, double minStep, double maxStep,
+                               uint64_t adaptRows, void* dynamic, const void* state, uint64_t stride, DLTensor* history,
+                               DLTensor* moments, void* stream) {
+  const char* fn = "ehmc_adapt_step";
+  if (!ctx || !stats || !dynamic) return fail(EHMC_ERR_INVALID, "%s: NULL argument", fn);
+  View vs, vh, vm;
+  TRY(parse_float(stats, "stats", 1, 64, &vs));
+  if (vs.host || vs.shape[0] < 5 || ((vs.shape[0] - 3) & 1)) return fail(EHMC_ERR_INVALID, "%s: stats must be a device float64[2D+3]", fn);
+  const int D = (int)((vs.shape[0] - 3) / 2);
+  if (!(numParticlesTotal > 0) || !(minStep > 0) || !(maxStep >= minStep) || stride < 1)
+    return fail(EHMC_ERR_INVALID, "%s: bad scalar arguments", fn);
+  double* hist = nullptr;
+  long long hist_rows = 0;
+  if (history) {
+    TRY(parse_float(history, "history", 2, 64, &vh));
+    if (vh.host || vh.shape[1] != 4 || vh.ld != 4) return fail(EHMC_ERR_INVALID, "%s: history must be a contiguous device float64[S,4]", fn);
+    hist = reinterpret_cast<double*>(vh.data);
+    hist_rows = vh.shape[0];
+  }
+  double* mom = nullptr;
+  if (moments) {
+    TRY(parse_float(moments, "moments", 1, 64, &vm));
+    if (vm.host || vm.shape[0] != 2 * D) return fail(EHMC_ERR_INVALID, "%s: moments must be a device float64[2D]", fn);
+    mom = reinterpret_cast<double*>(vm.data);
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  k_adapt_step<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const double*>(vs.data), D, numParticlesTotal,
+                                                                targetAccept, gain0, kappa, maxMove, std::log(minStep),
+                                                                std::log(maxStep), adaptRows, static_cast<DynArgs*>(dynamic),
+                                                                static_cast<const DynArgs*>(state ? state : dynamic), stride,
+                                                                hist, hist_rows, mom);
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return EHMC_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -232,8 +232,9 @@ __device__ __noinline__ float tc3_energy(uint32_t t_d, uint32_t t_hi, uint32_t t
 }
 
 template <int C8>
-__global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<float> A, const DenseTc3Args pa,
+__global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<float> Ain, const DenseTc3Args pa,
                                                               const int hmc) {
+  const IterArgs<float> A = resolve_dynamic(Ain);
   typedef Tc3Shape<C8> S;
   constexpr int NP = S::NP, KP = S::KP, K16 = S::K16, DC = S::DC, KCH = S::KCH;
   extern __shared__ __align__(128) unsigned char tc3_smem_raw[];

@@ -260,8 +260,9 @@ __device__ __forceinline__ void block_partials(double* out_row, int D, const dou
 // doubles cost 3x the trajectory itself at config 5).
 // ---------------------------------------------------------------------------
 template <typename T, int DT, class Pot, int INTEG, bool HMC>
-__global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> A, const Pot pot) {
+__global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, const Pot pot) {
   extern __shared__ double k1_smem[];
+  const IterArgs<T> A = resolve_dynamic(Ain);
   constexpr int NA = 2 * DT + 3;
   const bool want_stats = HMC && A.partials != nullptr;
   double* sacc = k1_smem + threadIdx.x;          // [NA][K1_THREADS], this thread's column

@@ -35,8 +35,9 @@ def test_header_symbols_all_exported():
 
 def test_version_and_struct_layout():
     assert _lib.load().ehmc_version() == 100
-    # struct ehmc_hmc_args: 4 x 32-bit, 4 doubles, 3 x u64
-    assert ctypes.sizeof(_lib.HmcArgs) == 16 + 32 + 24
+    # struct ehmc_hmc_args: 4 x 32-bit, 4 doubles, 3 x u64, 1 pointer; struct ehmc_dynamic: 2 doubles, 3 x u64
+    assert ctypes.sizeof(_lib.HmcArgs) == 16 + 32 + 24 + 8
+    assert ctypes.sizeof(_lib.Dynamic) == 40
     a = _lib.make_args(0.1, 0.1**2, int(1.0 / 0.1), 1.380649e-23, 300.0, seed=(1 << 40) + 5, iteration=7)
     assert a.struct_size == ctypes.sizeof(_lib.HmcArgs) and a.numSteps == 10 and a.seed == (1 << 40) + 5
 

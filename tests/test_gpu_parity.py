@@ -890,6 +890,50 @@ def test_run_adaptation_and_moments(E):
     assert 0 < m <= 128 * 120 * 3 and scaled == pytest.approx(m * P / 128)
 
 
+@pytest.mark.parametrize("case", ["funnel10", "dense40"])
+def test_run_device_adaptation_matches_host_adaptation(E, case):
+    """deviceAdapt=True (step size + iteration counter in device-resident ehmc_dynamic blocks, update by
+    ehmc_adapt_step on a side stream, optionally replayed from a CUDA graph) walks the same chain as the
+    host-side loop of HMC.run: same Philox stream, same Robbins-Monro rule, same one-iteration-stale
+    consumption of the statistics."""
+    import torch
+
+    P, S, L = 4096, 27, 6
+    rng = np.random.RandomState(21)
+    if case == "funnel10":
+        D, pot = 10, E.FunnelPotential(10, 3.0)
+    else:
+        D = 40
+        A = rng.standard_normal((D, D))
+        pot = E.GaussianPotential(precision=A @ A.T / D + np.eye(D))
+    q0 = torch.tensor(rng.standard_normal((D, P)), dtype=torch.float32, device="cuda")
+
+    def fresh():
+        ens = E.Ensemble(D, P, dtype=np.float32, device="cuda", seed=5)
+        ens.q.copy_(q0)
+        return ens, E.HMC(ens, L * 0.02 + 1e-9, 0.02, None, potential=pot, seed=5, bugCompat=False)
+
+    ens_h, hmc_h = fresh()
+    rh = hmc_h.run(S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=20, keepNumSteps=True)
+    outs = {}
+    for graph in (False, True):
+        ens_d, hmc_d = fresh()
+        r = hmc_d.run(S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=20, deviceAdapt=True, graph=graph)
+        assert hmc_d.iteration == S and hmc_d.integrator.numSteps == L
+        np.testing.assert_allclose(r["stepSize"], rh["stepSize"], rtol=1e-5)
+        np.testing.assert_allclose(r["meanAcceptProb"], rh["meanAcceptProb"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(r["meanH"], rh["meanH"], rtol=1e-4, atol=1e-4)
+        assert abs(hmc_d.stepSize - hmc_h.stepSize) < 1e-5 * hmc_h.stepSize
+        assert r["stepSize"][0] == 0.02 and r["stepSize"][1] == 0.02 and r["stepSize"][2] != 0.02  # one iteration stale
+        assert r["stepSize"][22] == r["stepSize"][26]  # adaptation stops after adaptIterations
+        np.testing.assert_allclose(r["var"].numpy(), rh["var"].numpy(), rtol=1e-3)
+        outs[graph] = ens_d.q.clone()
+    # eager and graph-replayed runs are the same sequence of launches: bit-identical ensembles
+    assert torch.equal(outs[False], outs[True])
+    # and the chain itself follows the host-adapted one (step sizes agree to ~1e-7 relative)
+    assert rel_err(outs[True].cpu().numpy(), ens_h.q.cpu().numpy()) < 1e-3
+
+
 # ---------------------------------------------------------------------------
 # logistic regression on the tensor cores (bf16 GEMM chain, tcgen05)
 # ---------------------------------------------------------------------------
