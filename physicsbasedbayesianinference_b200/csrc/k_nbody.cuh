@@ -47,33 +47,6 @@ struct V4<double> {
   }
 };
 
-// ---- packed float32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: two lanes of work per issue slot) ----
-// Measured (profiles/microbench/op_rates.cu): the packed instructions issue at 0.5 / clk / SM
-// sub-partition, i.e. the same flop rate as the scalar ones for HALF the issue slots -- the
-// all-pairs loop is issue bound in scalar form (13 slots + loop overhead per interaction against
-// 12 cycles of FMA pipe), so packing two of a thread's bodies per instruction makes it pipe bound.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-  return ((f32x2)__float_as_uint(hi) << 32) | (f32x2)__float_as_uint(lo);
-}
-__device__ __forceinline__ float pk_lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
-__device__ __forceinline__ float pk_hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 // bare MUFU.RSQ: rsqrtf() wraps it in a denormal-input rescue (FSETP + two predicated FMULs per call),
 // which squared distances never need
 __device__ __forceinline__ float rsqrt_ftz(float x) {

@@ -12,6 +12,8 @@
 // warp touches 128 B per dimension.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ehmc {
@@ -34,7 +36,24 @@ struct DiagPot {  // harmonicPotentialND, src/potential.py:27:  0.5 * dot(k, q**
     }
     return Ar<T>::mul(T(0.5), s);
   }
+  static constexpr bool kPacked = true;
+  __device__ __forceinline__ float grad2(const f32x2 (&Q)[(DT + 1) / 2], f32x2 (&G)[(DT + 1) / 2], bool wantE) const {
+    f32x2 S = 0ull;
+#pragma unroll
+    for (int i = 0; i < (DT + 1) / 2; ++i) {
+      G[i] = mul2(pk2((float)k[2 * i], 2 * i + 1 < DT ? (float)k[2 * i + 1] : 0.f), Q[i]);
+      if (wantE) S = fma2(G[i], Q[i], S);
+    }
+    return 0.5f * (pk_lo(S) + pk_hi(S));
+  }
 };
+
+// Packed float32 form of a potential functor (two dimensions per FFMA2 / FMUL2 issue slot), for the
+// functors that define grad2; the others run the scalar form.
+template <class Pot, typename = void>
+struct HasPacked : std::false_type {};
+template <class Pot>
+struct HasPacked<Pot, std::void_t<decltype(Pot::kPacked)>> : std::true_type {};
 
 template <typename T, int DT>
 struct DenseSmallPot {  // U = 0.5 x^T Lambda x, x = q - mu;  grad = Lambda x
@@ -73,6 +92,23 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL)
     const T hs = T(0.5) * ev * s2;
     g[0] = v * inv_s2 - hs + half_dm1;
     return T(0.5) * v * v * inv_s2 + hs + half_dm1 * v;
+  }
+  static constexpr bool kPacked = true;
+  // pair 0 = (v, q_1); padded dims hold q = 0 and contribute nothing
+  __device__ __forceinline__ float grad2(const f32x2 (&Q)[(DT + 1) / 2], f32x2 (&G)[(DT + 1) / 2], bool) const {
+    const float v = pk_lo(Q[0]), q1 = pk_hi(Q[0]);
+    const float ev = expf(-v);
+    const f32x2 ev2 = pk2(ev, ev);
+    f32x2 S = 0ull;
+#pragma unroll
+    for (int i = 1; i < (DT + 1) / 2; ++i) {
+      S = fma2(Q[i], Q[i], S);
+      G[i] = mul2(Q[i], ev2);
+    }
+    const float s2 = fmaf(q1, q1, pk_lo(S) + pk_hi(S));
+    const float hs = 0.5f * ev * s2;
+    G[0] = pk2(v * (float)inv_s2 - hs + (float)half_dm1, ev * q1);
+    return 0.5f * v * v * (float)inv_s2 + hs + (float)half_dm1 * v;
   }
 };
 
@@ -127,7 +163,44 @@ __device__ __forceinline__ T integrate_regs(const Pot& pot, T (&q)[DT], T (&p)[D
                                             bool wantE, T* U0) {
   typedef Ar<T> R;
   const T inv_m = T(1) / m;
-  if constexpr (sizeof(T) == 4 && INTEG == INTEG_LEAPFROG) {
+  if constexpr (sizeof(T) == 4 && INTEG == INTEG_LEAPFROG && HasPacked<Pot>::value) {
+    // float32, packed: the kick-drift-kick recurrence below on pairs of dimensions -- FFMA2 / FMUL2 do two
+    // lanes of work per issue slot and this loop is issue bound (ncu: 78 % issue active, FMA pipe 53 %)
+    constexpr int NP2 = (DT + 1) / 2;
+    f32x2 Q[NP2], V[NP2], G[NP2];
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) {
+      Q[i] = pk2(q[2 * i], 2 * i + 1 < DT ? q[2 * i + 1] : 0.f);
+      V[i] = pk2(p[2 * i] * inv_m, 2 * i + 1 < DT ? p[2 * i + 1] * inv_m : 0.f);
+    }
+    *U0 = pot.grad2(Q, G, wantE);
+    T Uend = *U0;
+    const float hm = h * inv_m, hmh = 0.5f * hm;
+    const f32x2 h2p = pk2(h, h), nhm = pk2(-hm, -hm), nhmh = pk2(-hmh, -hmh);
+    if (L > 0) {
+#pragma unroll
+      for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], nhmh, V[i]);
+    }
+    for (int j = 0; j < L; ++j) {
+#pragma unroll
+      for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
+      const bool last = j == L - 1;
+      Uend = pot.grad2(Q, G, wantE && last);
+      const f32x2 ck = last ? nhmh : nhm;
+#pragma unroll
+      for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], ck, V[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) {
+      q[2 * i] = pk_lo(Q[i]);
+      p[2 * i] = pk_lo(V[i]) * m;
+      if (2 * i + 1 < DT) {
+        q[2 * i + 1] = pk_hi(Q[i]);
+        p[2 * i + 1] = pk_hi(V[i]) * m;
+      }
+    }
+    return Uend;
+  } else if constexpr (sizeof(T) == 4 && INTEG == INTEG_LEAPFROG) {
     // float32: the same recurrence in kick-drift-kick form (v_half = v + a h / 2 ; q += h v_half ;
     // v = v_half + a' h / 2, consecutive half kicks merged): 2 FFMA per dimension and step instead of
     // the 8 operations of the reference's expression order, which only the float64 mode reproduces
