@@ -391,7 +391,7 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
         if (p->bits != 32) { rc = fail(EHMC_ERR_INVALID, "logistic: the tensor-core path needs float32 state"); break; }
         // bf16 chunks of 64 data rows in the canonical UMMA layout [DP/8][64][8] + y[64] (float); LT_NB
         const int D = p->D, N = p->N, DP = (D + 15) / 16 * 16, NB = 64, NC = (N + NB - 1) / NB;
-        const size_t cb = (size_t)DP * NB * 2 + NB * 4;
+        const size_t cb = (size_t)DP * NB * 2 + NB * 4 + NB * 2;  // X | y float | (1/2 - y) half
         std::vector<unsigned char> buf(cb * NC, 0);
         auto bf16 = [](float f) -> uint16_t {
           uint32_t b;
@@ -402,9 +402,11 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
         for (int c = 0; c < NC; ++c) {
           uint16_t* xs = reinterpret_cast<uint16_t*>(buf.data() + cb * c);
           float* ys = reinterpret_cast<float*>(buf.data() + cb * c + (size_t)DP * NB * 2);
+          __half* cs = reinterpret_cast<__half*>(buf.data() + cb * c + (size_t)DP * NB * 2 + NB * 4);
           for (int r = 0; r < NB; ++r) {
             const int n = c * NB + r;
             ys[r] = n < N ? (float)p->hp1[n] : 0.5f;
+            cs[r] = __float2half_rn(0.5f - ys[r]);
             if (n >= N) continue;
             for (int d = 0; d < D; ++d)
               xs[((size_t)(d / 8) * NB + r) * 8 + (d % 8)] = bf16((float)p->hp0[(size_t)n * D + d]);

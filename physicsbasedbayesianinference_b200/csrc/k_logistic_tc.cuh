@@ -31,6 +31,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "k_dense_tc.cuh"
@@ -46,7 +47,7 @@ constexpr int LT_EPI_WARPS = 8;
 constexpr int LT_THREADS = 32 * (2 + LT_EPI_WARPS);
 
 struct LogisticTcArgs {
-  const unsigned char* chunks;  // [NC] blocks of chunk_bytes: X part [DP/8][64][8] bf16, then y[64] float
+  const unsigned char* chunks;  // [NC] blocks of chunk_bytes: X part [DP/8][64][8] bf16, y[64] float, (1/2 - y)[64] half
   int NC;                       // number of chunks
   int DP;                       // D rounded up to 16
   int D;
@@ -254,23 +255,49 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
       tmem_ld16_issue(t_mine + (uint32_t)(b * 64 + 16), sv[1]);
       tmem_wait_ld16(sv[0]);
       tmem_wait_ld16(sv[1]);
-      const float* yv = reinterpret_cast<const float*>(Xs0 + (size_t)s * pa.chunk_bytes + (size_t)DP * LT_NB * 2) + half * 32;
+      const unsigned char* tail = Xs0 + (size_t)s * pa.chunk_bytes + (size_t)DP * LT_NB * 2;
+      const float* yv = reinterpret_cast<const float*>(tail) + half * 32;
       uint32_t rp[16];
+      if (WITH_E) {
+        // energy evaluations (first / last gradient of a trajectory): exact exp / log per logit
 #pragma unroll
-      for (int bb = 0; bb < 2; ++bb)
+        for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float r2[2];
+          for (int i = 0; i < 16; i += 2) {
+            float r2[2];
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const float sgm = __uint_as_float(sv[bb][i + t]);
-            const float yn = yv[16 * bb + i + t];
-            const float sig = fmaf(0.5f, tanh_approx(0.5f * sgm), 0.5f);
-            r2[t] = sig - yn;
-            if (WITH_E) Uacc += fmaxf(sgm, 0.f) + __logf(1.f + __expf(-fabsf(sgm))) - yn * sgm;
+            for (int t = 0; t < 2; ++t) {
+              const float sgm = __uint_as_float(sv[bb][i + t]);
+              const float yn = yv[16 * bb + i + t];
+              const float sig = fmaf(0.5f, tanh_approx(0.5f * sgm), 0.5f);
+              r2[t] = sig - yn;
+              Uacc += fmaxf(sgm, 0.f) + __logf(1.f + __expf(-fabsf(sgm))) - yn * sgm;
+            }
+            rp[(16 * bb + i) / 2] = pack_bf16x2(r2[0], r2[1]);
           }
-          rp[(16 * bb + i) / 2] = pack_bf16x2(r2[0], r2[1]);
+      } else {
+        // gradient only: two logits per MUFU op.  r = 1/2 tanh(s / 2) + (1/2 - y) in half2 (tanh.approx.f16x2,
+        // HFMA2); r is rounded to bf16 (8 significant bits) for GEMM2 anyway, fp16 (11 bits) loses nothing.
+        // (1/2 - y) comes pre-packed as half2 with the chunk.
+        const uint4* cv = reinterpret_cast<const uint4*>(tail + LT_NB * 4) + half * 4;  // 32 halves = 4 x 16 B
+        const __half2 half_ = __float2half2_rn(0.5f);
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const uint4 c4 = cv[g4];
+          const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = 4 * g4 + e;  // pair index: logits 2k, 2k + 1 of my 32
+            const float s0 = __uint_as_float(sv[k >> 3][(2 * k) & 15]), s1 = __uint_as_float(sv[k >> 3][(2 * k + 1) & 15]);
+            const __half2 x = __hmul2(__floats2half2_rn(s0, s1), half_);
+            uint32_t xb = *reinterpret_cast<const uint32_t*>(&x), tb;
+            asm("tanh.approx.f16x2 %0, %1;" : "=r"(tb) : "r"(xb));
+            const __half2 r = __hfma2(*reinterpret_cast<const __half2*>(&tb), half_, *reinterpret_cast<const __half2*>(&cw[e]));
+            const float2 rf = __half22float2(r);
+            rp[k] = pack_bf16x2(rf.x, rf.y);
+          }
         }
+      }
       tmem_st16(t_mine + (uint32_t)(b * 64), rp);  // R over the first 16 of my 32 S columns
       tmem_wait_st();
       tc_fence_before();
