@@ -13,7 +13,7 @@ run() {  # config, kernel regex, launches to skip
   echo "$cfg rc=$?"
 }
 run c2 k_dense_tc3 3
-run c3 'k_logistic_tc<0>|k_logistic_tcILb0' 12
+run c3 k_logistic_tc 12
 run c4 k_nbody 3
 run c5 k_small 4
 for cfg in c2 c3 c5; do
