@@ -181,7 +181,7 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
     if (value != 1 && value != 2) return fail(EHMC_ERR_INVALID, "dense_occupancy must be 1 or 2");
     c->dense_occupancy = (int)value;
   } else if (!strcmp(name, "dense_path")) {
-    if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4) return fail(EHMC_ERR_INVALID, "dense_path must be 0..4");
+    if (!(value >= 0 && value <= 4)) return fail(EHMC_ERR_INVALID, "dense_path must be 0..4");
     c->dense_path = (int)value;
   } else if (!strcmp(name, "tc_prof")) {
     c->tc_prof = (int)value;
@@ -834,7 +834,7 @@ extern "C" int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor*
     // only kernels that resolve the block themselves; everything else would silently use the host values
     const bool small = pot->family == EHMC_FAMILY_DIAG_GAUSSIAN || pot->family == EHMC_FAMILY_FUNNEL ||
                        pot->family == EHMC_FAMILY_COIN_TOSS || (pot->family == EHMC_FAMILY_DENSE_GAUSSIAN && pot->D <= 16);
-    const bool tc3 = v.bits == 32 && use_dense_tc(ctx, pot, a->integrator) && (ctx->dense_path == 0 || ctx->dense_path == 4);
+    const bool tc3 = v.bits == 32 && use_dense_tc(ctx, pot, a->integrator) && (ctx->dense_path == 0 || ctx->dense_path >= 4);
     if (v.q.host || !(small || tc3))
       return fail(EHMC_ERR_UNSUPPORTED, "%s: args.dynamic needs device tensors and a small-D or float32 dense (tensor-core) potential", fn);
   }

@@ -35,7 +35,8 @@
 
 namespace ehmc {
 
-constexpr int TC3_THREADS = 256;  // 2 groups x 4 warps
+constexpr int TC3_THREADS = 384;       // 2 consumer groups x 4 warps + 1 producer warpgroup (Philox normals)
+constexpr int TC3_CONSUMERS = 256;
 
 // C8 = ceil(D / 8): 8-dim chunks the epilogue touches.  MMA K = N = KP = C8 rounded up to 16 dims.
 template <int C8>
@@ -81,6 +82,22 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&u)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
@@ -242,8 +259,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
   uint4* Bhi = reinterpret_cast<uint4*>(tc3_smem_raw);  // [KCH][NP] x 16 bytes
   uint4* Blo = Bhi + (size_t)KCH * NP;
   float* mus = reinterpret_cast<float*>(Blo + (size_t)KCH * NP);  // [KP]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(mus + KP);         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(mus + KP);         // [2] MMA done, per group
+  uint64_t* zfull = mbar + 2;                                     // [2] the group's stash of normals is complete
+  uint64_t* zempty = mbar + 4;                                    // [2] ... has been consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 6);
   float* zstash_all = reinterpret_cast<float*>(tc3_smem_raw + (size_t)2 * KCH * NP * 16 + (size_t)KP * 4 + 64);
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -257,6 +276,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
     if (lane == 0) {
       mbar_init(&mbar[0], 1);
       mbar_init(&mbar[1], 1);
+      for (int g = 0; g < 2; ++g) {
+        mbar_init(&zfull[g], 128);
+        mbar_init(&zempty[g], 128);
+      }
       fence_barrier_init();
     }
   }
@@ -290,22 +313,48 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
   const long long tile0 = ntiles * blockIdx.x / gridDim.x, tile1 = ntiles * (blockIdx.x + 1) / gridDim.x;
   uint32_t phase = 0;
 
-  // Momentum refresh off the critical path: the standard normals of the group's NEXT tile are drawn
-  // 8 dims at a time in the shadow of the current tile's MMAs (one chunk per evaluation, right after
-  // the MMAs are issued) and kept in shared memory, zst[d][row] -- each thread only ever touches its
-  // own column, so no synchronisation is involved.  Measured before this change: the Philox /
-  // Box-Muller loop at the start of a tile took 11.6k of the tile's 154k cycles with the tensor pipe idle.
-  float* zst = zstash_all + (size_t)grp * DC * TC_M + row;
+  // Momentum refresh off the critical path: a PRODUCER warpgroup (warps 8..11, one thread per particle
+  // row, 56 registers after setmaxnreg) draws the standard normals of the tiles ahead of the two consumer
+  // groups into shared-memory stashes zst[g][d][row]; full / empty mbarriers per group.  Measured history:
+  // Philox + Box-Muller at the start of a tile cost 11.6k of the tile's 154k cycles with the tensor pipe idle;
+  // drawn by the consumer threads themselves in the shadow of their MMAs the L = 50 iteration was as fast as
+  // with this warpgroup (same-box A/B within the +-4 % run-to-run noise) but the first tile of every group
+  // still paid for it (L = 0: 0.54 ms against 0.39 ms); a separate warpgroup spreads the ~3k instructions
+  // per row over the whole tile.
   const bool philox = hmc && A.z == nullptr;
-  const PhiloxKey PK(A.seed, A.iter);
-  auto gen_chunk = [&](long long t, int c) {
-    const long long r = t * TC_M + row;
-    float zz[8];
-    NormalBlock<float>::draw_multi<2>(PK, A.offset + (u64)(r < A.P ? r : 0), (uint32_t)(2 * c), zz);
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (philox) {
+      const PhiloxKey PK(A.seed, A.iter);
+      const int prow = tid - TC3_CONSUMERS;  // 0 .. 127
+      uint32_t par0 = 0u, par1 = 0u;
+      for (long long t = tile0; t < tile1; ++t) {
+        const int g = (int)((t - tile0) & 1);
+        float* zs = zstash_all + (size_t)g * DC * TC_M + prow;
+        // first pass: a fresh barrier reads as "previous phase complete".  The producer is ~8x faster than a
+        // tile, so it mostly waits here: back off instead of spinning on the consumers' sub-partitions
+        const uint32_t want = g == 0 ? par0 ^ 1u : par1 ^ 1u;
+        while (!mbar_try_wait(&zempty[g], want)) __nanosleep(2000);
+        if (g == 0) par0 ^= 1u; else par1 ^= 1u;
+        const long long r = t * TC_M + prow;
+        const u64 pid = A.offset + (u64)(r < A.P ? r : 0);
+#pragma unroll 1
+        for (int c = 0; c < C8; ++c) {
+          float zz[8];
+          NormalBlock<float>::draw_multi<2>(PK, pid, (uint32_t)(2 * c), zz);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) zst[(8 * c + e) * TC_M] = zz[e];
-  };
-  int ngen = 0;  // chunks of the CURRENT tile's normals already in the stash
+          for (int e = 0; e < 8; ++e) zs[(8 * c + e) * TC_M] = zz[e];
+        }
+        mbar_arrive(&zfull[g]);  // release: the stash writes above are visible to the waiting consumers
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+  float* zst = zstash_all + (size_t)grp * DC * TC_M + row;
+  uint32_t zpar = 0;
 
   for (long long tile = tile0 + grp; tile < tile1; tile += 2) {
     // phase trace of one steady-state tile (the second of CTA 0 / group 0), thread 0
@@ -340,13 +389,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
 #pragma unroll
     for (int d = 0; d < DC; ++d) v[d] = col(qcol, A.q_ld, d);
     stamp();  // 1: position loads issued
-    if (philox) {
-      // first tile of the group (or a trajectory shorter than the chunk count): draw what is missing now,
-      // while the position loads land
-#pragma unroll 1
-      for (int c = ngen; c < C8; ++c) gen_chunk(tile, c);
-    }
-    stamp();  // 2: momenta drawn
+    stamp();  // 2
     // x = q - mu parked in the (idle) accumulator columns
 #pragma unroll
     for (int c = 0; c < C8; ++c) {
@@ -360,8 +403,11 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       tmem_st8(t_d + (uint32_t)(8 * c), xx);
     }
     if (philox) {
+      mbar_wait(&zfull[grp], zpar);
+      zpar ^= 1u;
 #pragma unroll
       for (int d = 0; d < DC; ++d) v[d] = (d < DC - 8 || d < D) ? zst[d * TC_M] * pstd : 0.f;
+      mbar_arrive(&zempty[grp]);  // (the loads above have returned: v[] is consumed by the arithmetic below)
     } else {
       // fed momenta (parity mode) or integrate()
       const float* mcol = (hmc ? A.z : A.p) + pc;
@@ -428,16 +474,12 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
         }
         umma_commit(&mbar[grp]);
       }
-      // in the shadow of the MMAs: one chunk of the next tile's normals, then an L2 prefetch of its positions
-      if (tile + 2 < tile1) {
-        if (philox && ev < C8) {
-          gen_chunk(tile + 2, ev);
-        } else if (ev == C8) {
-          const long long r0 = (tile + 2) * TC_M + quarter * 32;
-          if (r0 < A.P) {
-            for (int d = lane; d < D; d += 32)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(A.q + (long long)d * A.q_ld + r0));
-          }
+      // in the shadow of the MMAs: L2 prefetch of the next tile's positions
+      if (ev == 1 && tile + 2 < tile1) {
+        const long long r0 = (tile + 2) * TC_M + quarter * 32;
+        if (r0 < A.P) {
+          for (int d = lane; d < D; d += 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.q + (long long)d * A.q_ld + r0));
         }
       }
       mbar_wait(&mbar[grp], phase);
@@ -453,7 +495,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       if (!(pa.dbg & 2)) tc3_epilogue<C8>(v, t_d, t_hi, t_lo, ck, !last);
       if (ev < 2 || ev >= L - 1) stamp();  // 5, 6: first two evaluations; then the last two
     }
-    ngen = (philox && tile + 2 < tile1) ? (L + 1 < C8 ? L + 1 : C8) : 0;
     // U = 1/2 x . g_true = 1/2 (xs isc) . (G gs)
     U0 = (U0 * isc) * (0.5f * gs);
     U1 = (U1 * isc) * (0.5f * gs);
