@@ -153,8 +153,14 @@ EHMC_API int ehmc_ctx_destroy(ehmc_ctx* ctx);
 EHMC_API int ehmc_ctx_launch_count(const ehmc_ctx* ctx, uint64_t* out);
 /* out[0]=SM count, out[1]=SM clock MHz (max), out[2]=total HBM bytes, out[3]=L2 bytes. */
 EHMC_API int ehmc_ctx_device_info(const ehmc_ctx* ctx, double out[4]);
-/* Tuning knobs: "dense_occupancy" (1|2: CTAs/SM variant of the float32 dense kernel),
- * "host_chunk_mb" (bytes of state per staged chunk on the host path). */
+/* Tuning / diagnostic knobs:
+ *   "dense_path"      0 auto (float32 dense Gaussian on the 3xFP16 tensor-core kernel), 1 CUDA cores (exact
+ *                     fp32 FMA), 2 / 3 the 3xTF32 tensor-core kernels (one tile / two tiles), 4 force 3xFP16
+ *   "dense_occupancy" 1|2: CTAs/SM variant of the float32 CUDA-core dense kernel
+ *   "small_waves"     resident waves of CTAs of the persistent small-D kernel (default 8)
+ *   "nbody_ti"        bodies per thread of the N-body kernel (0 auto, 4, 8)
+ *   "host_chunk_mb"   bytes of state per staged chunk on the host path
+ *   "tc_debug", "tc_prof", "tc_prof_dump"  profiling aids of the tensor-core dense kernels */
 EHMC_API int ehmc_ctx_set_option(ehmc_ctx* ctx, const char* name, double value);
 /* Measures the sustained FP32 FMA rate of the device with a register-only FFMA
  * kernel (2 flop per FMA) for about `millis` ms; the FP32 roofline denominator
