@@ -470,6 +470,25 @@ def main():
             cpu = {"value": rate, "unit": "particle-leapfrog-steps/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{sample} of {P} particles x 3 iterations, median (NumPy float64 oracle port, "
                              f"BLAS on all host cores; {sum(times):.1f} s of CPU wall time)"}
+        fused = None
+        if args.config == "c1" and world == 1:
+            # the reference's own call on its own runnable configuration: HMC.getSamples, 1000 iterations, whose
+            # whole loop is one launch for the small-D families (ehmc_hmc_run)
+            import contextlib
+            import io
+
+            ens_f = E.Ensemble(D, P, dtype=np.float32, device=dev, seed=SEED)
+            hmc_f = E.HMC(ens_f, L * h + 1e-9, h, None, potential=pot, seed=SEED)
+            with contextlib.redirect_stdout(io.StringIO()):
+                hmc_f.getSamples(10, 1 / KB, 1.0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                hmc_f.getSamples(1000, 1 / KB, 1.0)
+                torch.cuda.synchronize()
+                tf = time.perf_counter() - t0
+            fused = {"value": P * L * 1000 / tf, "unit": "particle-leapfrog-steps/s", "ms_total": 1e3 * tf,
+                     "iterations": 1000, "api": "HMC.getSamples(1000, ...) on a device ensemble -> ehmc_hmc_run, "
+                     "one launch, samples and momenta (D, P, S) written by the kernel"}
         line = {
             "metric": "particle-leapfrog-steps/sec", "value": value, "unit": "particle-leapfrog-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -482,7 +501,7 @@ def main():
                        "rng": "philox in-kernel", "l2": "inputs_exceed_l2" if D * Pl * 4 > 126e6 else "resident",
                        "parallelism": f"particle-shard x{world}, no data-path collective"},
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-            "ess": ess, "adaptation": ({"final_step_size": run_out["stepSize"][-1],
+            "ess": ess, "getSamples_fused_loop": fused, "adaptation": ({"final_step_size": run_out["stepSize"][-1],
                                         "accept_rate_last": run_out["acceptRate"][-1]} if adaptive else None),
         }
         print(json.dumps(line), flush=True)

@@ -233,6 +233,21 @@ EHMC_API int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q
                   const DLTensor* mass, const ehmc_hmc_args* args, const DLTensor* z,
                   const DLTensor* u, DLTensor* accept_out, DLTensor* stats_out, void* stream);
 
+/* ---- the whole loop of getSamples, src/HMC.py:150-179, in ONE launch ---------------------- */
+/* numIterations HMC iterations (Philox iterations args.iteration .. + numIterations - 1) with the particle
+ * state held on chip in between; iteration k stores the position the reference stores in samples_hmc[:, :, k]
+ * (src/HMC.py:178) and the momentum of momentum_hmc[:, :, k] (:179, same conventions as p_out of ehmc_hmc_iter).
+ *   q            [D,P] in/out (device)
+ *   samples_out  [D*P, S] optional: the reference's (D, P, S) array viewed as 2-D; slots
+ *                sampleOffset .. sampleOffset + numIterations - 1 are written
+ *   momenta_out  [D*P, S] optional
+ *   accepted_out [P] int32 optional: accepted proposals per particle
+ * Device tensors and the small-D families only (diagonal / small dense Gaussian, funnel, coin toss);
+ * EHMC_ERR_UNSUPPORTED otherwise -- call ehmc_hmc_iter per iteration then. */
+EHMC_API int ehmc_hmc_run(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, const DLTensor* mass,
+                 const ehmc_hmc_args* args, int numIterations, DLTensor* samples_out, DLTensor* momenta_out,
+                 int64_t sampleOffset, DLTensor* accepted_out, void* stream);
+
 /* Consumes the (all-reduced) statistics of the iteration that just ran with the block `dynamic`:
  *   history[dynamic.row] = {acceptRate, meanAcceptProb, meanH, stepSize used}  (optional, float64 [S,4])
  *   moments[0:D] += sum q_d, moments[D:2D] += sum q_d^2                        (optional, float64 [2D])

@@ -160,6 +160,24 @@ class HMC:
             p_buf = torch.empty((D, P), dtype=dt, device=ens.device)
             acc = torch.empty(P, dtype=torch.uint8, device=ens.device)
 
+        if not host and self.rng == "philox" and numSamples > 0 and self._fused_loop_ok():
+            # device ensemble, Philox draws, small-D family: the whole loop is ONE kernel launch
+            # (ehmc_hmc_run); every iteration writes its slot of the (D, P, S) arrays directly
+            for i in range(0, numSamples, 100):
+                print("HMC iteration ", i + 1)
+            ctx = _lib.Context.get(ens.device.index)
+            bits = ens.q.element_size() * 8
+            _lib.hmc_run(ctx, self.potential.handle(bits, ctx), self.integrator.q, self.integrator.mass,
+                         self._args(temperature), numSamples, samples_hmc.view(D * P, numSamples),
+                         momentum_hmc.view(D * P, numSamples), 0, stream=_lib.current_stream_ptr(ens.q))
+            self.iteration += numSamples
+            p_buf.copy_(momentum_hmc[:, :, numSamples - 1])
+            self.integrator.p = p_buf
+            ens.p = p_buf
+            ens.q = self.integrator.q
+            self.lastAccept = None
+            return samples_hmc, momentum_hmc
+
         for i in range(numSamples):
             if i % 100 == 0:
                 print("HMC iteration ", i + 1)
@@ -184,6 +202,12 @@ class HMC:
         self.lastAccept = acc
         return samples_hmc, momentum_hmc
 
+
+    def _fused_loop_ok(self):
+        """Families whose getSamples loop runs as one launch (ehmc_hmc_run)."""
+        pot = self.potential
+        return pot.family in (_lib.FAMILY_DIAG_GAUSSIAN, _lib.FAMILY_FUNNEL, _lib.FAMILY_COIN_TOSS) and \
+            pot.numDimensions <= 32 or (pot.family == _lib.FAMILY_DENSE_GAUSSIAN and pot.numDimensions <= 16)
 
     # ------------------------------------------------------------------------------------
     def run(self, numIterations, temperature, *, adapt=False, targetAccept=0.8, adaptIterations=None,

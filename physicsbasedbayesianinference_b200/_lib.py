@@ -33,7 +33,7 @@ SYMBOLS = (
     "ehmc_version", "ehmc_last_error", "ehmc_ctx_create", "ehmc_ctx_destroy", "ehmc_ctx_launch_count",
     "ehmc_ctx_device_info", "ehmc_ctx_set_option", "ehmc_measure_fp32_peak", "ehmc_potential_create", "ehmc_potential_destroy",
     "ehmc_potential_eval", "ehmc_set_position", "ehmc_set_momentum", "ehmc_philox_fill", "ehmc_leapfrog",
-    "ehmc_stormer_verlet", "ehmc_integrate_nbody_mode", "ehmc_hmc_iter", "ehmc_adapt_step",
+    "ehmc_stormer_verlet", "ehmc_integrate_nbody_mode", "ehmc_hmc_iter", "ehmc_hmc_run", "ehmc_adapt_step",
 )
 
 
@@ -110,6 +110,7 @@ def load():
             "ehmc_stormer_verlet": [vp, vp, vp, vp, vp, cd, cd, ci, vp],
             "ehmc_integrate_nbody_mode": [vp, ci, vp, vp, vp, cd, cd, cd, ci, vp],
             "ehmc_hmc_iter": [vp, vp, vp, vp, vp, ctypes.POINTER(HmcArgs), vp, vp, vp, vp, vp],
+            "ehmc_hmc_run": [vp, vp, vp, vp, ctypes.POINTER(HmcArgs), ci, vp, vp, ctypes.c_int64, vp, vp],
             "ehmc_adapt_step": [vp, vp, cd, cd, cd, cd, cd, cd, cd, u64, vp, vp, u64, vp, vp, vp],
         }
         for name, args in sigs.items():
@@ -324,6 +325,15 @@ def hmc_iter(ctx, pot, q, mass, args, p_out=None, z=None, u=None, accept=None, s
     vp, vz, vu, va, vs = dl(p_out), dl(z), dl(u), dl(accept), dl(stats)
     check(ctx.lib.ehmc_hmc_iter(ctx.handle, pot.handle, vq.ptr, _p(vp), vm.ptr, ctypes.byref(args), _p(vz), _p(vu),
                                 _p(va), _p(vs), stream))
+
+
+def hmc_run(ctx, pot, q, mass, args, num_iterations, samples=None, momenta=None, sample_offset=0, accepted=None,
+            stream=None):
+    """numIterations iterations in one launch; samples / momenta are [D*P, S] views of (D, P, S) arrays."""
+    vq, vm = dl(q), dl(mass)
+    vs, vmo, va = dl(samples), dl(momenta), dl(accepted)
+    check(ctx.lib.ehmc_hmc_run(ctx.handle, pot.handle, vq.ptr, vm.ptr, ctypes.byref(args), int(num_iterations), _p(vs),
+                               _p(vmo), int(sample_offset), _p(va), stream))
 
 
 def philox_fill(ctx, z=None, u=None, seed=0, iteration=0, particle_offset=0, stream=None):

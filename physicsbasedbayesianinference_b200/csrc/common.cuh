@@ -204,6 +204,17 @@ __device__ __forceinline__ IterArgs<T> resolve_dynamic(const IterArgs<T>& in) {
   return A;
 }
 
+// output side of the fused multi-iteration kernel (k_small_run)
+template <typename T>
+struct RunArgs {
+  T* samples;       // [D*P][S] (element (d, i, s) at (d*P + i)*S + s) or null
+  T* momenta;       // same layout or null
+  int* accepted;    // [P] number of accepted proposals, or null
+  long long S;      // samples per particle in the arrays
+  long long s0;     // first sample slot written by this launch
+  int nIter;
+};
+
 constexpr unsigned FLAG_BUGCOMPAT = 1u;
 constexpr unsigned FLAG_REJECT_NONFINITE = 2u;
 

@@ -853,6 +853,77 @@ extern "C" int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor*
 }
 
 // ---------------------------------------------------------------------------
+// getSamples' loop in one launch
+// ---------------------------------------------------------------------------
+template <typename T>
+static int hmc_run_typed(ehmc_ctx* ctx, const ehmc_potential* pot, const CallViews& v, const ehmc_hmc_args* a, int nIter,
+                         const View* vs, const View* vm, long long s0, long long S, int* accepted, cudaStream_t st) {
+  IterArgs<T> A = base_args<T>(v, a->stepSize, a->stepSizeSq, a->numSteps);
+  A.flags = a->flags;
+  A.kB = a->boltzmann;
+  A.temp = a->temperature;
+  A.pscale = std::sqrt(a->boltzmann * a->temperature);
+  A.seed = a->seed;
+  A.iter = a->iteration;
+  A.offset = a->particleOffset;
+  RunArgs<T> R;
+  R.samples = vs ? reinterpret_cast<T*>(vs->data) : nullptr;
+  R.momenta = vm ? reinterpret_cast<T*>(vm->data) : nullptr;
+  R.accepted = accepted;
+  R.S = S;
+  R.s0 = s0;
+  R.nIter = nIter;
+  if (A.P == 0 || nIter == 0) return EHMC_OK;
+  return run_small<T>(ctx, pot, A, a->integrator, R, st);
+}
+
+extern "C" int ehmc_hmc_run(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, const DLTensor* mass,
+                            const ehmc_hmc_args* a, int numIterations, DLTensor* samples_out, DLTensor* momenta_out,
+                            int64_t sampleOffset, DLTensor* accepted_out, void* stream) {
+  const char* fn = "ehmc_hmc_run";
+  CallViews v;
+  TRY(common_checks(ctx, pot, q, mass, &v, fn));
+  if (!a) return fail(EHMC_ERR_INVALID, "%s: args is NULL", fn);
+  if (a->struct_size != sizeof(ehmc_hmc_args))
+    return fail(EHMC_ERR_INVALID, "%s: args.struct_size %u != %zu", fn, a->struct_size, sizeof(ehmc_hmc_args));
+  if (a->numSteps < 0 || numIterations < 0 || sampleOffset < 0) return fail(EHMC_ERR_INVALID, "%s: negative count", fn);
+  if (a->integrator != EHMC_LEAPFROG && a->integrator != EHMC_STORMER_VERLET)
+    return fail(EHMC_ERR_INVALID, "%s: Invalid integration method selected.", fn);
+  if (a->dynamic != nullptr) return fail(EHMC_ERR_UNSUPPORTED, "%s: args.dynamic is not supported here", fn);
+  const bool small = pot->family == EHMC_FAMILY_DIAG_GAUSSIAN || pot->family == EHMC_FAMILY_FUNNEL ||
+                     pot->family == EHMC_FAMILY_COIN_TOSS || (pot->family == EHMC_FAMILY_DENSE_GAUSSIAN && pot->D <= 16);
+  if (v.q.host || !small)
+    return fail(EHMC_ERR_UNSUPPORTED, "%s: device tensors and a small-D potential family are required", fn);
+  View vs, vm, va;
+  long long S = 0;
+  for (int k = 0; k < 2; ++k) {
+    DLTensor* t = k == 0 ? samples_out : momenta_out;
+    if (!t) continue;
+    View* w = k == 0 ? &vs : &vm;
+    TRY(parse_float(t, k == 0 ? "samples_out" : "momenta_out", 2, v.bits, w));
+    if (w->host || w->shape[0] != v.D * v.P || w->ld != w->shape[1])
+      return fail(EHMC_ERR_INVALID, "%s: sample arrays must be contiguous device [D*P, S] views of (D, P, S)", fn);
+    if (S && S != w->shape[1]) return fail(EHMC_ERR_INVALID, "%s: samples_out and momenta_out differ in S", fn);
+    S = w->shape[1];
+  }
+  if ((samples_out || momenta_out) && sampleOffset + numIterations > S)
+    return fail(EHMC_ERR_INVALID, "%s: sampleOffset + numIterations exceeds S = %lld", fn, S);
+  int* accepted = nullptr;
+  if (accepted_out) {
+    TRY(parse(accepted_out, "accepted_out", 1, &va));
+    if (va.host || va.bits != 32 || va.shape[0] != v.P) return fail(EHMC_ERR_INVALID, "%s: accepted_out must be device int32[P]", fn);
+    accepted = reinterpret_cast<int*>(va.data);
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (v.bits == 32)
+    return hmc_run_typed<float>(ctx, pot, v, a, numIterations, samples_out ? &vs : nullptr, momenta_out ? &vm : nullptr,
+                                sampleOffset, S, accepted, st);
+  return hmc_run_typed<double>(ctx, pot, v, a, numIterations, samples_out ? &vs : nullptr, momenta_out ? &vm : nullptr,
+                               sampleOffset, S, accepted, st);
+}
+
+// ---------------------------------------------------------------------------
 // device-side step-size adaptation (ehmc_dynamic)
 // ---------------------------------------------------------------------------
 static __global__ void k_adapt_step(const double* __restrict__ stats, int D, double P, double target, double gain0,

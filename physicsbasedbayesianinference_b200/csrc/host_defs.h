@@ -100,6 +100,9 @@ constexpr int K2_WARPS_HOST = 8;
 // fused trajectory kernels, D <= 32 register-resident families
 template <typename T>
 int launch_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);
+// getSamples' whole loop in one launch (small-D families, Philox draws)
+template <typename T>
+int run_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, const RunArgs<T>& R, cudaStream_t st);
 // dense Gaussian, 16 < D <= 128
 template <typename T>
 int launch_dense(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);

@@ -117,6 +117,45 @@ int launch_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int
   return fail(EHMC_ERR_UNSUPPORTED, "small-D kernel: D = %d > 32", D);
 }
 
+template <typename T, int DT, class Pot>
+static int run_small_pot(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, int integ, const RunArgs<T>& R, cudaStream_t st) {
+  const unsigned grid = (unsigned)std::max<long long>(1, (A.P + K1_THREADS - 1) / K1_THREADS);
+  if (integ == INTEG_LEAPFROG)
+    k_small_run<T, DT, Pot, INTEG_LEAPFROG><<<grid, K1_THREADS, 0, st>>>(A, pot, R);
+  else
+    k_small_run<T, DT, Pot, INTEG_STORMER><<<grid, K1_THREADS, 0, st>>>(A, pot, R);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return EHMC_OK;
+}
+
+template <typename T, int DT>
+static int run_small_dt(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, const RunArgs<T>& R,
+                        cudaStream_t st) {
+  switch (p->family) {
+    case EHMC_FAMILY_DIAG_GAUSSIAN: return run_small_pot<T, DT>(c, A, make_diag<T, DT>(p), integ, R, st);
+    case EHMC_FAMILY_FUNNEL: return run_small_pot<T, DT>(c, A, make_funnel<T, DT>(p), integ, R, st);
+    case EHMC_FAMILY_COIN_TOSS: return run_small_pot<T, DT>(c, A, make_coin<T, DT>(p), integ, R, st);
+    case EHMC_FAMILY_DENSE_GAUSSIAN:
+      if constexpr (DT <= 16) return run_small_pot<T, DT>(c, A, make_dense_small<T, DT>(p), integ, R, st);
+      break;
+    default: break;
+  }
+  return fail(EHMC_ERR_UNSUPPORTED, "family %d has no fused multi-iteration kernel for D = %d", p->family, p->D);
+}
+
+template <typename T>
+int run_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, const RunArgs<T>& R, cudaStream_t st) {
+  const int D = p->D;
+  if (D <= 2) return run_small_dt<T, 2>(c, p, A, integ, R, st);
+  if (D <= 4) return run_small_dt<T, 4>(c, p, A, integ, R, st);
+  if (D <= 8) return run_small_dt<T, 8>(c, p, A, integ, R, st);
+  if (D <= 10) return run_small_dt<T, 10>(c, p, A, integ, R, st);
+  if (D <= 16) return run_small_dt<T, 16>(c, p, A, integ, R, st);
+  if (D <= 32) return run_small_dt<T, 32>(c, p, A, integ, R, st);
+  return fail(EHMC_ERR_UNSUPPORTED, "small-D kernel: D = %d > 32", D);
+}
+
 template <typename T, int DT>
 static int eval_small_dt(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
                          long long g_ld, cudaStream_t st) {

@@ -436,4 +436,62 @@ __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, con
     block_partials<K1_THREADS, DT>(A.partials + (size_t)blockIdx.x * (2 * A.D + 3), A.D, k1_smem, sred);
 }
 
+// ---------------------------------------------------------------------------
+// HMC.getSamples' WHOLE loop (src/HMC.py:150-179) as one launch: every thread keeps its particle in
+// registers across `nIter` iterations (momentum refresh from Philox iteration A.iter + it, trajectory,
+// Metropolis, restore) and stores each iteration's position / momentum into the reference's own
+// (D, P, S) sample arrays.  For the launch-bound regime of the reference's runnable configurations
+// (config 1: P = 1024, 1000 iterations: one launch instead of 1000 launches + 2000 copies).
+// ---------------------------------------------------------------------------
+template <typename T, int DT, class Pot, int INTEG>
+__global__ void __launch_bounds__(K1_THREADS) k_small_run(const IterArgs<T> Ain, const Pot pot, const RunArgs<T> R) {
+  const long long stride = (long long)gridDim.x * K1_THREADS;
+  for (long long i = (long long)blockIdx.x * K1_THREADS + threadIdx.x; i < Ain.P; i += stride) {
+    IterArgs<T> A = Ain;
+    T q[DT], qold[DT], p[DT], p0[DT];
+    const T m = A.mass[i], inv_m = T(1) / m;
+    const T pstd = momentum_std<T>(m, A.kB, A.temp, A.pscale);
+#pragma unroll
+    for (int d = 0; d < DT; ++d) q[d] = d < A.D ? A.q[d * A.q_ld + i] : T(0);
+    int nacc = 0;
+    for (int it = 0; it < R.nIter; ++it) {
+      A.iter = Ain.iter + (u64)it;
+      draw_momentum<T, DT>(A, i, pstd, p);
+#pragma unroll
+      for (int d = 0; d < DT; ++d) {
+        qold[d] = q[d];
+        p0[d] = p[d];
+      }
+      const T K0 = kinetic<T, DT>(p, m, inv_m);
+      T U0;
+      const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, A.h, A.h2, A.L, true, &U0);
+      const T oldH = Ar<T>::add(K0, U0);
+      const T newH = Ar<T>::add(kinetic<T, DT>(p, m, inv_m), U1);
+      const T u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)i);
+      T accp;
+      const bool rej = metropolis_reject<T>(oldH, newH, u, A.flags, &accp);
+      nacc += rej ? 0 : 1;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) {
+        if (rej) {
+          q[d] = qold[d];                                         // HMC.py:175
+          p[d] = (A.flags & FLAG_BUGCOMPAT) ? qold[d] : p0[d];    // HMC.py:176 (sic) / the old momentum
+        }
+        if (d < A.D) {
+          const long long o = ((long long)d * A.P + i) * R.S + R.s0 + it;
+          if (R.samples != nullptr) R.samples[o] = q[d];          // HMC.py:178
+          if (R.momenta != nullptr) R.momenta[o] = p[d];          // HMC.py:179 (un-flipped, :164)
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < DT; ++d)
+      if (d < A.D) {
+        A.q[d * A.q_ld + i] = q[d];
+        if (A.p != nullptr) A.p[d * A.p_ld + i] = p[d];
+      }
+    if (R.accepted != nullptr) R.accepted[i] = nacc;
+  }
+}
+
 }  // namespace ehmc

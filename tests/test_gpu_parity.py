@@ -258,6 +258,53 @@ def test_getSamples_drop_in_numpy_stream(E, capsys):
     assert rel_err(momenta, g["momenta"]) < 1e-12
 
 
+@pytest.mark.parametrize("case", ["iso2", "funnel10", "dense8", "coin2"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("bug", [True, False])
+def test_getSamples_fused_loop_equals_iteration_by_iteration(E, case, dt, bug, capsys):
+    """getSamples on a device ensemble with Philox draws runs the whole loop of src/HMC.py:150-179 as ONE
+    launch (ehmc_hmc_run); it must reproduce the per-iteration path (one ehmc_hmc_iter per iteration,
+    samples copied out in between) bit for bit, including the stored momenta of rejected particles."""
+    import torch
+
+    rng = np.random.RandomState(31)
+    P, S = 777, 23
+    if case == "iso2":
+        D, pot, h, T = 2, E.HarmonicPotential([1.0, 2.5]), 0.3, 0.9
+    elif case == "funnel10":
+        D, pot, h, T = 10, E.FunnelPotential(10, 3.0), 0.2, 1.0
+    elif case == "coin2":
+        D, pot, h, T = 2, E.CoinTossPotential([10, 15], [20, 20]), 0.02, 0.2
+    else:
+        D = 8
+        A = rng.standard_normal((D, D))
+        pot, h, T = E.GaussianPotential(precision=A @ A.T / D + np.eye(D), mean=rng.standard_normal(D)), 0.25, 1.0
+    q0 = rng.uniform(0.3, 0.7, (D, P)) if case == "coin2" else rng.standard_normal((D, P))
+    mass = rng.uniform(0.5, 2.0, P)
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+
+    def fresh(method):
+        ens = E.Ensemble(D, P, dtype=dt, device="cuda", seed=9)
+        ens.mass = torch.tensor(mass, dtype=tdt, device="cuda")
+        hmc = E.HMC(ens, T, h, None, potential=pot, seed=9, bugCompat=bug, method=method)
+        ens.setPosition = lambda qStd: ens.q.copy_(torch.tensor(q0, dtype=tdt))  # fixed start (copy_ returns ens.q)
+        return ens, hmc
+
+    for method in ("Leapfrog", "Stormer-Verlet"):
+        ens_a, hmc_a = fresh(method)
+        sa, ma = hmc_a.getSamples(S, 1 / KB, 1.0)  # fused
+        ens_b, hmc_b = fresh(method)
+        hmc_b._fused_loop_ok = lambda: False
+        sb, mb = hmc_b.getSamples(S, 1 / KB, 1.0)  # one launch per iteration
+        assert hmc_a.iteration == hmc_b.iteration == S
+        assert torch.equal(sa, sb), (case, method)
+        assert torch.equal(ma, mb), (case, method)
+        assert torch.equal(ens_a.q, ens_b.q) and torch.equal(ens_a.p, ens_b.p)
+        moved = (sa[:, :, -1] != torch.tensor(q0, dtype=tdt, device="cuda")).any(0).float().mean().item()
+        assert moved > 0.5  # the chain actually accepts proposals
+    capsys.readouterr()
+
+
 def test_bugcompat_flag(E):
     """bugCompat=False stores the OLD MOMENTUM of rejected particles instead of the old
     position (src/HMC.py:176)."""
