@@ -22,7 +22,7 @@ for fused in (True, False):
     if not fused:
         hmc._fused_loop_ok = lambda: False
     with contextlib.redirect_stdout(io.StringIO()):
-        hmc.getSamples(10, 1 / KB, 1.0)
+        hmc.getSamples(S, 1 / KB, 1.0)  # warm-up of the same size (first-use cudaMalloc of the (D, P, S) arrays)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         s, m = hmc.getSamples(S, 1 / KB, 1.0)
