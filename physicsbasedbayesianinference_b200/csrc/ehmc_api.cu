@@ -10,8 +10,16 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only (dlopens the tools library only when a profiler is attached)
+
 #include "host_defs.h"
 #include "k_misc.cuh"
+
+// NVTX range around a C-ABI call (the reference's only tracing is cProfile around integrate())
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 using namespace ehmc;
 
@@ -769,12 +777,14 @@ static int integrate_entry(ehmc_ctx* ctx, const ehmc_potential* pot, int integ, 
 
 extern "C" int ehmc_leapfrog(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p, const DLTensor* mass,
                              double stepSize, double stepSizeSq, int numSteps, void* stream) {
+  NvtxRange nvtx_range("ehmc_leapfrog");
   return integrate_entry(ctx, pot, INTEG_LEAPFROG, q, p, mass, stepSize, stepSizeSq, numSteps, stream, "ehmc_leapfrog");
 }
 
 extern "C" int ehmc_stormer_verlet(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p,
                                    const DLTensor* mass, double stepSize, double stepSizeSq, int numSteps,
                                    void* stream) {
+  NvtxRange nvtx_range("ehmc_stormer_verlet");
   return integrate_entry(ctx, pot, INTEG_STORMER, q, p, mass, stepSize, stepSizeSq, numSteps, stream,
                          "ehmc_stormer_verlet");
 }
@@ -782,6 +792,7 @@ extern "C" int ehmc_stormer_verlet(ehmc_ctx* ctx, const ehmc_potential* pot, DLT
 extern "C" int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p_out,
                              const DLTensor* mass, const ehmc_hmc_args* a, const DLTensor* z, const DLTensor* u,
                              DLTensor* accept_out, DLTensor* stats_out, void* stream) {
+  NvtxRange nvtx_range("ehmc_hmc_iter");
   const char* fn = "ehmc_hmc_iter";
   CallViews v;
   TRY(common_checks(ctx, pot, q, mass, &v, fn));
@@ -880,6 +891,7 @@ static int hmc_run_typed(ehmc_ctx* ctx, const ehmc_potential* pot, const CallVie
 extern "C" int ehmc_hmc_run(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, const DLTensor* mass,
                             const ehmc_hmc_args* a, int numIterations, DLTensor* samples_out, DLTensor* momenta_out,
                             int64_t sampleOffset, DLTensor* accepted_out, void* stream) {
+  NvtxRange nvtx_range("ehmc_hmc_run");
   const char* fn = "ehmc_hmc_run";
   CallViews v;
   TRY(common_checks(ctx, pot, q, mass, &v, fn));
@@ -962,6 +974,7 @@ extern "C" int ehmc_adapt_step(ehmc_ctx* ctx, const DLTensor* stats, double numP
                                double gain0, double kappa, double maxMove, double minStep, double maxStep,
                                uint64_t adaptRows, void* dynamic, const void* state, uint64_t stride, DLTensor* history,
                                DLTensor* moments, void* stream) {
+  NvtxRange nvtx_range("ehmc_adapt_step");
   const char* fn = "ehmc_adapt_step";
   if (!ctx || !stats || !dynamic) return fail(EHMC_ERR_INVALID, "%s: NULL argument", fn);
   View vs, vh, vm;
@@ -1037,6 +1050,7 @@ static int eval_any(ehmc_ctx* c, const ehmc_potential* p, const View& q, const V
 
 extern "C" int ehmc_potential_eval(ehmc_ctx* ctx, const ehmc_potential* pot, const DLTensor* q, DLTensor* energy_out,
                                    DLTensor* grad_out, void* stream) {
+  NvtxRange nvtx_range("ehmc_potential_eval");
   const char* fn = "ehmc_potential_eval";
   if (!ctx || !pot) return fail(EHMC_ERR_INVALID, "%s: NULL context or potential", fn);
   View vq, ve, vg;
