@@ -305,7 +305,7 @@ def main():
         hmc.run(args.warmup, 1 / KB, adapt=True, group=group, keepNumSteps=True, deviceAdapt=dev_adapt)
     else:
         for _ in range(args.warmup):
-            hmc.step(1 / KB)
+            hmc.step(1 / KB, reuseEndpoint=True)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -321,7 +321,7 @@ def main():
         ev[-1].record()
     else:
         for i in range(args.steps):
-            hmc.step(1 / KB)
+            hmc.step(1 / KB, reuseEndpoint=True)  # q is only touched by the step itself
             ev[i + 1].record()
     barrier()
     launches = ctx.launch_count() - launches0

@@ -113,6 +113,14 @@ typedef enum {
 #define EHMC_FLAG_REJECT_NONFINITE 2u   /* reject when exp(oldH-newH) is NaN; the reference      \
                                            ACCEPTS those (u > NaN is False, src/HMC.py:168-173) */
 
+#define EHMC_FLAG_REUSE_ENDPOINT 4u     /* the caller guarantees that q and the potential are exactly what the  \
+                                           previous ehmc_hmc_iter on this context left behind (nothing else     \
+                                           touched them): families that keep an endpoint cache (logistic        \
+                                           regression) then take grad U(q) and U(q) of the trajectory's start   \
+                                           from the kept end of the previous one instead of re-evaluating them  \
+                                           -- L instead of L + 1 gradient evaluations per iteration, identical  \
+                                           results.  Ignored when no valid cache exists. */
+
 typedef struct {
   uint32_t struct_size;    /* sizeof(ehmc_hmc_args), for ABI growth */
   uint32_t flags;          /* EHMC_FLAG_* */

@@ -112,13 +112,18 @@ class HMC:
         return (_lib.FLAG_BUGCOMPAT_MOMENTUM if self.bugCompat else 0) | (
             _lib.FLAG_REJECT_NONFINITE if self.rejectNonFinite else 0)
 
-    def _args(self, temperature, dynamic=None):
+    def _args(self, temperature, dynamic=None, reuseEndpoint=False):
         integ = _lib.LEAPFROG if self.method == "Leapfrog" else _lib.STORMER_VERLET
+        flags = self._flags() | (_lib.FLAG_REUSE_ENDPOINT if reuseEndpoint else 0)
         return _lib.make_args(self.stepSize, self.stepSize**2, self.integrator.numSteps, boltzmannConst, temperature,
-                              integ, self._flags(), self.seed, self.iteration, self.ensemble.particleOffset, dynamic)
+                              integ, flags, self.seed, self.iteration, self.ensemble.particleOffset, dynamic)
 
-    def step(self, temperature, p_out=None, accept=None, stats=None, z=None, u=None, dynamic=None):
-        """One HMC iteration on ``integrator.q`` in place (the body of getSamples' loop)."""
+    def step(self, temperature, p_out=None, accept=None, stats=None, z=None, u=None, dynamic=None, reuseEndpoint=False):
+        """One HMC iteration on ``integrator.q`` in place (the body of getSamples' loop).
+
+        reuseEndpoint=True is the caller's promise that nothing touched ``q`` since the previous step() of
+        this driver: families with an endpoint cache (logistic regression) then start the trajectory from the
+        gradient and energy kept at the end of the previous one (L instead of L + 1 gradient evaluations)."""
         q = self.integrator.q
         host = isinstance(q, np.ndarray)
         ctx = _lib.Context.get(None if host else q.device.index)
@@ -126,7 +131,7 @@ class HMC:
         mass = self.integrator.mass
         if host:
             mass = np.ascontiguousarray(mass, dtype=q.dtype)
-        args = self._args(temperature, dynamic)
+        args = self._args(temperature, dynamic, reuseEndpoint)
         _lib.hmc_iter(ctx, self.potential.handle(bits, ctx), q, mass, args, p_out=p_out, z=z, u=u, accept=accept,
                       stats=stats, stream=_lib.current_stream_ptr(q))
         self.iteration += 1
@@ -300,7 +305,7 @@ class HMC:
             slot = it & 1
             out["stepSize"].append(self.stepSize)
             out["numSteps"].append(self.integrator.numSteps)
-            self.step(temperature, stats=stats[slot] if collectStats else None)
+            self.step(temperature, stats=stats[slot] if collectStats else None, reuseEndpoint=it > 0)
             if trace is not None:
                 trace[:, :, it] = ens.q[:, :traceParticles]
             if collectStats:

@@ -27,6 +27,7 @@ LEAPFROG = 0
 STORMER_VERLET = 1
 FLAG_BUGCOMPAT_MOMENTUM = 1
 FLAG_REJECT_NONFINITE = 2
+FLAG_REUSE_ENDPOINT = 4
 
 # every symbol include/ehmc.h declares (tests/test_abi.py checks the export list)
 SYMBOLS = (

@@ -217,6 +217,7 @@ struct RunArgs {
 
 constexpr unsigned FLAG_BUGCOMPAT = 1u;
 constexpr unsigned FLAG_REJECT_NONFINITE = 2u;
+constexpr unsigned FLAG_REUSE_ENDPOINT = 4u;
 
 constexpr int INTEG_LEAPFROG = 0;
 constexpr int INTEG_STORMER = 1;

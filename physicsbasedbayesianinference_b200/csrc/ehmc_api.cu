@@ -157,6 +157,10 @@ extern "C" int ehmc_ctx_destroy(ehmc_ctx* c) {
   c->stage_stats.release();
   c->pstats.release();
   c->tc_prof_buf.release();
+  for (int k = 0; k < 2; ++k) {
+    c->ep_grad[k].release();
+    c->ep_energy[k].release();
+  }
   for (int i = 0; i < N_STAGE; ++i) {
     c->stage[i].release();
     c->uf[i].release();
@@ -516,6 +520,7 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
 extern "C" int ehmc_potential_destroy(ehmc_potential* p) {
   if (!p) return EHMC_OK;
   if (p->ctx) cudaSetDevice(p->ctx->device);
+  if (p->ctx && p->ctx->ep_pot == p) p->ctx->ep_valid = false;  // a new potential may reuse this address
   if (p->d0) cudaFree(p->d0);
   if (p->d1) cudaFree(p->d1);
   if (p->d2) cudaFree(p->d2);
@@ -629,7 +634,10 @@ static int run_device(ehmc_ctx* c, const ehmc_potential* pot, IterArgs<T> A, int
     TRY(c->partials.ensure(sizeof(double) * (size_t)std::max(1LL, nblk) * NS));
     A.partials = static_cast<double*>(c->partials.ptr);
   }
-  TRY(launch_traj<T>(c, pot, A, integ, hmc, st));
+  c->ep_enabled = true;  // the endpoint cache is only meaningful when one call covers the resident ensemble
+  const int rc_traj = launch_traj<T>(c, pot, A, integ, hmc, st);
+  c->ep_enabled = false;
+  TRY(rc_traj);
   if (stats_dev != nullptr && A.P > 0) {
     if (!pps) nblk = c->last_rows;
     k_stats_finalize<<<NS, 256, 0, st>>>(A.partials, (int)nblk, NS, stats_dev);
@@ -777,6 +785,7 @@ static int integrate_entry(ehmc_ctx* ctx, const ehmc_potential* pot, int integ, 
 
 extern "C" int ehmc_leapfrog(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p, const DLTensor* mass,
                              double stepSize, double stepSizeSq, int numSteps, void* stream) {
+  if (ctx) ctx->ep_valid = false;  // q is about to change outside ehmc_hmc_iter
   NvtxRange nvtx_range("ehmc_leapfrog");
   return integrate_entry(ctx, pot, INTEG_LEAPFROG, q, p, mass, stepSize, stepSizeSq, numSteps, stream, "ehmc_leapfrog");
 }
@@ -784,6 +793,7 @@ extern "C" int ehmc_leapfrog(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor*
 extern "C" int ehmc_stormer_verlet(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, DLTensor* p,
                                    const DLTensor* mass, double stepSize, double stepSizeSq, int numSteps,
                                    void* stream) {
+  if (ctx) ctx->ep_valid = false;  // q is about to change outside ehmc_hmc_iter
   NvtxRange nvtx_range("ehmc_stormer_verlet");
   return integrate_entry(ctx, pot, INTEG_STORMER, q, p, mass, stepSize, stepSizeSq, numSteps, stream,
                          "ehmc_stormer_verlet");
@@ -891,6 +901,7 @@ static int hmc_run_typed(ehmc_ctx* ctx, const ehmc_potential* pot, const CallVie
 extern "C" int ehmc_hmc_run(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, const DLTensor* mass,
                             const ehmc_hmc_args* a, int numIterations, DLTensor* samples_out, DLTensor* momenta_out,
                             int64_t sampleOffset, DLTensor* accepted_out, void* stream) {
+  if (ctx) ctx->ep_valid = false;  // q is about to change outside ehmc_hmc_iter
   NvtxRange nvtx_range("ehmc_hmc_run");
   const char* fn = "ehmc_hmc_run";
   CallViews v;
@@ -1131,6 +1142,7 @@ extern "C" int ehmc_philox_fill(ehmc_ctx* ctx, DLTensor* z, DLTensor* u, uint64_
 
 extern "C" int ehmc_set_position(ehmc_ctx* ctx, DLTensor* q, double qStd, uint64_t seed, uint64_t particleOffset,
                                  void* stream) {
+  if (ctx) ctx->ep_valid = false;  // q is about to change outside ehmc_hmc_iter
   if (!ctx) return fail(EHMC_ERR_INVALID, "ehmc_set_position: NULL context");
   View vq;
   TRY(parse_float(q, "q", 2, 0, &vq));

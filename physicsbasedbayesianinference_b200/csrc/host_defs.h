@@ -49,6 +49,15 @@ struct ehmc_ctx {
   DevBuf stage_stats;
   DevBuf pstats;          // per-particle statistics rows [P][3] (CTA-per-particle / unfused families)
   DevBuf uf[N_STAGE];     // scratch of the unfused path: w, v, g [D][P] + K0, U0, U1 [P]
+  // endpoint cache of the unfused (logistic) family: grad U and U at the position the last ehmc_hmc_iter kept
+  DevBuf ep_grad[2], ep_energy[2];
+  int ep_cur = 0;                  // slot holding the valid cache
+  bool ep_valid = false;
+  bool ep_enabled = false;         // set by the device path of ehmc_hmc_iter only (the host path stages chunks)
+  const void* ep_q = nullptr;      // identity of the cached call: q pointer, potential, P, dtype
+  const ehmc_potential* ep_pot = nullptr;
+  long long ep_P = 0;
+  int ep_bits = 0;
   cudaStream_t streams[N_STAGE] = {nullptr, nullptr, nullptr};
   // tuning options (ehmc_ctx_set_option)
   int small_waves = 8;            // k_small grid = this many resident waves of CTAs (grid-stride over particles)

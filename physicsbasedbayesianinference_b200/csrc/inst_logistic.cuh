@@ -41,6 +41,9 @@ int eval_logistic(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_
 }
 
 // One HMC iteration / one integrate() call as a sequence of launches on `st`.
+// Endpoint cache (device path, leapfrog, HMC): the gradient and energy at the position every particle keeps
+// are saved by the final kernel; with EHMC_FLAG_REUSE_ENDPOINT the next iteration starts from them instead
+// of re-evaluating (L instead of L + 1 gradient launches, the energy variant only once).
 template <typename T>
 int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st,
                     int slot) {
@@ -55,12 +58,30 @@ int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, 
   T* U1 = U0 + P;
   const unsigned grid = (unsigned)((P + 127) / 128);
   const T h = A.h, h2 = A.h2;
+  // ep_enabled is set by the device path only (one call = the whole resident ensemble)
+  const bool cacheable = hmc && integ == INTEG_LEAPFROG && slot == 0 && c->ep_enabled && L > 0;
+  const bool hit = cacheable && (A.flags & FLAG_REUSE_ENDPOINT) && c->ep_valid && c->ep_q == (const void*)A.q &&
+                   c->ep_pot == p && c->ep_P == P && c->ep_bits == (int)sizeof(T) * 8;
+  T *g_start = g, *u_start = U0, *g_keep = nullptr, *u_keep = nullptr;
+  if (cacheable) {
+    for (int k = 0; k < 2; ++k) {
+      TRY(c->ep_grad[k].ensure(sizeof(T) * (size_t)D * P));
+      TRY(c->ep_energy[k].ensure(sizeof(T) * (size_t)P));
+    }
+    const int cur = hit ? c->ep_cur : 0;
+    g_start = static_cast<T*>(c->ep_grad[cur].ptr);
+    u_start = static_cast<T*>(c->ep_energy[cur].ptr);
+    g_keep = static_cast<T*>(c->ep_grad[cur ^ 1].ptr);
+    u_keep = static_cast<T*>(c->ep_energy[cur ^ 1].ptr);
+    c->ep_cur = cur ^ 1;
+  }
+  c->ep_valid = false;  // re-established below on success
   k_uf_init<T><<<grid, 128, 0, st>>>(A, w, v, hmc ? K0 : nullptr, hmc ? 1 : 0);
   c->launches++;
-  TRY(logistic_grad<T>(c, p, w, P, P, g, P, hmc ? U0 : nullptr, st));
+  if (!hit) TRY(logistic_grad<T>(c, p, w, P, P, g_start, P, hmc ? u_start : nullptr, st));
   if (integ == INTEG_LEAPFROG) {
     if (L > 0) {
-      k_uf_kick_drift<T><<<grid, 128, 0, st>>>(w, v, g, A.mass, P, D, T(0.5) * h, h);
+      k_uf_kick_drift<T><<<grid, 128, 0, st>>>(w, v, g_start, A.mass, P, D, T(0.5) * h, h);
       c->launches++;
     }
     for (int s = 0; s < L; ++s) {
@@ -69,9 +90,9 @@ int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, 
       k_uf_kick_drift<T><<<grid, 128, 0, st>>>(w, v, g, A.mass, P, D, last ? T(0.5) * h : h, last ? T(0) : h);
       c->launches++;
     }
-    if (L == 0 && hmc) CUDA_TRY(cudaMemcpyAsync(U1, U0, sizeof(T) * P, cudaMemcpyDeviceToDevice, st));
+    if (L == 0 && hmc) CUDA_TRY(cudaMemcpyAsync(U1, u_start, sizeof(T) * P, cudaMemcpyDeviceToDevice, st));
   } else {
-    k_uf_sv_step<T><<<grid, 128, 0, st>>>(w, v, g, A.mass, P, D, h, h2, 1);
+    k_uf_sv_step<T><<<grid, 128, 0, st>>>(w, v, g_start, A.mass, P, D, h, h2, 1);
     c->launches++;
     for (int s = 0; s < L; ++s) {
       TRY(logistic_grad<T>(c, p, w, P, P, g, P, nullptr, st));
@@ -82,9 +103,16 @@ int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, 
     c->launches++;
     if (hmc) TRY(logistic_grad<T>(c, p, w, P, P, nullptr, 0, U1, st));
   }
-  k_uf_final<T><<<grid, 128, 0, st>>>(A, w, v, K0, U0, U1, hmc ? 1 : 0, A.partials);
+  k_uf_final<T><<<grid, 128, 0, st>>>(A, w, v, K0, u_start, U1, hmc ? 1 : 0, A.partials, g_start, g, g_keep, u_keep);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
+  if (cacheable) {
+    c->ep_valid = true;
+    c->ep_q = A.q;
+    c->ep_pot = p;
+    c->ep_P = P;
+    c->ep_bits = (int)sizeof(T) * 8;
+  }
   return EHMC_OK;
 }
 

@@ -229,7 +229,8 @@ __global__ void k_uf_sv_finish(const T* w, T* v, long long P, int D, T h) {
 // final: p = v * m ; newH ; Metropolis ; write q / p_out / accept / per-particle stats partials
 template <typename T>
 __global__ void k_uf_final(const IterArgs<T> A, const T* w, const T* v, const T* K0, const T* U0, const T* U1,
-                           int hmc, double* pstats /* [P][3] or null */) {
+                           int hmc, double* pstats /* [P][3] or null */, const T* g_start = nullptr,
+                           const T* g_end = nullptr, T* g_keep = nullptr, T* u_keep = nullptr) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.P) return;
   const T m = A.mass[i];
@@ -276,7 +277,10 @@ __global__ void k_uf_final(const IterArgs<T> A, const T* w, const T* v, const T*
       A.p[d * A.p_ld + i] = pv;
     }
     if (!rej) A.q[d * A.q_ld + i] = w[d * A.P + i];
+    // endpoint cache: gradient at the position this particle keeps
+    if (g_keep != nullptr) g_keep[d * A.P + i] = rej ? g_start[d * A.P + i] : g_end[d * A.P + i];
   }
+  if (u_keep != nullptr) u_keep[i] = rej ? U0[i] : U1[i];
   if (A.accept != nullptr) A.accept[i] = rej ? 0 : 1;
   if (pstats != nullptr) {
     pstats[i * 3 + 0] = rej ? 0.0 : 1.0;

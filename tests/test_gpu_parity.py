@@ -1052,6 +1052,40 @@ def test_logistic_tensor_core_gradient(E, N, D, P):
     assert rel_err(u, po.energy(th)) < 2e-3
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_logistic_endpoint_cache_is_exact(E, precision):
+    """EHMC_FLAG_REUSE_ENDPOINT: starting every trajectory from the gradient / energy kept at the end of the
+    previous one (accepted: the trajectory's end, rejected: its start) gives bit-identical chains with one
+    gradient launch less per iteration."""
+    import torch
+
+    rng = np.random.RandomState(41)
+    N, D, P, L = 600, 40, 700, 4
+    X = rng.standard_normal((N, D)) / np.sqrt(D)
+    y = (rng.uniform(size=N) < 0.5).astype(np.float64)
+    pot = E.LogisticPotential(X, y, 1.0, precision=precision)
+    q0 = torch.tensor(rng.standard_normal((D, P)), dtype=torch.float32, device="cuda")
+    ctx = E._lib.Context.get()
+    res = {}
+    for reuse in (False, True):
+        ens = E.Ensemble(D, P, dtype=np.float32, device="cuda", seed=3)
+        ens.q.copy_(q0)
+        hmc = E.HMC(ens, L * 0.3 + 1e-9, 0.3, None, potential=pot, seed=3, bugCompat=False)
+        acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+        n0 = ctx.launch_count()
+        tot = 0
+        for it in range(6):
+            hmc.step(1 / KB, accept=acc, reuseEndpoint=reuse)
+            tot += int(acc.sum().item())
+            if it == 2:
+                # an external change of q invalidates the promise: the caller must drop the flag once
+                ens.q.mul_(1.0)
+        res[reuse] = (ens.q.clone(), tot, ctx.launch_count() - n0)
+    assert torch.equal(res[False][0], res[True][0])
+    assert res[False][1] == res[True][1] and 0.2 * 6 * P < res[True][1] < 6 * P  # accepts and rejects both occur
+    assert res[False][2] - res[True][2] == 5  # one gradient launch less in every iteration but the first
+
+
 def test_logistic_tensor_core_hmc_iteration(E):
     """A whole HMC iteration driven by the tensor-core gradient stays close to the exact one."""
     import torch
