@@ -116,7 +116,7 @@ typedef enum {
 #define EHMC_FLAG_REUSE_ENDPOINT 4u     /* the caller guarantees that q and the potential are exactly what the  \
                                            previous ehmc_hmc_iter on this context left behind (nothing else     \
                                            touched them): families that keep an endpoint cache (logistic        \
-                                           regression) then take grad U(q) and U(q) of the trajectory's start   \
+                                           regression, pairwise gravity) take grad U(q) and U(q) of the start   \
                                            from the kept end of the previous one instead of re-evaluating them  \
                                            -- L instead of L + 1 gradient evaluations per iteration, identical  \
                                            results.  Ignored when no valid cache exists. */

@@ -18,6 +18,9 @@ static NBodyArgs<T> nbody_args(const ehmc_potential* p) {
   pa.B = p->B;
   pa.G = (T)p->scalars[0];
   pa.eps2 = (T)(p->scalars[1] * p->scalars[1]);
+  pa.fcache = nullptr;
+  pa.ucache = nullptr;
+  pa.cache_read = 0;
   return pa;
 }
 
@@ -28,7 +31,19 @@ static int launch_nbody_ti(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<
   if (nt * TI < B) return fail(EHMC_ERR_UNSUPPORTED, "nbody: B = %d > %d bodies", B, 1024 * TI);
   const size_t sm = (size_t)B * BodyRec<T>::VECS * 4 * sizeof(T) + 40 * sizeof(T);
   if (sm > 227 * 1024) return fail(EHMC_ERR_UNSUPPORTED, "nbody: B = %d needs %zu B shared memory", B, sm);
-  const NBodyArgs<T> pa = nbody_args<T>(p);
+  NBodyArgs<T> pa = nbody_args<T>(p);
+  // endpoint cache (device path of ehmc_hmc_iter, leapfrog): see EHMC_FLAG_REUSE_ENDPOINT
+  const bool cacheable = hmc && integ == INTEG_LEAPFROG && c->ep_enabled && A.L > 0;
+  if (cacheable) {
+    const bool hit = (A.flags & FLAG_REUSE_ENDPOINT) && c->ep_valid && c->ep_q == (const void*)A.q && c->ep_pot == p &&
+                     c->ep_P == A.P && c->ep_bits == (int)sizeof(T) * 8;
+    TRY(c->ep_grad[0].ensure(sizeof(T) * (size_t)A.D * A.P));
+    TRY(c->ep_energy[0].ensure(sizeof(T) * (size_t)A.P));
+    pa.fcache = static_cast<T*>(c->ep_grad[0].ptr);
+    pa.ucache = static_cast<T*>(c->ep_energy[0].ptr);
+    pa.cache_read = hit ? 1 : 0;
+  }
+  c->ep_valid = false;
   const bool eps0 = p->scalars[1] == 0.0;
   void (*k)(const IterArgs<T>, const NBodyArgs<T>, const int, const int);
   if (nt <= 128)
@@ -41,6 +56,13 @@ static int launch_nbody_ti(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<
   k<<<(unsigned)A.P, nt, sm, st>>>(A, pa, integ, hmc ? 1 : 0);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
+  if (cacheable) {
+    c->ep_valid = true;
+    c->ep_q = A.q;
+    c->ep_pot = p;
+    c->ep_P = A.P;
+    c->ep_bits = (int)sizeof(T) * 8;
+  }
   return EHMC_OK;
 }
 

@@ -30,6 +30,11 @@ struct NBodyArgs {
   int B;
   T G;
   T eps2;
+  // endpoint cache (EHMC_FLAG_REUSE_ENDPOINT): f = sum_j m_j (r_j - r_i) / r^3 per coordinate, [3B][P] like q,
+  // and U per particle, at the position the previous iteration kept
+  T* fcache;
+  T* ucache;
+  int cache_read;  // 1: start from the cache instead of the first all-pairs sweep
 };
 
 template <typename T>
@@ -275,11 +280,29 @@ __global__ void __launch_bounds__(NTMAX) k_nbody(const IterArgs<T> A, const NBod
   };
 
   __syncthreads();
-  sweep(hmc);
   T oldH = T(0), newH = T(0);
-  if (hmc) {
-    const T U0 = energy();
-    oldH = T(0.5) * block_sum<T>(ksum, red, nwarps) * inv_M + U0;
+  const bool caching = hmc && pa.fcache != nullptr;
+  if (caching && pa.cache_read) {
+    // the previous iteration left f and U of this very position behind: no sweep
+#pragma unroll
+    for (int s = 0; s < NB_TI; ++s)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) f[s][c] = own[s] ? pa.fcache[((long long)c * B + body[s]) * A.P + part] : T(0);
+    oldH = T(0.5) * block_sum<T>(ksum, red, nwarps) * inv_M + pa.ucache[part];
+  } else {
+    sweep(hmc);
+    if (hmc) {
+      const T U0 = energy();
+      oldH = T(0.5) * block_sum<T>(ksum, red, nwarps) * inv_M + U0;
+      if (caching) {  // seed the cache with the start state (kept if the proposal is rejected)
+#pragma unroll
+        for (int s = 0; s < NB_TI; ++s)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (own[s]) pa.fcache[((long long)c * B + body[s]) * A.P + part] = f[s][c];
+        if (tid == 0) pa.ucache[part] = U0;
+      }
+    }
   }
   // acceleration of coordinate (s, c) = -dU/dq / M = G m_i f / M
   const T h = A.h, h2 = A.h2;
@@ -346,8 +369,9 @@ __global__ void __launch_bounds__(NTMAX) k_nbody(const IterArgs<T> A, const NBod
 
   bool rej = false;
   T accp = T(1);
+  T U1 = T(0);
   if (hmc) {
-    const T U1 = energy();
+    U1 = energy();
     newH = T(0.5) * block_sum<T>(ksum, red, nwarps) * inv_M + U1;
     T u;
     if (A.u != nullptr)
@@ -364,6 +388,14 @@ __global__ void __launch_bounds__(NTMAX) k_nbody(const IterArgs<T> A, const NBod
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         if (own[s]) A.q[((long long)c * B + body[s]) * A.q_ld + part] = x[s][c];
+    if (caching && integ == INTEG_LEAPFROG && L > 0) {  // f, U of the accepted end state (the last sweep's)
+#pragma unroll
+      for (int s = 0; s < NB_TI; ++s)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (own[s]) pa.fcache[((long long)c * B + body[s]) * A.P + part] = f[s][c];
+      if (tid == 0) pa.ucache[part] = U1;
+    }
   }
   if (A.p != nullptr) {
     if (rej) {

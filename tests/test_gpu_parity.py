@@ -1086,6 +1086,35 @@ def test_logistic_endpoint_cache_is_exact(E, precision):
     assert res[False][2] - res[True][2] == 5  # one gradient launch less in every iteration but the first
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_nbody_endpoint_cache_is_exact(E, dt):
+    """The same promise for the pairwise-gravity family: the first all-pairs sweep of every iteration is
+    replaced by the forces / energy kept from the previous one; chains stay bit-identical."""
+    import torch
+
+    rng = np.random.RandomState(43)
+    B, P, L = 24, 150, 3
+    pot = E.NBodyPotential(rng.uniform(0.5, 1.5, B) / B, G=1.0, eps=0.1)
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    q0 = torch.tensor(rng.standard_normal((3 * B, P)), dtype=tdt, device="cuda")
+    res = {}
+    for reuse in (False, True):
+        ens = E.Ensemble(3 * B, P, dtype=dt, device="cuda", seed=3)
+        ens.q.copy_(q0)
+        hmc = E.HMC(ens, L * 0.2 + 1e-9, 0.2, None, potential=pot, seed=3, bugCompat=False)
+        acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+        st = torch.zeros(2 * 3 * B + 3, dtype=torch.float64, device="cuda")
+        tot, hsum = 0, 0.0
+        for it in range(7):
+            hmc.step(1 / KB, accept=acc, stats=st, reuseEndpoint=reuse)
+            tot += int(acc.sum().item())
+            hsum += float(st[2].item())
+        res[reuse] = (ens.q.clone(), tot, hsum)
+    assert torch.equal(res[False][0], res[True][0])
+    assert res[False][1] == res[True][1] and 0.1 * 7 * P < res[True][1] < 7 * P
+    assert res[False][2] == res[True][2]  # the Hamiltonians entering the statistics are the same numbers
+
+
 def test_logistic_tensor_core_hmc_iteration(E):
     """A whole HMC iteration driven by the tensor-core gradient stays close to the exact one."""
     import torch
