@@ -1,5 +1,7 @@
 #pragma once
 
+#include <algorithm>
+
 #include "host_defs.h"
 #include "k_logistic.cuh"
 
@@ -57,6 +59,9 @@ int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, 
   T* U0 = K0 + P;
   T* U1 = U0 + P;
   const unsigned grid = (unsigned)((P + 127) / 128);
+  // kick/drift: enough CTAs to fill the GPU (particles x dimension slices)
+  const unsigned ysplit = (unsigned)std::max(1, std::min(D, (int)((8 * c->prop.multiProcessorCount + grid - 1) / grid)));
+  const dim3 kgrid(grid, ysplit);
   const T h = A.h, h2 = A.h2;
   // ep_enabled is set by the device path only (one call = the whole resident ensemble)
   const bool cacheable = hmc && integ == INTEG_LEAPFROG && slot == 0 && c->ep_enabled && L > 0;
@@ -81,13 +86,13 @@ int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, 
   if (!hit) TRY(logistic_grad<T>(c, p, w, P, P, g_start, P, hmc ? u_start : nullptr, st));
   if (integ == INTEG_LEAPFROG) {
     if (L > 0) {
-      k_uf_kick_drift<T><<<grid, 128, 0, st>>>(w, v, g_start, A.mass, P, D, T(0.5) * h, h);
+      k_uf_kick_drift<T><<<kgrid, 128, 0, st>>>(w, v, g_start, A.mass, P, D, T(0.5) * h, h);
       c->launches++;
     }
     for (int s = 0; s < L; ++s) {
       const bool last = s == L - 1;
       TRY(logistic_grad<T>(c, p, w, P, P, g, P, (hmc && last) ? U1 : nullptr, st));
-      k_uf_kick_drift<T><<<grid, 128, 0, st>>>(w, v, g, A.mass, P, D, last ? T(0.5) * h : h, last ? T(0) : h);
+      k_uf_kick_drift<T><<<kgrid, 128, 0, st>>>(w, v, g, A.mass, P, D, last ? T(0.5) * h : h, last ? T(0) : h);
       c->launches++;
     }
     if (L == 0 && hmc) CUDA_TRY(cudaMemcpyAsync(U1, u_start, sizeof(T) * P, cudaMemcpyDeviceToDevice, st));

@@ -195,10 +195,14 @@ __global__ void k_uf_init(const IterArgs<T> A, T* w, T* v, T* K0, int hmc) {
 // kick-drift: v -= ck * g / m ; w += cd * v   (ck, cd select half/full kicks and the drift)
 template <typename T>
 __global__ void k_uf_kick_drift(T* w, T* v, const T* g, const T* mass, long long P, int D, T ck, T cd) {
+  // grid.y splits the dimensions: a thread per particle alone leaves too few loads in flight to reach HBM speed
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const T c = ck / mass[i];
-  for (int d = 0; d < D; ++d) {
+  const int dper = (D + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int d0 = (int)blockIdx.y * dper, d1 = d0 + dper < D ? d0 + dper : D;
+#pragma unroll 4
+  for (int d = d0; d < d1; ++d) {
     const T vv = v[d * P + i] - c * g[d * P + i];
     v[d * P + i] = vv;
     if (cd != T(0)) w[d * P + i] += cd * vv;
