@@ -198,7 +198,8 @@ class HMC:
                 else:
                     z = torch.from_numpy(z).to(device=ens.device, dtype=dt)
                     u = torch.from_numpy(u).to(device=ens.device, dtype=dt)
-            self.step(temperature, p_out=p_buf, accept=acc, z=z, u=u)
+            # between iterations q is only read (copied into samples_hmc): the endpoint cache may be used
+            self.step(temperature, p_out=p_buf, accept=acc, z=z, u=u, reuseEndpoint=i > 0)
             self.integrator.p = p_buf
             ens.p = p_buf
             samples_hmc[:, :, i] = self.integrator.q
