@@ -949,6 +949,72 @@ def test_dense_tensor_core_zero_step(E):
     np.testing.assert_allclose(q.cpu().numpy(), q0, rtol=3e-7, atol=1e-7)
 
 
+@pytest.mark.parametrize("case", ["diag2", "funnel10", "dense100", "dense40_cuda_cores", "nbody", "logistic", "logistic_tc"])
+def test_no_out_of_bounds_writes_canary(E, case):
+    """Every in/out tensor of ehmc_hmc_iter is a window into a larger canary-filled allocation (one guard row
+    above and below, 37 guard columns left and right, ragged P): after the call every guard element still
+    holds the canary.  (compute-sanitizer is closed on this pool; this is the bounds check of our own.)"""
+    import torch
+
+    rng = np.random.RandomState(51)
+    P, L, h = 333, 3, 0.05
+    path = 0
+    if case == "diag2":
+        D, pot = 2, E.HarmonicPotential([1.0, 2.0])
+    elif case == "funnel10":
+        D, pot = 10, E.FunnelPotential(10, 3.0)
+    elif case.startswith("dense"):
+        D = 100 if case == "dense100" else 40
+        A = rng.standard_normal((D, D))
+        pot = E.GaussianPotential(precision=A @ A.T / D + np.eye(D), mean=rng.standard_normal(D))
+        path = 1 if case.endswith("cuda_cores") else 0
+    elif case == "nbody":
+        B = 21
+        D, pot, h = 3 * B, E.NBodyPotential(np.ones(B) / B, G=1.0, eps=0.1), 0.01
+    else:
+        N, D = 300, 24
+        X = rng.standard_normal((N, D)) / np.sqrt(D)
+        y = (rng.uniform(size=N) < 0.5).astype(np.float64)
+        pot = E.LogisticPotential(X, y, 1.0, precision="bf16" if case.endswith("tc") else "fp32")
+    CAN, G = -777.25, 37
+
+    def window(rows, dtype=torch.float32):
+        big = torch.full((rows + 2, P + 2 * G), CAN, dtype=dtype, device="cuda")
+        return big, big[1:rows + 1, G:G + P]
+
+    qb, q = window(D)
+    pb, p = window(D)
+    q.copy_(torch.tensor(rng.standard_normal((D, P)), dtype=torch.float32))
+    mb = torch.full((P + 2 * G,), CAN, dtype=torch.float32, device="cuda")
+    mass = mb[G:G + P]
+    mass.fill_(1.3)
+    ab = torch.full((P + 2 * G,), 77, dtype=torch.uint8, device="cuda")
+    acc = ab[G:G + P]
+    sb = torch.full((2 * D + 3 + 2 * G,), CAN, dtype=torch.float64, device="cuda")
+    st = sb[G:G + 2 * D + 3]
+    ctx = E._lib.Context.get()
+    ctx.set_option("dense_path", path)
+    try:
+        args = E._lib.make_args(h, h * h, L, KB, 1 / KB, seed=2, iteration=1)
+        E._lib.hmc_iter(ctx, pot.handle(32, ctx), q, mass, args, p_out=p, accept=acc, stats=st)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_option("dense_path", 0)
+
+    def guards_intact(big, inner_rows, value):
+        g = big.clone()
+        if big.dim() == 2:
+            g[1:inner_rows + 1, G:G + P] = value
+        else:
+            g[G:G + inner_rows] = value
+        return bool((g == value).all().item())
+
+    assert guards_intact(qb, D, CAN) and guards_intact(pb, D, CAN)
+    assert guards_intact(mb, P, CAN) and guards_intact(ab, P, 77) and guards_intact(sb, 2 * D + 3, CAN)
+    assert torch.isfinite(q).all() and torch.isfinite(p).all() and (acc <= 1).all()
+    assert st[0].item() == acc.sum().item()
+
+
 # ---------------------------------------------------------------------------
 # production loop: statistics, adaptation, ESS
 # ---------------------------------------------------------------------------
