@@ -543,9 +543,9 @@ static bool per_particle_stats(const ehmc_potential* p) {
 
 // the float32 dense family runs on the tensor cores (3xTF32) unless told otherwise
 static bool use_dense_tc(const ehmc_ctx* c, const ehmc_potential* p, int integ) {
-  if (!(p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->bits == 32 && integ == INTEG_LEAPFROG) || c->dense_path == 1)
-    return false;
-  if (c->dense_path == 2 || c->dense_path == 3) return p->tc_nch >= 2;  // the 3xTF32 kernels (D <= 104)
+  if (!(p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->bits == 32) || c->dense_path == 1) return false;
+  if (c->dense_path == 2 || c->dense_path == 3)  // the 3xTF32 kernels (D <= 104, leapfrog only)
+    return p->tc_nch >= 2 && integ == INTEG_LEAPFROG;
   return p->tc3_c8 >= 3;                                                // 0 (auto), 4: 3xFP16 persistent kernel
 }
 
@@ -573,7 +573,7 @@ static int launch_traj(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& 
   if (p->family == EHMC_FAMILY_NBODY) return launch_nbody<T>(c, p, A, integ, hmc, st);
   if (p->family == EHMC_FAMILY_LOGISTIC) return launch_logistic<T>(c, p, A, integ, hmc, st, slot);
   if constexpr (sizeof(T) == 4) {
-    if (use_dense_tc(c, p, integ)) return launch_dense_tc(c, p, A, hmc, st);
+    if (use_dense_tc(c, p, integ)) return launch_dense_tc(c, p, A, integ, hmc, st);
   }
   if (c->dense_path >= 2 && p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16 && sizeof(T) == 4)
     return fail(EHMC_ERR_UNSUPPORTED, "dense_path >= 2 (tensor cores) but this call is not eligible (D = %d, integrator %d)", p->D, integ);

@@ -115,10 +115,10 @@ int run_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int in
 // dense Gaussian, 16 < D <= 128
 template <typename T>
 int launch_dense(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);
-// float32 3xTF32 tensor-core variant (leapfrog only)
-int launch_dense_tc(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, bool hmc, cudaStream_t st);
-// float32 3xFP16 persistent tensor-core variant (leapfrog only; the default)
-int launch_dense_tc3(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, bool hmc, cudaStream_t st);
+// float32 tensor-core variants (3xTF32: leapfrog only)
+int launch_dense_tc(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, int integ, bool hmc, cudaStream_t st);
+// float32 3xFP16 persistent tensor-core variant (leapfrog and Stormer-Verlet; the default)
+int launch_dense_tc3(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, int integ, bool hmc, cudaStream_t st);
 template <typename T>
 int dense_particles_per_cta();
 int dense_tn(int D);

@@ -42,8 +42,8 @@ static int launch_tc2_k8(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<fl
   return EHMC_OK;
 }
 
-int launch_dense_tc(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, bool hmc, cudaStream_t st) {
-  if (c->dense_path == 0 || c->dense_path >= 4) return launch_dense_tc3(c, p, A, hmc, st);
+int launch_dense_tc(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, int integ, bool hmc, cudaStream_t st) {
+  if (c->dense_path == 0 || c->dense_path >= 4) return launch_dense_tc3(c, p, A, integ, hmc, st);
   if (c->dense_path != 2) {  // two-tile TS-mode kernel (default); dense_path = 2 selects the one-tile SS kernel
     switch (p->tc_kp / 8) {
       case 3: return launch_tc2_k8<3>(c, p, A, hmc, st);

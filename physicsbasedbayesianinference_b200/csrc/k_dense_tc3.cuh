@@ -250,7 +250,7 @@ __device__ __noinline__ float tc3_energy(uint32_t t_d, uint32_t t_hi, uint32_t t
 
 template <int C8>
 __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<float> Ain, const DenseTc3Args pa,
-                                                              const int hmc) {
+                                                              const int hmc, const int integ) {
   const IterArgs<float> A = resolve_dynamic(Ain);
   typedef Tc3Shape<C8> S;
   constexpr int NP = S::NP, KP = S::KP, K16 = S::K16, DC = S::DC, KCH = S::KCH;
@@ -458,7 +458,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
     const float ckf = (h * inv_m) * (h * pa.inv_lscale), ckh = 0.5f * ckf;  // hs * (h / m) * gs
     float U0 = 0.f, U1 = 0.f;
 
-    for (int ev = 0; ev <= L; ++ev) {
+    // Leapfrog (src/integrator.py:105-120): evaluations 0 .. L; half kick, (L - 1) x [drift, kick], drift, half kick.
+    // Stormer-Verlet (src/integrator.py:142-163) in displacement form d_n = q_n - q_{n-1} (w IS sc d_n):
+    //   start-up q_1 = q_0 + v h + a_0 h^2 / 2  = half kick + drift;  q_{n+1} = 2 q_n - q_{n-1} + a_n h^2 = kick + drift,
+    //   L + 1 drifts in all, v = d_{L+1} / h (backward difference, no closing half kick); one more evaluation
+    //   (no kick, no drift) only for the energy at q_{L+1}.
+    const bool sv = integ == INTEG_STORMER;
+    const int Lend = (sv && hmc) ? L + 1 : L;
+    for (int ev = 0; ev <= Lend; ++ev) {
       // the tile's operands are complete once all 128 rows arrive
       tc_fence_before();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -485,13 +492,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       mbar_wait(&mbar[grp], phase);
       phase ^= 1u;
       tc_fence_after();
-      const bool first = ev == 0, last = ev == L;
+      const bool first = ev == 0;
+      const bool last = sv ? ev == L + 1 : ev == L;  // the evaluation that neither drifts nor stores
       if (hmc && (first || last)) {
         const float Uev = tc3_energy<C8>(t_d, t_hi, t_lo);
         if (first) U0 = Uev;
         if (last) U1 = Uev;
       }
-      const float ck = L == 0 ? 0.f : ((first || last) ? ckh : ckf);
+      const float ck = sv ? (first ? ckh : (last ? 0.f : ckf)) : (L == 0 ? 0.f : ((first || last) ? ckh : ckf));
       if (!(pa.dbg & 2)) tc3_epilogue<C8>(v, t_d, t_hi, t_lo, ck, !last);
       if (ev < 2 || ev >= L - 1) stamp();  // 5, 6: first two evaluations; then the last two
     }

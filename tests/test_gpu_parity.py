@@ -881,6 +881,60 @@ def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
     print("D", D, {f"path{k}-vs-oracle": float(rel_err(out[k][0], qr)) for k in paths})
 
 
+@pytest.mark.parametrize("D,P,L", [(100, 700, 20), (40, 129, 0), (128, 300, 7), (24, 1000, 3)])
+def test_dense_tensor_core_stormer_verlet(E, D, P, L):
+    """method="Stormer-Verlet" (src/integrator.py:142-163: L + 1 position updates, backward-difference
+    momentum) on the tensor-core kernel: one HMC iteration and a bare integrate() against the oracle."""
+    import torch
+
+    rng = np.random.RandomState(D + L)
+    A = rng.standard_normal((D, D))
+    prec = A @ A.T / D + np.eye(D)
+    mu = rng.standard_normal(D)
+    pe, po = E.GaussianPotential(precision=prec, mean=mu), O.DenseGaussian(prec, mu)
+    q0 = rng.standard_normal((D, P)) + mu[:, None]
+    z = rng.standard_normal((D, P))
+    u = rng.uniform(size=P)
+    mass = rng.uniform(0.5, 2.0, P)
+    h = 0.05
+    qr, pr, accr, oh, nh = O.hmc_iter(q0, z, u, mass, 1 / KB, h, L, po, integrator="Stormer-Verlet", bug_compat=False)
+    ctx = E._lib.Context.get()
+    hd = pe.handle(32, ctx)
+    args = E._lib.make_args(h, h**2, L, KB, 1 / KB, integrator=E._lib.STORMER_VERLET, flags=0)
+    out = {}
+    try:
+        for path in (1, 4):  # CUDA cores, tensor cores
+            ctx.set_option("dense_path", path)
+            q = torch.tensor(q0, dtype=torch.float32, device="cuda")
+            p = torch.empty_like(q)
+            acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+            E._lib.hmc_iter(ctx, hd, q, torch.tensor(mass, dtype=torch.float32, device="cuda"), args, p_out=p,
+                            z=torch.tensor(z, dtype=torch.float32, device="cuda"),
+                            u=torch.tensor(u, dtype=torch.float32, device="cuda"), accept=acc)
+            torch.cuda.synchronize()
+            out[path] = (q.cpu().numpy(), p.cpu().numpy(), acc.cpu().numpy().astype(bool))
+    finally:
+        ctx.set_option("dense_path", 0)
+    with np.errstate(over="ignore"):
+        clear = np.abs(u - np.minimum(1, np.exp(oh - nh))) > TIE[np.float32]
+    for path in (1, 4):
+        q, p, a = out[path]
+        assert np.array_equal(a[clear], accr[clear]), f"path {path}"
+        same = a == accr
+        assert rel_err(q[:, same], qr[:, same]) < 1e-5, f"path {path}"
+        # the backward-difference momentum (q_{L+1} - q_L) / h loses log10(|q| / (h |v|)) digits in float32
+        assert rel_err(p[:, same], pr[:, same]) < 2e-4, f"path {path}"
+    # integrate() without Metropolis
+    p0 = rng.standard_normal((D, P))
+    qi, pi = O.stormer_verlet(q0, p0, mass, h, L, po.grad)
+    ens = E.Ensemble(D, P, dtype=np.float32, device="cuda")
+    ens.q.copy_(torch.tensor(q0, dtype=torch.float32))
+    ens.p.copy_(torch.tensor(p0, dtype=torch.float32))
+    ens.mass = torch.tensor(mass, dtype=torch.float32, device="cuda")
+    qg, pg = E.StormerVerlet(ens, h, L * h + 1e-9, pe).integrate()
+    assert rel_err(qg.cpu().numpy(), qi) < 1e-5 and rel_err(pg.cpu().numpy(), pi) < 2e-4
+
+
 def test_dense_tensor_core_integrate_only(E):
     """Leapfrog.integrate() (no Metropolis) on the tensor-core path."""
     import torch
