@@ -537,11 +537,14 @@ extern "C" int ehmc_potential_destroy(ehmc_potential* p) {
 
 // number of CTAs the trajectory kernel uses for P particles (statistics partials)
 // families whose trajectory kernel reports statistics per particle ([P][3]) and needs k_colstats
-static bool per_particle_stats(const ehmc_potential* p) {
-  return p->family == EHMC_FAMILY_NBODY || p->family == EHMC_FAMILY_LOGISTIC;
+static bool use_dense_tc(const ehmc_ctx* c, const ehmc_potential* p, int integ);
+static bool per_particle_stats(const ehmc_ctx* c, const ehmc_potential* p, int integ) {
+  if (p->family == EHMC_FAMILY_NBODY || p->family == EHMC_FAMILY_LOGISTIC) return true;
+  // the 3xFP16 tensor-core dense kernel reports per-particle scalars too
+  return use_dense_tc(c, p, integ) && (c->dense_path == 0 || c->dense_path == 4);
 }
 
-// the float32 dense family runs on the tensor cores (3xTF32) unless told otherwise
+// the float32 dense family runs on the tensor cores unless told otherwise
 static bool use_dense_tc(const ehmc_ctx* c, const ehmc_potential* p, int integ) {
   if (!(p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->bits == 32) || c->dense_path == 1) return false;
   if (c->dense_path == 2 || c->dense_path == 3)  // the 3xTF32 kernels (D <= 104, leapfrog only)
@@ -551,7 +554,7 @@ static bool use_dense_tc(const ehmc_ctx* c, const ehmc_potential* p, int integ) 
 
 template <typename T>
 static long long traj_blocks(const ehmc_ctx* c, const ehmc_potential* p, long long P, int integ) {
-  if (per_particle_stats(p)) return P;
+  if (per_particle_stats(c, p, integ)) return P;
   if (use_dense_tc(c, p, integ)) {
     if (c->dense_path == 2) return 8 * ((P + 127) / 128);
     if (c->dense_path == 3) return 8 * ((P + 255) / 256);
@@ -626,24 +629,46 @@ static IterArgs<T> base_args(const CallViews& v, double h, double h2, int L) {
 template <typename T>
 static int run_device(ehmc_ctx* c, const ehmc_potential* pot, IterArgs<T> A, int integ, bool hmc, double* stats_dev,
                       cudaStream_t st) {
-  const bool pps = per_particle_stats(pot);
-  const int NS = pps ? 3 : 2 * A.D + 3;
+  const bool pps = per_particle_stats(c, pot, integ);
+  const int NS = 2 * A.D + 3;
   long long nblk = 0;
   if (stats_dev != nullptr) {
-    nblk = traj_blocks<T>(c, pot, A.P, integ);
-    TRY(c->partials.ensure(sizeof(double) * (size_t)std::max(1LL, nblk) * NS));
-    A.partials = static_cast<double*>(c->partials.ptr);
+    if (pps) {
+      // per-particle scalars [P][3] from the trajectory kernel; reduced together with the coordinate sums below
+      nblk = std::max<long long>(1, std::min<long long>(4LL * c->prop.multiProcessorCount, (A.P + 255) / 256));
+      TRY(c->pstats.ensure(sizeof(double) * 3 * (size_t)std::max(1LL, A.P)));
+      if (A.P >= 16LL * A.D) TRY(c->partials.ensure(sizeof(double) * (size_t)nblk * NS));
+      A.partials = static_cast<double*>(c->pstats.ptr);
+    } else {
+      nblk = traj_blocks<T>(c, pot, A.P, integ);
+      TRY(c->partials.ensure(sizeof(double) * (size_t)std::max(1LL, nblk) * NS));
+      A.partials = static_cast<double*>(c->partials.ptr);
+    }
   }
   c->ep_enabled = true;  // the endpoint cache is only meaningful when one call covers the resident ensemble
   const int rc_traj = launch_traj<T>(c, pot, A, integ, hmc, st);
   c->ep_enabled = false;
   TRY(rc_traj);
   if (stats_dev != nullptr && A.P > 0) {
-    if (!pps) nblk = c->last_rows;
-    k_stats_finalize<<<NS, 256, 0, st>>>(A.partials, (int)nblk, NS, stats_dev);
+    double* rows = static_cast<double*>(c->partials.ptr);
+    if (pps && A.P < 16LL * A.D) {
+      // few particles, many coordinates (N-body): one CTA per statistic / per coordinate
+      k_stats_finalize<<<3, 256, 0, st>>>(A.partials, (int)A.P, 3, stats_dev);
+      c->launches++;
+      CUDA_TRY(cudaGetLastError());
+      TRY(colstats<T>(c, A.q, A.q_ld, A.P, A.D, stats_dev, st));
+      return EHMC_OK;
+    }
+    if (pps) {
+      // many particles: one streaming pass over pstats and q, particle slices per CTA
+      k_ens_stats_partial<T><<<(unsigned)nblk, 256, 0, st>>>(A.partials, A.q, A.q_ld, A.P, A.D, rows);
+      c->launches++;
+    } else {
+      nblk = c->last_rows;
+    }
+    k_stats_finalize<<<NS, 256, 0, st>>>(rows, (int)nblk, NS, stats_dev);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    if (pps) TRY(colstats<T>(c, A.q, A.q_ld, A.P, A.D, stats_dev, st));
   }
   return EHMC_OK;
 }
@@ -670,7 +695,7 @@ static int run_host(ehmc_ctx* c, const ehmc_potential* pot, const CallViews& v, 
   for (int i = 0; i < N_STAGE; ++i) TRY(c->stage[i].ensure(slab_bytes));
   long long blocks_total = 0;  // upper bound of the statistics rows (exact count: rows_done below)
   for (long long k = 0; k < nchunks; ++k) blocks_total += traj_blocks<T>(c, pot, std::min(chunk, P - k * chunk), integ);
-  const bool pps = per_particle_stats(pot);
+  const bool pps = per_particle_stats(c, pot, integ);
   if (v.has_stats) {
     // fused families: one row of NS sums per CTA.  per-particle families: [P][3] rows in pstats plus
     // one row of coordinate sums per chunk (k_colstats) in partials.

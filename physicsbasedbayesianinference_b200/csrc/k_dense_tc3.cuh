@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       rej = metropolis_reject<float>(oldH, newH, u, A.flags, &accp);
     }
     stamp();  // Metropolis decided
-    const bool fast = A.p == nullptr && A.partials == nullptr;
+    const bool fast = A.p == nullptr;  // statistics are per-particle scalars here (A.partials = [P][3]), see below
     const bool wr = valid && !rej;  // HMC.py:175: rejected rows keep the value in HBM
     // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only accepted rows store.
     // Rolled loops (see the prologue note on code size).
@@ -559,8 +559,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
         tmem_st8(t_d + (uint32_t)(8 * c), pk);
       }
       tmem_wait_st();
-      const bool need_old = rej && (A.partials != nullptr || (A.flags & FLAG_BUGCOMPAT));
-      double* prow_out = A.partials ? A.partials + ((size_t)tile * 4 + quarter) * (2 * D + 3) : nullptr;
+      const bool need_old = rej && (A.flags & FLAG_BUGCOMPAT);
 #pragma unroll 1
       for (int c = 0; c < C8; ++c) {
         uint32_t hh[4], ll[4], pk[8];
@@ -592,30 +591,18 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
             }
             A.p[d * A.p_ld + pc] = pv;
           }
-          if (prow_out != nullptr) {
-            const double qk = valid ? (double)(rej ? qold : qn) : 0.0;
-            const double s1 = warp_sum(qk), s2 = warp_sum(qk * qk);
-            if (lane == 0) {
-              prow_out[3 + d] = s1;
-              prow_out[3 + D + d] = s2;
-            }
-          }
-        }
-      }
-      if (prow_out != nullptr) {
-        double s_acc = valid ? (rej ? 0.0 : 1.0) : 0.0, s_accp = valid ? (double)accp : 0.0;
-        double s_h = valid ? (double)(rej ? oldH : newH) : 0.0;
-        s_acc = warp_sum(s_acc);
-        s_accp = warp_sum(s_accp);
-        s_h = warp_sum(s_h);
-        if (lane == 0) {
-          prow_out[0] = s_acc;
-          prow_out[1] = s_accp;
-          prow_out[2] = s_h;
         }
       }
     }
     if (hmc && valid && A.accept != nullptr) A.accept[pc] = rej ? 0 : 1;
+    // ensemble statistics: this kernel only reports the per-particle scalars; the coordinate sums are taken
+    // from q by k_ens_stats_partial afterwards (a warp reduction of 2 D doubles per tile cost 1.3 ms per
+    // iteration at config 2, a streaming pass over q costs 0.1 ms)
+    if (hmc && valid && A.partials != nullptr) {
+      A.partials[pc * 3 + 0] = rej ? 0.0 : 1.0;
+      A.partials[pc * 3 + 1] = (double)accp;
+      A.partials[pc * 3 + 2] = (double)(rej ? oldH : newH);
+    }
     stamp();  // write-back issued
     if (prof) pa.prof[63] = (long long)pi;
   }

@@ -24,6 +24,56 @@ static __global__ void k_stats_finalize(const double* __restrict__ partials, int
   }
 }
 
+// Ensemble statistics of the families that report per-particle scalars (pstats [P][3] = accepted, acceptance
+// probability, H of the kept state): CTA b sums its contiguous slice of particles -- the three scalars and, straight
+// from q, sum_i q[d, i] and sum_i q[d, i]^2 of every coordinate -- into row b of rows[gridDim.x][2D+3];
+// k_stats_finalize adds the rows.  Fixed slicing, float64 sums: deterministic and shard-additive.
+template <typename T>
+__global__ void __launch_bounds__(256) k_ens_stats_partial(const double* __restrict__ pstats, const T* __restrict__ q,
+                                                           long long q_ld, long long P, int D, double* __restrict__ rows) {
+  const long long lo = P * blockIdx.x / gridDim.x, hi = P * (blockIdx.x + 1) / gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  __shared__ double sm[2][8];
+  double* row = rows + (size_t)blockIdx.x * (2 * D + 3);
+  auto block_sum2 = [&](double a, double b, double* oa, double* ob) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) {
+      sm[0][w] = a;
+      sm[1][w] = b;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double x = 0.0, y = 0.0;
+      for (int k = 0; k < 8; ++k) {
+        x += sm[0][k];
+        y += sm[1][k];
+      }
+      *oa = x;
+      if (ob) *ob = y;
+    }
+  };
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (long long i = lo + tid; i < hi; i += 256) {
+    s0 += pstats[i * 3 + 0];
+    s1 += pstats[i * 3 + 1];
+    s2 += pstats[i * 3 + 2];
+  }
+  block_sum2(s0, s1, &row[0], &row[1]);
+  block_sum2(s2, 0.0, &row[2], nullptr);
+  for (int d = 0; d < D; ++d) {
+    const T* qd = q + (long long)d * q_ld;
+    double a = 0.0, b = 0.0;
+    for (long long i = lo + tid; i < hi; i += 256) {
+      const double v = (double)qd[i];
+      a += v;
+      b = fma(v, v, b);
+    }
+    block_sum2(a, b, &row[3 + d], &row[3 + D + d]);
+  }
+}
+
 // U and/or grad U for the register-resident families (vectorised potential(q[:, i])).
 template <typename T, int DT, class Pot>
 __global__ void k_eval_small(const T* __restrict__ q, long long q_ld, long long P, int D, T* energy, T* grad,
