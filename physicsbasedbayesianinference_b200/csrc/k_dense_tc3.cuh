@@ -85,6 +85,30 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The evaluation loop is a serial chain per group (sync -> MMA issue -> wait -> epilogue); anything the
+// compiler re-materialises inside it (generic->shared address conversions with their S2UR CgaCtaId, descriptor
+// arithmetic, kick coefficients) lengthens the chain.  pin() makes a value opaque so that it is computed once and
+// kept in a register; the *_a helpers take precomputed 32-bit shared addresses.
+__device__ __forceinline__ void pin(uint32_t& x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void pin(uint64_t& x) { asm volatile("" : "+l"(x)); }
+__device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -300,8 +324,19 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
   const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
   const uint32_t t_d = tmem_base + (uint32_t)(grp * 256) + lane_off;  // this row's accumulator
   const uint32_t t_hi = t_d + (uint32_t)S::HI_COL, t_lo = t_d + (uint32_t)S::LO_COL;
-  const uint32_t idesc = umma_idesc_f16(TC_M, NP);
-  const uint64_t db_hi = umma_desc(smem_u32(Bhi), NP), db_lo = umma_desc(smem_u32(Blo), NP);
+  uint32_t idesc = umma_idesc_f16(TC_M, NP);
+  uint64_t db_hi = umma_desc(smem_u32(Bhi), NP), db_lo = umma_desc(smem_u32(Blo), NP);
+  uint32_t mbar_a = smem_u32(&mbar[grp < 2 ? grp : 0]);
+  pin(idesc);
+  pin(db_hi);
+  pin(db_lo);
+  pin(mbar_a);
+  // kernel parameters tested in every evaluation: one constant-bank load each, here, instead of an LDC -> use
+  // latency in the serial chain of every evaluation
+  uint32_t k_dbg = (uint32_t)pa.dbg, k_hmc = (uint32_t)hmc, k_sv = integ == INTEG_STORMER ? 1u : 0u;
+  pin(k_dbg);
+  pin(k_hmc);
+  pin(k_sv);
   constexpr uint64_t b_step = (2u * NP * 16u) >> 4;
   const uint32_t mma_d = tmem_base + (uint32_t)(grp * 256);
   const uint32_t mma_hi = mma_d + (uint32_t)S::HI_COL, mma_lo = mma_d + (uint32_t)S::LO_COL;
@@ -455,7 +490,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
     const float hs = h * sc, gs = isc * pa.inv_lscale;
 #pragma unroll
     for (int d = 0; d < DC; ++d) v[d] *= hs;
-    const float ckf = (h * inv_m) * (h * pa.inv_lscale), ckh = 0.5f * ckf;  // hs * (h / m) * gs
+    float ckf = (h * inv_m) * (h * pa.inv_lscale), ckh = 0.5f * ckf;  // hs * (h / m) * gs
+    pin(ckf);
+    pin(ckh);
     float U0 = 0.f, U1 = 0.f;
 
     // Leapfrog (src/integrator.py:105-120): evaluations 0 .. L; half kick, (L - 1) x [drift, kick], drift, half kick.
@@ -463,15 +500,18 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
     //   start-up q_1 = q_0 + v h + a_0 h^2 / 2  = half kick + drift;  q_{n+1} = 2 q_n - q_{n-1} + a_n h^2 = kick + drift,
     //   L + 1 drifts in all, v = d_{L+1} / h (backward difference, no closing half kick); one more evaluation
     //   (no kick, no drift) only for the energy at q_{L+1}.
-    const bool sv = integ == INTEG_STORMER;
-    const int Lend = (sv && hmc) ? L + 1 : L;
+    // first row of this warp in the group's next tile (null: no next tile / past the end)
+    const float* pf_row = (tile + 2 < tile1 && (tile + 2) * TC_M + quarter * 32 < A.P)
+                              ? A.q + (tile + 2) * TC_M + quarter * 32 : nullptr;
+    const bool sv = k_sv != 0u;
+    const int Lend = (sv && k_hmc) ? L + 1 : L;
     for (int ev = 0; ev <= Lend; ++ev) {
       // the tile's operands are complete once all 128 rows arrive
       tc_fence_before();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       if (quarter == 0 && elect_one()) {
         tc_fence_after();
-        if (!(pa.dbg & 1)) {
+        if (!(k_dbg & 1u)) {
 #pragma unroll
           for (int j = 0; j < K16; ++j) umma_f16_ts(mma_d, mma_hi + 8u * j, db_hi + j * b_step, idesc, j > 0);
 #pragma unroll
@@ -479,28 +519,24 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
 #pragma unroll
           for (int j = 0; j < K16; ++j) umma_f16_ts(mma_d, mma_hi + 8u * j, db_lo + j * b_step, idesc, 1);
         }
-        umma_commit(&mbar[grp]);
+        umma_commit_a(mbar_a);
       }
       // in the shadow of the MMAs: L2 prefetch of the next tile's positions
-      if (ev == 1 && tile + 2 < tile1) {
-        const long long r0 = (tile + 2) * TC_M + quarter * 32;
-        if (r0 < A.P) {
-          for (int d = lane; d < D; d += 32)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.q + (long long)d * A.q_ld + r0));
-        }
+      if (ev == 1 && pf_row != nullptr) {
+        for (int d = lane; d < D; d += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row + (long long)d * A.q_ld));
       }
-      mbar_wait(&mbar[grp], phase);
+      mbar_wait_a(mbar_a, phase);
       phase ^= 1u;
       tc_fence_after();
       const bool first = ev == 0;
       const bool last = sv ? ev == L + 1 : ev == L;  // the evaluation that neither drifts nor stores
-      if (hmc && (first || last)) {
+      if (k_hmc && (first || last)) {
         const float Uev = tc3_energy<C8>(t_d, t_hi, t_lo);
         if (first) U0 = Uev;
         if (last) U1 = Uev;
       }
       const float ck = sv ? (first ? ckh : (last ? 0.f : ckf)) : (L == 0 ? 0.f : ((first || last) ? ckh : ckf));
-      if (!(pa.dbg & 2)) tc3_epilogue<C8>(v, t_d, t_hi, t_lo, ck, !last);
+      if (!(k_dbg & 2u)) tc3_epilogue<C8>(v, t_d, t_hi, t_lo, ck, !last);
       if (ev < 2 || ev >= L - 1) stamp();  // 5, 6: first two evaluations; then the last two
     }
     // U = 1/2 x . g_true = 1/2 (xs isc) . (G gs)
