@@ -248,6 +248,12 @@ __device__ __forceinline__ void tc3_epilogue(float (&w)[8 * C8], uint32_t t_d, u
   if (store) tmem_wait_st();
 }
 
+// L2 prefetch of one warp's 32 rows of the next tile, all D coordinates (out of line: inlined, the compiler
+// folds its lane / D tests into the branch of EVERY evaluation, an S2R and an LDC in the serial chain)
+static __device__ __noinline__ void tc3_prefetch_rows(const float* row0, long long ld, int D) {
+  for (int d = (int)(threadIdx.x & 31); d < D; d += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row0 + (long long)d * ld));
+}
+
 // sum_d xs_d G_d of this row (first and last evaluation only: a rolled loop, kept out of the
 // unrolled epilogue so that the 49 middle evaluations do not pay for it)
 template <int C8>
@@ -522,9 +528,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
         umma_commit_a(mbar_a);
       }
       // in the shadow of the MMAs: L2 prefetch of the next tile's positions
-      if (ev == 1 && pf_row != nullptr) {
-        for (int d = lane; d < D; d += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row + (long long)d * A.q_ld));
-      }
+      if (ev == 1 && pf_row != nullptr) tc3_prefetch_rows(pf_row, A.q_ld, D);
       mbar_wait_a(mbar_a, phase);
       phase ^= 1u;
       tc_fence_after();
