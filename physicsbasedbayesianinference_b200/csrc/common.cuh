@@ -27,6 +27,14 @@ struct Ar<float> {
   static __device__ __forceinline__ float divm(float x, float m, float inv_m) { return x * inv_m; }
   static __device__ __forceinline__ float exp_(float x) { return expf(x); }
   static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+  // 1 / m as one MUFU.RCP (<= 1 ulp, exact for powers of two such as the reference's unit masses): the IEEE
+  // divide carries a slow-path branch, and a branch right after the mass load pins every later instruction
+  // (the whole momentum draw) behind that load
+  static __device__ __forceinline__ float rcp_(float x) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+  }
 };
 
 template <>
@@ -37,6 +45,7 @@ struct Ar<double> {
   static __device__ __forceinline__ double divm(double x, double m, double) { return x / m; }
   static __device__ __forceinline__ double exp_(double x) { return exp(x); }
   static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+  static __device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
 };
 
 // ---------------------------------------------------------------------------
@@ -231,10 +240,11 @@ __device__ __forceinline__ double momentum_std<double>(double m, double kB, doub
   return sqrt(__dmul_rn(__dmul_rn(m, kB), temp));
 }
 // float32 mode: sqrt(m) * sqrt(kB T), the scalar factor pscale = sqrt(kB T) formed in double on the
-// host; 2 ulp (float) from the reference expression, no double-precision work per particle.
+// host; 3 ulp (float) from the reference expression, no double-precision work per particle and no
+// branch (sqrtf's slow path) between the mass load and the momentum draw.
 template <>
 __device__ __forceinline__ float momentum_std<float>(float m, double, double, double pscale) {
-  return sqrtf(m) * (float)pscale;
+  return sqrt_approx(m) * (float)pscale;
 }
 
 // Metropolis rule of src/HMC.py:168-173: reject iff u > min(1, exp(oldH - newH)).

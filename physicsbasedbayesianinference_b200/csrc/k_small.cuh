@@ -133,10 +133,10 @@ struct CoinPot {  // EHMC_FAMILY_COIN_TOSS: U = -sum k ln q + (n - k) ln(1 - q)
 // momentum draw: p = z * pstd, z fed or from Philox
 // ---------------------------------------------------------------------------
 template <typename T, int DT>
-__device__ __forceinline__ void draw_momentum(const IterArgs<T>& A, long long i, T pstd, T (&p)[DT]) {
+__device__ __forceinline__ void draw_momentum(const IterArgs<T>& A, int Dn, long long i, T pstd, T (&p)[DT]) {
   if (A.z != nullptr) {
 #pragma unroll
-    for (int d = 0; d < DT; ++d) p[d] = d < A.D ? Ar<T>::mul(A.z[d * A.z_ld + i], pstd) : T(0);
+    for (int d = 0; d < DT; ++d) p[d] = d < Dn ? Ar<T>::mul(A.z[d * A.z_ld + i], pstd) : T(0);
   } else {
     const PhiloxKey K(A.seed, A.iter);
     constexpr int NB = NormalBlock<T>::N;
@@ -147,7 +147,7 @@ __device__ __forceinline__ void draw_momentum(const IterArgs<T>& A, long long i,
 #pragma unroll
       for (int t = 0; t < NB; ++t) {
         const int d = b * NB + t;
-        if (d < DT) p[d] = d < A.D ? Ar<T>::mul(zz[t], pstd) : T(0);
+        if (d < DT) p[d] = d < Dn ? Ar<T>::mul(zz[t], pstd) : T(0);
       }
     }
   }
@@ -162,7 +162,7 @@ template <typename T, int DT, class Pot, int INTEG>
 __device__ __forceinline__ T integrate_regs(const Pot& pot, T (&q)[DT], T (&p)[DT], T m, T h, T h2, int L,
                                             bool wantE, T* U0) {
   typedef Ar<T> R;
-  const T inv_m = T(1) / m;
+  const T inv_m = R::rcp_(m);
   if constexpr (sizeof(T) == 4 && INTEG == INTEG_LEAPFROG && HasPacked<Pot>::value) {
     // float32, packed: the kick-drift-kick recurrence below on pairs of dimensions -- FFMA2 / FMUL2 do two
     // lanes of work per issue slot and this loop is issue bound (ncu: 78 % issue active, FMA pipe 53 %)
@@ -332,10 +332,13 @@ __device__ __forceinline__ void block_partials(double* out_row, int D, const dou
 // thread (in shared memory) and reduced across the block ONCE per launch (a per-particle block reduction of 23
 // doubles cost 3x the trajectory itself at config 5).
 // ---------------------------------------------------------------------------
-template <typename T, int DT, class Pot, int INTEG, bool HMC>
-__global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, const Pot pot) {
-  extern __shared__ double k1_smem[];
-  const IterArgs<T> A = resolve_dynamic(Ain);
+// EXACT: A.D == DT (no padded dimensions): the per-dimension bounds tests fold away.  With them the ten loads of
+// config 5 cost 140 instructions (predicated address arithmetic, selects against zero) and -- worse -- the selects
+// consumed the loaded values at once, so every warp waited for HBM BEFORE its ~300 instructions of Philox work
+// instead of behind them (profiles/r01_k1_dbg_probe.txt, r01_ncu_full_k1l4_before.txt).
+template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT>
+__device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& pot, double* k1_smem) {
+  const int Dn = EXACT ? DT : A.D;
   constexpr int NA = 2 * DT + 3;
   const bool want_stats = HMC && A.partials != nullptr;
   double* sacc = k1_smem + threadIdx.x;          // [NA][K1_THREADS], this thread's column
@@ -354,19 +357,23 @@ __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, con
     T q[DT], p[DT];
     const T m = A.mass[ic];
 #pragma unroll
-    for (int d = 0; d < DT; ++d) q[d] = d < A.D ? A.q[d * A.q_ld + ic] : T(0);
+    for (int d = 0; d < DT; ++d) q[d] = d < Dn ? A.q[d * A.q_ld + ic] : T(0);
 
     T pstd = T(0);
     if (HMC) {
+      // the unit normals first: ~300 instructions that depend on nothing in flight; the mass is first touched
+      // after them (z * 1 is exact, so p = z * pstd below is the product the one-step form gave)
+      draw_momentum<T, DT>(A, Dn, ic, T(1), p);
       pstd = momentum_std<T>(m, A.kB, A.temp, A.pscale);
-      draw_momentum<T, DT>(A, ic, pstd, p);
+#pragma unroll
+      for (int d = 0; d < DT; ++d) p[d] = Ar<T>::mul(p[d], pstd);
     } else {
 #pragma unroll
-      for (int d = 0; d < DT; ++d) p[d] = d < A.D ? A.p[d * A.p_ld + ic] : T(0);
+      for (int d = 0; d < DT; ++d) p[d] = d < Dn ? A.p[d * A.p_ld + ic] : T(0);
     }
 
     T K0 = T(0);
-    const T inv_m = T(1) / m;
+    const T inv_m = Ar<T>::rcp_(m);
     if (HMC) K0 = kinetic<T, DT>(p, m, inv_m);
     T U0;
     const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, A.h, A.h2, A.L, HMC, &U0);
@@ -375,7 +382,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, con
       if (active) {
 #pragma unroll
         for (int d = 0; d < DT; ++d)
-          if (d < A.D) {
+          if (d < Dn) {
             A.q[d * A.q_ld + i] = q[d];
             A.p[d * A.p_ld + i] = p[d];
           }
@@ -397,20 +404,20 @@ __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, con
       if (!rej) {
 #pragma unroll
         for (int d = 0; d < DT; ++d)
-          if (d < A.D) A.q[d * A.q_ld + i] = q[d];  // HMC.py:175 (rejected: q in HBM is still oldQ)
+          if (d < Dn) A.q[d * A.q_ld + i] = q[d];  // HMC.py:175 (rejected: q in HBM is still oldQ)
       }
       if (A.p != nullptr) {
         if (rej) {
           if (A.flags & FLAG_BUGCOMPAT) {
 #pragma unroll
-            for (int d = 0; d < DT; ++d) p[d] = d < A.D ? A.q[d * A.q_ld + i] : T(0);  // HMC.py:176 (sic)
+            for (int d = 0; d < DT; ++d) p[d] = d < Dn ? A.q[d * A.q_ld + i] : T(0);  // HMC.py:176 (sic)
           } else {
-            draw_momentum<T, DT>(A, i, pstd, p);  // oldP
+            draw_momentum<T, DT>(A, Dn, i, pstd, p);  // oldP
           }
         }
 #pragma unroll
         for (int d = 0; d < DT; ++d)
-          if (d < A.D) A.p[d * A.p_ld + i] = p[d];  // un-flipped, HMC.py:164,179
+          if (d < Dn) A.p[d * A.p_ld + i] = p[d];  // un-flipped, HMC.py:164,179
       }
       if (A.accept != nullptr) A.accept[i] = rej ? 0 : 1;
     }
@@ -419,7 +426,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, con
       // kept state for the statistics
       if (rej) {
 #pragma unroll
-        for (int d = 0; d < DT; ++d) q[d] = d < A.D ? A.q[d * A.q_ld + i] : T(0);
+        for (int d = 0; d < DT; ++d) q[d] = d < Dn ? A.q[d * A.q_ld + i] : T(0);
       }
       sacc[0 * K1_THREADS] += rej ? 0.0 : 1.0;
       sacc[1 * K1_THREADS] += (double)accp;
@@ -433,7 +440,17 @@ __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, con
     }
   }
   if (want_stats)
-    block_partials<K1_THREADS, DT>(A.partials + (size_t)blockIdx.x * (2 * A.D + 3), A.D, k1_smem, sred);
+    block_partials<K1_THREADS, DT>(A.partials + (size_t)blockIdx.x * (2 * Dn + 3), Dn, k1_smem, sred);
+}
+
+template <typename T, int DT, class Pot, int INTEG, bool HMC>
+__global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, const Pot pot) {
+  extern __shared__ double k1_smem[];
+  const IterArgs<T> A = resolve_dynamic(Ain);
+  if (A.D == DT)
+    k_small_body<T, DT, Pot, INTEG, HMC, true>(A, pot, k1_smem);
+  else
+    k_small_body<T, DT, Pot, INTEG, HMC, false>(A, pot, k1_smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -449,14 +466,14 @@ __global__ void __launch_bounds__(K1_THREADS) k_small_run(const IterArgs<T> Ain,
   for (long long i = (long long)blockIdx.x * K1_THREADS + threadIdx.x; i < Ain.P; i += stride) {
     IterArgs<T> A = Ain;
     T q[DT], qold[DT], p[DT], p0[DT];
-    const T m = A.mass[i], inv_m = T(1) / m;
+    const T m = A.mass[i], inv_m = Ar<T>::rcp_(m);
     const T pstd = momentum_std<T>(m, A.kB, A.temp, A.pscale);
 #pragma unroll
     for (int d = 0; d < DT; ++d) q[d] = d < A.D ? A.q[d * A.q_ld + i] : T(0);
     int nacc = 0;
     for (int it = 0; it < R.nIter; ++it) {
       A.iter = Ain.iter + (u64)it;
-      draw_momentum<T, DT>(A, i, pstd, p);
+      draw_momentum<T, DT>(A, A.D, i, pstd, p);
 #pragma unroll
       for (int d = 0; d < DT; ++d) {
         qold[d] = q[d];

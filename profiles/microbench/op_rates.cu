@@ -47,6 +47,13 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, float s
       if (OP == 18) asm volatile("rsqrt.approx.f32 %0, %0;" : "+f"(a[i]));                         // MUFU.RSQ
       if (OP == 19) { asm volatile("rsqrt.approx.f32 %0, %0;" : "+f"(a[i])); asm volatile("fma.rn.f32x2 %0, %0, %1, %0;" : "+l"(w[i]) : "l"(wseed)); asm volatile("fma.rn.f32x2 %0, %0, %1, %0;" : "+l"(w[(i + 4) & 7]) : "l"(wseed)); }
       if (OP == 15) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(seed));
+      if (OP == 20) asm volatile("{.reg .b32 lo, hi; mov.b64 {lo, hi}, %0; xor.b32 lo, lo, hi; mul.wide.u32 %0, lo, 0xD2511F53;}" : "+l"(w[i]));  // IMAD.WIDE.U32 (+ LOP3)
+      if (OP == 21) asm volatile("mul.wide.u32 %0, %1, 0xD2511F53;" : "=l"(w[i]) : "r"(u[i]));  // IMAD.WIDE.U32 independent
+      if (OP == 22) asm volatile("mad.lo.u32 %0, %0, %1, %0;" : "+r"(u[i]) : "r"(0xD2511F53u));  // IMAD
+      if (OP == 23) asm volatile("lg2.approx.f32 %0, %0;" : "+f"(a[i]));
+      if (OP == 24) asm volatile("sin.approx.f32 %0, %0;" : "+f"(a[i]));
+      if (OP == 25) asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(a[i]) : "r"(u[i] + it));  // I2FP (+ IADD)
+      if (OP == 26) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(u[i]) : "r"(0xD2511F53u));  // IMAD.HI.U32
     }
   }
   long long t1 = clock64();
@@ -98,5 +105,12 @@ int main() {
   run<8>("PRMT", out, cyc);
   run<9>("SHF", out, cyc);
   run<10>("IADD", out, cyc);
+  run<20>("LOP3 + IMAD.WIDE.U32 (per pair)", out, cyc);
+  run<21>("IMAD.WIDE.U32 independent", out, cyc);
+  run<22>("IMAD (mad.lo.u32)", out, cyc);
+  run<26>("IMAD.HI.U32", out, cyc);
+  run<23>("MUFU.LG2", out, cyc);
+  run<24>("MUFU.SIN", out, cyc);
+  run<25>("I2FP.F32.U32 (+ IADD)", out, cyc);
   return 0;
 }
