@@ -63,22 +63,22 @@ static int launch_small_pot(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, i
   // statistics: per-thread accumulators [2DT+3][128] + per-warp rows [4][2DT+3] (doubles)
   const size_t sm = A.partials != nullptr ? sizeof(double) * (K1_THREADS + K1_THREADS / 32) * (2 * DT + 3) : 0;
   unsigned grid = 1;
+  auto go = [&](auto kernel) -> int {
+    TRY(small_grid(c, kernel, sm, A.P, &grid));
+    kernel<<<grid, K1_THREADS, sm, st>>>(A, pot);
+    return EHMC_OK;
+  };
+  const bool exact = A.D == DT;  // no padded dimensions: the kernel without the per-dimension bounds tests
   if (hmc) {
-    if (integ == INTEG_LEAPFROG) {
-      TRY(small_grid(c, k_small<T, DT, Pot, INTEG_LEAPFROG, true>, sm, A.P, &grid));
-      k_small<T, DT, Pot, INTEG_LEAPFROG, true><<<grid, K1_THREADS, sm, st>>>(A, pot);
-    } else {
-      TRY(small_grid(c, k_small<T, DT, Pot, INTEG_STORMER, true>, sm, A.P, &grid));
-      k_small<T, DT, Pot, INTEG_STORMER, true><<<grid, K1_THREADS, sm, st>>>(A, pot);
-    }
+    if (integ == INTEG_LEAPFROG)
+      TRY(exact ? go(k_small<T, DT, Pot, INTEG_LEAPFROG, true, true>) : go(k_small<T, DT, Pot, INTEG_LEAPFROG, true, false>));
+    else
+      TRY(exact ? go(k_small<T, DT, Pot, INTEG_STORMER, true, true>) : go(k_small<T, DT, Pot, INTEG_STORMER, true, false>));
   } else {
-    if (integ == INTEG_LEAPFROG) {
-      TRY(small_grid(c, k_small<T, DT, Pot, INTEG_LEAPFROG, false>, sm, A.P, &grid));
-      k_small<T, DT, Pot, INTEG_LEAPFROG, false><<<grid, K1_THREADS, sm, st>>>(A, pot);
-    } else {
-      TRY(small_grid(c, k_small<T, DT, Pot, INTEG_STORMER, false>, sm, A.P, &grid));
-      k_small<T, DT, Pot, INTEG_STORMER, false><<<grid, K1_THREADS, sm, st>>>(A, pot);
-    }
+    if (integ == INTEG_LEAPFROG)
+      TRY(exact ? go(k_small<T, DT, Pot, INTEG_LEAPFROG, false, true>) : go(k_small<T, DT, Pot, INTEG_LEAPFROG, false, false>));
+    else
+      TRY(exact ? go(k_small<T, DT, Pot, INTEG_STORMER, false, true>) : go(k_small<T, DT, Pot, INTEG_STORMER, false, false>));
   }
   c->launches++;
   c->last_rows = grid;  // statistics partials: one row per CTA actually launched

@@ -443,14 +443,14 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
     block_partials<K1_THREADS, DT>(A.partials + (size_t)blockIdx.x * (2 * Dn + 3), Dn, k1_smem, sred);
 }
 
-template <typename T, int DT, class Pot, int INTEG, bool HMC>
+// Two kernels (picked on the host by D == DT) rather than one with both bodies: a kernel gets the register
+// count of its hungrier body.  (Capping the float32 HMC kernel at 64 registers for 8 CTAs per SM instead of 7
+// measured 7 % slower at config 5: the Philox rounds of the three blocks no longer interleave.)
+template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT>
 __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, const Pot pot) {
   extern __shared__ double k1_smem[];
   const IterArgs<T> A = resolve_dynamic(Ain);
-  if (A.D == DT)
-    k_small_body<T, DT, Pot, INTEG, HMC, true>(A, pot, k1_smem);
-  else
-    k_small_body<T, DT, Pot, INTEG, HMC, false>(A, pot, k1_smem);
+  k_small_body<T, DT, Pot, INTEG, HMC, EXACT>(A, pot, k1_smem);
 }
 
 // ---------------------------------------------------------------------------
