@@ -54,6 +54,10 @@ template <class Pot, typename = void>
 struct HasPacked : std::false_type {};
 template <class Pot>
 struct HasPacked<Pot, std::void_t<decltype(Pot::kPacked)>> : std::true_type {};
+template <class Pot, typename = void>
+struct HasFusedKick : std::false_type {};
+template <class Pot>
+struct HasFusedKick<Pot, std::void_t<decltype(Pot::kFusedKick)>> : std::true_type {};
 
 template <typename T, int DT>
 struct DenseSmallPot {  // U = 0.5 x^T Lambda x, x = q - mu;  grad = Lambda x
@@ -108,6 +112,26 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL)
     const float s2 = fmaf(q1, q1, pk_lo(S) + pk_hi(S));
     const float hs = 0.5f * ev * s2;
     G[0] = pk2(v * (float)inv_s2 - hs + (float)half_dm1, ev * q1);
+    return 0.5f * v * v * (float)inv_s2 + hs + (float)half_dm1 * v;
+  }
+  // Gradient and kick in one: V += c * grad U(Q).  For the pairs above the first, grad = e^{-v} q, so the kick is
+  // ONE FFMA2 with the scalar c e^{-v} instead of FMUL2 (gradient) + FFMA2 (kick): the trajectory loop is bound by
+  // the FMA pipe (ncu: math_pipe_throttle is its top stall) and this is 4 of its 18 packed instructions at D = 10.
+  static constexpr bool kFusedKick = true;
+  __device__ __forceinline__ float kick2(const f32x2 (&Q)[(DT + 1) / 2], f32x2 (&V)[(DT + 1) / 2], float c) const {
+    const float v = pk_lo(Q[0]), q1 = pk_hi(Q[0]);
+    const float ev = expf(-v);
+    const float cev = c * ev;
+    const f32x2 cev2 = pk2(cev, cev);
+    f32x2 S = 0ull;
+#pragma unroll
+    for (int i = 1; i < (DT + 1) / 2; ++i) {
+      S = fma2(Q[i], Q[i], S);
+      V[i] = fma2(Q[i], cev2, V[i]);
+    }
+    const float s2 = fmaf(q1, q1, pk_lo(S) + pk_hi(S));
+    const float hs = 0.5f * ev * s2;
+    V[0] = fma2(pk2(v * (float)inv_s2 - hs + (float)half_dm1, ev * q1), pk2(c, c), V[0]);
     return 0.5f * v * v * (float)inv_s2 + hs + (float)half_dm1 * v;
   }
 };
@@ -173,22 +197,34 @@ __device__ __forceinline__ T integrate_regs(const Pot& pot, T (&q)[DT], T (&p)[D
       Q[i] = pk2(q[2 * i], 2 * i + 1 < DT ? q[2 * i + 1] : 0.f);
       V[i] = pk2(p[2 * i] * inv_m, 2 * i + 1 < DT ? p[2 * i + 1] * inv_m : 0.f);
     }
-    *U0 = pot.grad2(Q, G, wantE);
-    T Uend = *U0;
     const float hm = h * inv_m, hmh = 0.5f * hm;
     const f32x2 h2p = pk2(h, h), nhm = pk2(-hm, -hm), nhmh = pk2(-hmh, -hmh);
-    if (L > 0) {
+    T Uend;
+    if constexpr (HasFusedKick<Pot>::value) {
+      // L = 0: c = 0 leaves V untouched (V + 0 * g; a non-finite gradient there is a non-finite U0 as well)
+      *U0 = L > 0 ? pot.kick2(Q, V, -hmh) : pot.grad2(Q, G, wantE);
+      Uend = *U0;
+      for (int j = 0; j < L; ++j) {
 #pragma unroll
-      for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], nhmh, V[i]);
-    }
-    for (int j = 0; j < L; ++j) {
+        for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
+        Uend = pot.kick2(Q, V, j == L - 1 ? -hmh : -hm);
+      }
+    } else {
+      *U0 = pot.grad2(Q, G, wantE);
+      Uend = *U0;
+      if (L > 0) {
 #pragma unroll
-      for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
-      const bool last = j == L - 1;
-      Uend = pot.grad2(Q, G, wantE && last);
-      const f32x2 ck = last ? nhmh : nhm;
+        for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], nhmh, V[i]);
+      }
+      for (int j = 0; j < L; ++j) {
 #pragma unroll
-      for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], ck, V[i]);
+        for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
+        const bool last = j == L - 1;
+        Uend = pot.grad2(Q, G, wantE && last);
+        const f32x2 ck = last ? nhmh : nhm;
+#pragma unroll
+        for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], ck, V[i]);
+      }
     }
 #pragma unroll
     for (int i = 0; i < NP2; ++i) {
