@@ -111,7 +111,7 @@ def make_oracle_potential(O, name, D):
 # ---------------------------------------------------------------------------
 class ClockSampler:
     """Samples SM clock, power and throttle reasons of one GPU through NVML (nvidia_ml_py) every
-    20 ms in a thread while the timed region runs; falls back to one nvidia-smi query."""
+    few ms in a thread while the timed region runs; falls back to one nvidia-smi query."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -148,7 +148,7 @@ class ClockSampler:
                 self.samples.append((sm, pw, rs))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def stop(self):
         if self.nvml is None:
@@ -169,7 +169,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
                 "sm_max_mhz": float(mx) if mx else None,
                 "power_w_max": max(x[1] for x in self.samples) if self.samples else None,
-                "samples": len(sm), "reasons": sorted(reasons), "source": "nvml, 20 ms period, during the timed region"}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvml, 5 ms sleep between queries, during the timed region"}
 
     def _smi_once(self):
         try:
