@@ -169,6 +169,23 @@ struct NormalBlock<double> {
   }
 };
 
+// Zero unless `on`: a predicated load INTO a zeroed register.  Written as `on ? *p : 0` the compiler loads into a
+// temporary and selects, and the select is a consumer of the load: with ten of them at the top of k_small every
+// warp waited for HBM before it started its RNG work (and ran out of predicate registers: 14 instructions per
+// element).  This form is setp + mov + @p ld and the register has no reader until the state is used.
+__device__ __forceinline__ float ld_if(const float* p, bool on) {
+  float v;
+  asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n mov.f32 %0, 0f00000000;\n @q ld.global.f32 %0, [%1];\n}"
+               : "=f"(v) : "l"(p), "r"((int)on));
+  return v;
+}
+__device__ __forceinline__ double ld_if(const double* p, bool on) {
+  double v;
+  asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n mov.f64 %0, 0d0000000000000000;\n @q ld.global.f64 %0, [%1];\n}"
+               : "=d"(v) : "l"(p), "r"((int)on));
+  return v;
+}
+
 // ---------------------------------------------------------------------------
 // Kernel argument block shared by every fused trajectory kernel.
 // (D,P) arrays: element [d, i] at base[d * ld + i].

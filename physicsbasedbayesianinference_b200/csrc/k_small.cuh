@@ -393,7 +393,7 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
     T q[DT], p[DT];
     const T m = A.mass[ic];
 #pragma unroll
-    for (int d = 0; d < DT; ++d) q[d] = d < Dn ? A.q[d * A.q_ld + ic] : T(0);
+    for (int d = 0; d < DT; ++d) q[d] = EXACT ? A.q[d * A.q_ld + ic] : ld_if(A.q + (d * A.q_ld + ic), d < Dn);
 
     T pstd = T(0);
     if (HMC) {
@@ -405,7 +405,7 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
       for (int d = 0; d < DT; ++d) p[d] = Ar<T>::mul(p[d], pstd);
     } else {
 #pragma unroll
-      for (int d = 0; d < DT; ++d) p[d] = d < Dn ? A.p[d * A.p_ld + ic] : T(0);
+      for (int d = 0; d < DT; ++d) p[d] = EXACT ? A.p[d * A.p_ld + ic] : ld_if(A.p + (d * A.p_ld + ic), d < Dn);
     }
 
     T K0 = T(0);
