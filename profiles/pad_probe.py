@@ -1,3 +1,7 @@
+"""Small-D kernel at dimensions padded up to the instantiated width (D = 9 -> 10, 3 -> 4) next to the exact widths:
+funnel, P = 2^22, float32, Leapfrog.integrate and HMC.step with in-kernel Philox.  Run from the repository root:
+    python profiles/pad_probe.py
+"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
