@@ -92,7 +92,11 @@ typedef enum {
    * (src/potential.py:30-53) for eps = 0.  params: bodyMass[B].  scalars: {G, eps}. */
   EHMC_FAMILY_NBODY = 4,
   /* Bayesian logistic regression: U = sum_n softplus(x_n.q) - y_n x_n.q + 0.5 |q|^2 / s^2.
-   * params: X[N,D] (row-major), y[N].  scalars: {s}. */
+   * params: X[N,D] (row-major), y[N].  scalars: {s, precision?}.  precision selects the gradient kernel:
+   * 0 (default) CUDA cores, exact fp32 / fp64;  2 tensor cores at float32 accuracy (tcgen05 GEMM chain, every
+   * operand a 2-term fp16 split, 3 MMA passes per GEMM; float32 state);  3 auto = 2 when the state is float32 and
+   * the split represents X to 2^-20 per column, else 0;  1 tensor cores with bf16-rounded operands (fast, 5e-3
+   * gradient accuracy: outside the 1e-5 trajectory tolerance, opt-in only). */
   EHMC_FAMILY_LOGISTIC = 5,
   /* Independent coin biases q_d in (0, 1) with a flat prior -- the reference's own NumPyro sample
    * (samples/NumpyroExamples/CoinToss/CoinToss.py:6-25):
@@ -159,11 +163,18 @@ EHMC_API int ehmc_ctx_create(int device, ehmc_ctx** out);
 EHMC_API int ehmc_ctx_destroy(ehmc_ctx* ctx);
 /* Number of kernels of THIS library launched through ctx since creation. */
 EHMC_API int ehmc_ctx_launch_count(const ehmc_ctx* ctx, uint64_t* out);
+/* Rows of ehmc_leapfrog / ehmc_stormer_verlet calls on the float32 tensor-core dense kernel whose position left
+ * the fp16 operand range of the row's scale (a divergent trajectory: |q| grew more than 256x past
+ * max(|q0|, h L |v0|)) since the last reset.  Those rows hold saturated, finite garbage; re-run the call with
+ * option "dense_path" = 1 (exact CUDA-core kernel).  ehmc_hmc_iter needs no such check: it rejects those rows.
+ * Synchronises the device. */
+EHMC_API int ehmc_ctx_overflow_count(ehmc_ctx* ctx, uint64_t* out, int reset);
 /* out[0]=SM count, out[1]=SM clock MHz (max), out[2]=total HBM bytes, out[3]=L2 bytes. */
 EHMC_API int ehmc_ctx_device_info(const ehmc_ctx* ctx, double out[4]);
 /* Tuning / diagnostic knobs:
- *   "dense_path"      0 auto (float32 dense Gaussian on the 3xFP16 tensor-core kernel), 1 CUDA cores (exact
- *                     fp32 FMA), 2 / 3 the 3xTF32 tensor-core kernels (one tile / two tiles), 4 force 3xFP16
+ *   "dense_path"      0 auto (float32 dense Gaussian on the 3xFP16 tensor-core kernel unless the fp16 split of
+ *                     Lambda would lose accuracy: ill-conditioned / wide-range matrices run on CUDA cores),
+ *                     1 CUDA cores (exact fp32 FMA), 4 force 3xFP16
  *   "dense_occupancy" 1|2: CTAs/SM variant of the float32 CUDA-core dense kernel
  *   "small_waves"     resident waves of CTAs of the persistent small-D kernel (default 8)
  *   "nbody_ti"        bodies per thread of the N-body kernel (0 auto, 4, 8)

@@ -32,6 +32,7 @@ FLAG_REUSE_ENDPOINT = 4
 # every symbol include/ehmc.h declares (tests/test_abi.py checks the export list)
 SYMBOLS = (
     "ehmc_version", "ehmc_last_error", "ehmc_ctx_create", "ehmc_ctx_destroy", "ehmc_ctx_launch_count",
+    "ehmc_ctx_overflow_count",
     "ehmc_ctx_device_info", "ehmc_ctx_set_option", "ehmc_measure_fp32_peak", "ehmc_potential_create", "ehmc_potential_destroy",
     "ehmc_potential_eval", "ehmc_set_position", "ehmc_set_momentum", "ehmc_philox_fill", "ehmc_leapfrog",
     "ehmc_stormer_verlet", "ehmc_integrate_nbody_mode", "ehmc_hmc_iter", "ehmc_hmc_run", "ehmc_adapt_step",
@@ -98,6 +99,7 @@ def load():
             "ehmc_ctx_create": [ci, ctypes.POINTER(vp)],
             "ehmc_ctx_destroy": [vp],
             "ehmc_ctx_launch_count": [vp, ctypes.POINTER(u64)],
+            "ehmc_ctx_overflow_count": [vp, ctypes.POINTER(u64), ci],
             "ehmc_ctx_device_info": [vp, ctypes.POINTER(cd)],
             "ehmc_ctx_set_option": [vp, ctypes.c_char_p, cd],
             "ehmc_measure_fp32_peak": [vp, cd, ctypes.POINTER(cd)],
@@ -219,6 +221,12 @@ class Context:
     def launch_count(self):
         n = ctypes.c_uint64()
         check(self.lib.ehmc_ctx_launch_count(self.handle, ctypes.byref(n)))
+        return n.value
+
+    def overflow_count(self, reset=True):
+        """Rows of integrate() calls on the tensor-core dense kernel that left the fp16 operand range (synchronises)."""
+        n = ctypes.c_uint64()
+        check(self.lib.ehmc_ctx_overflow_count(self.handle, ctypes.byref(n), 1 if reset else 0))
         return n.value
 
     def device_info(self):

@@ -157,6 +157,7 @@ extern "C" int ehmc_ctx_destroy(ehmc_ctx* c) {
   c->stage_stats.release();
   c->pstats.release();
   c->tc_prof_buf.release();
+  c->overflow.release();
   for (int k = 0; k < 2; ++k) {
     c->ep_grad[k].release();
     c->ep_energy[k].release();
@@ -173,6 +174,18 @@ extern "C" int ehmc_ctx_destroy(ehmc_ctx* c) {
 extern "C" int ehmc_ctx_launch_count(const ehmc_ctx* c, uint64_t* out) {
   if (!c || !out) return fail(EHMC_ERR_INVALID, "ehmc_ctx_launch_count: NULL argument");
   *out = c->launches;
+  return EHMC_OK;
+}
+
+extern "C" int ehmc_ctx_overflow_count(ehmc_ctx* c, uint64_t* out, int reset) {
+  if (!c || !out) return fail(EHMC_ERR_INVALID, "ehmc_ctx_overflow_count: NULL argument");
+  *out = 0;
+  if (c->overflow.ptr == nullptr) return EHMC_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  unsigned v = 0;
+  CUDA_TRY(cudaMemcpy(&v, c->overflow.ptr, sizeof(v), cudaMemcpyDeviceToHost));  // synchronises the device
+  if (reset && v) CUDA_TRY(cudaMemset(c->overflow.ptr, 0, sizeof(v)));
+  *out = v;
   return EHMC_OK;
 }
 
@@ -193,7 +206,8 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
     if (value != 1 && value != 2) return fail(EHMC_ERR_INVALID, "dense_occupancy must be 1 or 2");
     c->dense_occupancy = (int)value;
   } else if (!strcmp(name, "dense_path")) {
-    if (!(value >= 0 && value <= 4)) return fail(EHMC_ERR_INVALID, "dense_path must be 0..4");
+    if (value != 0 && value != 1 && value != 4)
+      return fail(EHMC_ERR_INVALID, "dense_path must be 0 (auto), 1 (CUDA cores) or 4 (force the 3xFP16 tensor-core kernel)");
     c->dense_path = (int)value;
   } else if (!strcmp(name, "tc_prof")) {
     c->tc_prof = (int)value;
@@ -386,7 +400,7 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       break;
     }
     case EHMC_FAMILY_LOGISTIC: {
-      if (nparams != 2 || nscalars < 1 || nscalars > 2) { rc = fail(EHMC_ERR_INVALID, "logistic: params = {X[N,D], y[N]}, scalars = {priorScale, useTensorCores?}"); break; }
+      if (nparams != 2 || nscalars < 1 || nscalars > 2) { rc = fail(EHMC_ERR_INVALID, "logistic: params = {X[N,D], y[N]}, scalars = {priorScale, precision?}"); break; }
       rc = fetch_param(params[0], "X", 2, &p->hp0, &v);
       if (rc) break;
       p->N = (int)v.shape[0];
@@ -398,8 +412,63 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       if (!(scalars[0] > 0)) { rc = fail(EHMC_ERR_INVALID, "logistic: priorScale must be > 0"); break; }
       rc = upload_bits(p->bits, p->hp0, &p->d0);
       if (rc == EHMC_OK) rc = upload_bits(p->bits, p->hp1, &p->d1);
-      p->use_tc = (nscalars == 2 && scalars[1] != 0.0) ? 1 : 0;
-      if (rc == EHMC_OK && p->use_tc) {
+      p->use_tc = nscalars == 2 ? (int)scalars[1] : 0;
+      if (p->use_tc < 0 || p->use_tc > 3) { rc = fail(EHMC_ERR_INVALID, "logistic: precision selector must be 0 (CUDA cores), 1 (bf16), 2 (fp16 split) or 3 (auto)"); break; }
+      if (p->use_tc == 3 && p->bits != 32) p->use_tc = 0;  // auto: float64 state runs the exact kernel
+      if (rc == EHMC_OK && p->use_tc >= 2) {
+        // float32-accurate tensor-core path (k_logistic_tcs): X * 2^a as fp16 (hi, lo) pairs, half-chunk ring entries
+        // [DP/8][64][8] fp16 + 64 floats (2^10 y in the hi entry).  Guard (auto only): one power-of-two scale serves
+        // the whole matrix, so a column whose entries sit more than ~2^10 below max |X| has its lo parts in fp16's
+        // subnormal range; if any column's worst split error exceeds 2^-20 of the column's own max, auto selects the
+        // exact CUDA-core kernel instead.
+        if (p->bits != 32) { rc = fail(EHMC_ERR_INVALID, "logistic: the tensor-core path needs float32 state"); break; }
+        const int D = p->D, N = p->N, DP = (D + 15) / 16 * 16, NB = 64, NC = (N + NB - 1) / NB;
+        double amax = 0.0;
+        for (size_t i = 0; i < (size_t)N * D; ++i) amax = std::max(amax, std::fabs((double)(float)p->hp0[i]));
+        int ex = 0;
+        if (amax > 0 && std::isfinite(amax)) std::frexp(amax, &ex);  // amax = f * 2^ex, f in [0.5, 1)
+        const int sh = std::max(-100, std::min(100, 8 - ex));
+        const double xscale = std::ldexp(1.0, sh);
+        const size_t eb = (size_t)DP * NB * 2 + NB * 4;
+        std::vector<unsigned char> buf(eb * 2 * NC, 0);
+        std::vector<double> colmax(D, 0.0), colerr(D, 0.0);
+        for (int c = 0; c < NC; ++c) {
+          // ring order: entry 2c = Xl, entry 2c + 1 = Xh followed by 2^10 y (the small products run first)
+          __half* xl = reinterpret_cast<__half*>(buf.data() + eb * (2 * c));
+          __half* xh = reinterpret_cast<__half*>(buf.data() + eb * (2 * c + 1));
+          float* ky = reinterpret_cast<float*>(buf.data() + eb * (2 * c + 1) + (size_t)DP * NB * 2);
+          for (int r = 0; r < NB; ++r) {
+            const int n = c * NB + r;
+            ky[r] = 1024.f * (n < N ? (float)p->hp1[n] : 0.5f);
+            if (n >= N) continue;
+            for (int d = 0; d < D; ++d) {
+              const float x = (float)((double)(float)p->hp0[(size_t)n * D + d] * xscale);
+              const __half hi = __float2half_rn(x);
+              const __half lo = __float2half_rn(x - __half2float(hi));
+              const size_t o = ((size_t)(d / 8) * NB + r) * 8 + (d % 8);
+              xh[o] = hi;
+              xl[o] = lo;
+              colmax[d] = std::max(colmax[d], (double)std::fabs(x));
+              colerr[d] = std::max(colerr[d], std::fabs((double)x - (double)__half2float(hi) - (double)__half2float(lo)));
+            }
+          }
+        }
+        bool ok = std::isfinite(amax);
+        for (int d = 0; d < D && ok; ++d) ok = colerr[d] <= colmax[d] * 9.5367431640625e-7;  // 2^-20
+        if (p->use_tc == 3 && !ok) {
+          p->use_tc = 0;
+        } else {
+          p->use_tc = 2;
+          if (cudaMalloc(&p->d6, buf.size()) != cudaSuccess) { rc = fail(EHMC_ERR_NOMEM, "cudaMalloc(%zu) failed", buf.size()); break; }
+          if (cudaMemcpy(p->d6, buf.data(), buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(EHMC_ERR_CUDA, "upload of the packed X failed"); break; }
+          p->lt_nc = NC;
+          p->lt_dp = DP;
+          p->lt_npad = NC * NB - N;
+          p->lt_chunk_bytes = (unsigned)eb;
+          p->lts_x_iscale = (float)std::ldexp(1.0, -sh);
+        }
+      }
+      if (rc == EHMC_OK && p->use_tc == 1) {
         if (p->bits != 32) { rc = fail(EHMC_ERR_INVALID, "logistic: the tensor-core path needs float32 state"); break; }
         // bf16 chunks of 64 data rows in the canonical UMMA layout [DP/8][64][8] + y[64] (float); LT_NB
         const int D = p->D, N = p->N, DP = (D + 15) / 16 * 16, NB = 64, NC = (N + NB - 1) / NB;
@@ -453,30 +522,6 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       for (int d = 0; d < D; ++d) mu[d] = p->hp1[d];
       rc = upload_bits(p->bits, Ls, &p->d0);
       if (rc == EHMC_OK) rc = upload_bits(p->bits, mu, &p->d1);
-      if (rc == EHMC_OK && p->bits == 32 && D <= 104) {
-        // 3xTF32 tensor-core operands: Lambda_hi = Lambda (the MMA truncates), Lambda_lo = Lambda - trunc(Lambda),
-        // canonical K-major no-swizzle UMMA layout [KP/4][NP][4] (B[n][k] = Lambda[n][k])
-        const int KP = (D + 7) / 8 * 8, NP = (KP + 15) / 16 * 16, NCH = NP / 16, K4 = KP / 4;
-        std::vector<double> bhi((size_t)K4 * NP * 4, 0.0), blo(bhi.size(), 0.0), mu2(KP, 0.0);
-        for (int n = 0; n < D; ++n)
-          for (int k = 0; k < D; ++k) {
-            const float x = (float)p->hp0[(size_t)n * D + k];
-            uint32_t b;
-            memcpy(&b, &x, 4);
-            b &= 0xFFFFE000u;  // what the tf32 MMA reads of x (low 13 mantissa bits ignored)
-            float hi;
-            memcpy(&hi, &b, 4);
-            const size_t o = ((size_t)(k / 4) * NP + n) * 4 + (k % 4);
-            bhi[o] = x;  // the full float32 pattern is the "hi" operand
-            blo[o] = (double)(x - hi);
-          }
-        for (int d = 0; d < D; ++d) mu2[d] = p->hp1[d];
-        rc = upload<float>(bhi, &p->d3);
-        if (rc == EHMC_OK) rc = upload<float>(blo, &p->d4);
-        if (rc == EHMC_OK) rc = upload<float>(mu2, &p->d5);
-        p->tc_nch = NCH;
-        p->tc_kp = KP;
-      }
       if (rc == EHMC_OK && p->bits == 32 && D <= 128) {
         // 3xFP16 tensor-core operands (k_dense_tc3): Lambda scaled by a power of two so that max |Lambda| lands in
         // [2^13, 2^14), hi = rn16, lo = rn16(remainder); canonical K-major no-swizzle layout [KP/8][NP][8].
@@ -488,7 +533,21 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
         const int sh = std::max(-100, std::min(100, 14 - ex));
         const double lscale = std::ldexp(1.0, sh);
         std::vector<__half> bhi((size_t)KCH * NP * 8, __float2half_rn(0.f)), blo(bhi.size(), __float2half_rn(0.f));
-        for (int n = 0; n < D; ++n)
+        // Guard of the split (auto path only; dense_path = 4 overrides).  fp16 has 5 exponent bits: entries more
+        // than ~2^27 below max |Lambda| lose bits (hi subnormal, lo flushed).  What that does to the gradient is
+        // measured in the units the target itself sets: x_k ~ Lambda_kk^-1/2 and (grad U)_n ~ Lambda_nn^1/2, so the
+        // relative gradient error of row n is rss_k( dLambda_nk / sqrt(Lambda_nn Lambda_kk) ).  The same argument on
+        // the x side (one power-of-two scale per particle row, 2^7 headroom) bounds the spread of the coordinate
+        // scales: sqrt(max Lambda_kk / min Lambda_kk) <= 2^10.  Otherwise the exact CUDA-core kernel runs.
+        double dmin = INFINITY, dmax = 0.0;
+        for (int d = 0; d < D; ++d) {
+          dmin = std::min(dmin, p->hp0[(size_t)d * D + d]);
+          dmax = std::max(dmax, p->hp0[(size_t)d * D + d]);
+        }
+        bool ok = dmin > 0 && std::isfinite(dmax) && dmax <= dmin * 1048576.0;
+        double worst = 0.0;
+        for (int n = 0; n < D; ++n) {
+          double rss = 0.0;
           for (int k = 0; k < D; ++k) {
             const float x = (float)((double)(float)p->hp0[(size_t)n * D + k] * lscale);
             const __half hi = __float2half_rn(x);
@@ -496,7 +555,14 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
             const size_t o = ((size_t)(k / 8) * NP + n) * 8 + (k % 8);
             bhi[o] = hi;
             blo[o] = lo;
+            if (ok) {
+              const double err = ((double)x - (double)__half2float(hi) - (double)__half2float(lo)) / lscale;
+              rss += err * err / (p->hp0[(size_t)n * D + n] * p->hp0[(size_t)k * D + k]);
+            }
           }
+          worst = std::max(worst, rss);
+        }
+        p->tc3_ok = (ok && std::sqrt(worst) <= 9.5367431640625e-7) ? 1 : 0;  // 2^-20
         std::vector<float> mu3(128, 0.f);
         for (int d = 0; d < D; ++d) mu3[d] = (float)p->hp1[d];
         rc = upload_raw(bhi.data(), sizeof(__half) * bhi.size(), &p->d7);
@@ -524,9 +590,6 @@ extern "C" int ehmc_potential_destroy(ehmc_potential* p) {
   if (p->d0) cudaFree(p->d0);
   if (p->d1) cudaFree(p->d1);
   if (p->d2) cudaFree(p->d2);
-  if (p->d3) cudaFree(p->d3);
-  if (p->d4) cudaFree(p->d4);
-  if (p->d5) cudaFree(p->d5);
   if (p->d6) cudaFree(p->d6);
   if (p->d7) cudaFree(p->d7);
   if (p->d8) cudaFree(p->d8);
@@ -541,25 +604,19 @@ static bool use_dense_tc(const ehmc_ctx* c, const ehmc_potential* p, int integ);
 static bool per_particle_stats(const ehmc_ctx* c, const ehmc_potential* p, int integ) {
   if (p->family == EHMC_FAMILY_NBODY || p->family == EHMC_FAMILY_LOGISTIC) return true;
   // the 3xFP16 tensor-core dense kernel reports per-particle scalars too
-  return use_dense_tc(c, p, integ) && (c->dense_path == 0 || c->dense_path == 4);
+  return use_dense_tc(c, p, integ);
 }
 
 // the float32 dense family runs on the tensor cores unless told otherwise
 static bool use_dense_tc(const ehmc_ctx* c, const ehmc_potential* p, int integ) {
   if (!(p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->bits == 32) || c->dense_path == 1) return false;
-  if (c->dense_path == 2 || c->dense_path == 3)  // the 3xTF32 kernels (D <= 104, leapfrog only)
-    return p->tc_nch >= 2 && integ == INTEG_LEAPFROG;
-  return p->tc3_c8 >= 3;                                                // 0 (auto), 4: 3xFP16 persistent kernel
+  (void)integ;
+  return p->tc3_c8 >= 3 && (p->tc3_ok || c->dense_path == 4);  // 0 (auto), 4 (forced): 3xFP16 persistent kernel
 }
 
 template <typename T>
 static long long traj_blocks(const ehmc_ctx* c, const ehmc_potential* p, long long P, int integ) {
   if (per_particle_stats(c, p, integ)) return P;
-  if (use_dense_tc(c, p, integ)) {
-    if (c->dense_path == 2) return 8 * ((P + 127) / 128);
-    if (c->dense_path == 3) return 8 * ((P + 255) / 256);
-    return 4 * ((P + 127) / 128);  // k_dense_tc3: one row per warp and 128-particle tile
-  }
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) {
     const int PT = dense_particles_per_cta<T>();
     return (P + PT - 1) / PT;
@@ -576,10 +633,10 @@ static int launch_traj(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& 
   if (p->family == EHMC_FAMILY_NBODY) return launch_nbody<T>(c, p, A, integ, hmc, st);
   if (p->family == EHMC_FAMILY_LOGISTIC) return launch_logistic<T>(c, p, A, integ, hmc, st, slot);
   if constexpr (sizeof(T) == 4) {
-    if (use_dense_tc(c, p, integ)) return launch_dense_tc(c, p, A, integ, hmc, st);
+    if (use_dense_tc(c, p, integ)) return launch_dense_tc3(c, p, A, integ, hmc, st);
   }
-  if (c->dense_path >= 2 && p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16 && sizeof(T) == 4)
-    return fail(EHMC_ERR_UNSUPPORTED, "dense_path >= 2 (tensor cores) but this call is not eligible (D = %d, integrator %d)", p->D, integ);
+  if (c->dense_path == 4 && p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16 && sizeof(T) == 4)
+    return fail(EHMC_ERR_UNSUPPORTED, "dense_path = 4 (tensor cores) but this call is not eligible (D = %d, integrator %d)", p->D, integ);
   if (p->family == EHMC_FAMILY_DENSE_GAUSSIAN && p->D > 16) return launch_dense<T>(c, p, A, integ, hmc, st);
   return launch_small<T>(c, p, A, integ, hmc, st);
 }
@@ -880,7 +937,7 @@ extern "C" int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor*
     // only kernels that resolve the block themselves; everything else would silently use the host values
     const bool small = pot->family == EHMC_FAMILY_DIAG_GAUSSIAN || pot->family == EHMC_FAMILY_FUNNEL ||
                        pot->family == EHMC_FAMILY_COIN_TOSS || (pot->family == EHMC_FAMILY_DENSE_GAUSSIAN && pot->D <= 16);
-    const bool tc3 = v.bits == 32 && use_dense_tc(ctx, pot, a->integrator) && (ctx->dense_path == 0 || ctx->dense_path >= 4);
+    const bool tc3 = v.bits == 32 && use_dense_tc(ctx, pot, a->integrator);
     if (v.q.host || !(small || tc3))
       return fail(EHMC_ERR_UNSUPPORTED, "%s: args.dynamic needs device tensors and a small-D or float32 dense (tensor-core) potential", fn);
   }

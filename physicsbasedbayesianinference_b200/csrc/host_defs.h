@@ -64,10 +64,11 @@ struct ehmc_ctx {
   int nbody_ti = 0;               // bodies per thread of k_nbody: 0 auto, 4 or 8
   int dense_occupancy = 2;        // CTAs/SM the float32 dense kernel is compiled for (1 or 2)
   int dense_path = 0;             // 0 auto (3xFP16 tensor cores when eligible), 1 CUDA cores (exact fp32 FMA),
-                                  // 2 / 3 the 3xTF32 kernels (one tile SS / two tiles TS), 4 force 3xFP16
+                                  // 4 force 3xFP16 (even when the split of Lambda loses accuracy)
   long long host_chunk_bytes = 32LL << 20;
   int tc_prof = 0;                // 1: record a clock64 trace of CTA 0 into tc_prof_buf (64 x int64)
   DevBuf tc_prof_buf;
+  DevBuf overflow;                // unsigned: integrate() rows that saturated the fp16 operand range of k_dense_tc3
   int tc_debug = 0;               // profiling knobs of the tensor-core kernels (see DenseTcArgs::dbg)
 };
 
@@ -81,11 +82,6 @@ struct ehmc_potential {
   void* d0 = nullptr;  // dense: packed Ls ; nbody: body masses ; logistic: X
   void* d1 = nullptr;  // dense: mu (padded) ; logistic: y
   void* d2 = nullptr;  // dense: plain Lambda row-major (eval kernel)
-  void* d3 = nullptr;  // dense float32 tensor-core path: Lambda_hi [KP/4][NP][4]
-  void* d4 = nullptr;  //                                 Lambda_lo
-  void* d5 = nullptr;  //                                 mu [NP]
-  int tc_nch = 0;      // 16-column chunks of the tensor-core path (0 = not eligible)
-  int tc_kp = 0;       // K padded to a multiple of 8
   int TN = 0;          // dense tile selection
   void* d6 = nullptr;  // logistic tensor-core path: packed bf16 X chunks + y
   int lt_nc = 0, lt_dp = 0, lt_npad = 0;
@@ -94,8 +90,11 @@ struct ehmc_potential {
   void* d8 = nullptr;  //                                       Lambda_lo
   void* d9 = nullptr;  //                                       mu [128]
   int tc3_c8 = 0;      // ceil(D / 8) (0 = not eligible)
+  int tc3_ok = 0;      // 1: the (hi, lo) fp16 split represents Lambda to float32 accuracy (no entry flushes)
   float tc3_inv_lscale = 1.f;
-  int use_tc = 0;      // logistic: 1 = bf16 tensor-core gradient (scalars[1])
+  int use_tc = 0;      // logistic (scalars[1]): 0 = CUDA cores (exact), 1 = bf16 tensor-core gradient,
+                       // 2 = float32-accurate tensor-core gradient (3-pass fp16 split)
+  float lts_x_iscale = 1.f;  // 1 / (power-of-two scale of the packed fp16 X)
   int B = 0;           // nbody: bodies per particle
   int N = 0;           // logistic: data rows
 };
@@ -115,8 +114,6 @@ int run_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int in
 // dense Gaussian, 16 < D <= 128
 template <typename T>
 int launch_dense(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);
-// float32 tensor-core variants (3xTF32: leapfrog only)
-int launch_dense_tc(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, int integ, bool hmc, cudaStream_t st);
 // float32 3xFP16 persistent tensor-core variant (leapfrog and Stormer-Verlet; the default)
 int launch_dense_tc3(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<float>& A, int integ, bool hmc, cudaStream_t st);
 template <typename T>
@@ -144,7 +141,10 @@ int launch_logistic(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, 
                     int slot);
 // bf16 tensor-core gradient (float32 state only)
 int logistic_grad_tc(ehmc_ctx* c, const ehmc_potential* p, const float* theta, long long t_ld, long long P, float* g,
-                     long long g_ld, float* e, cudaStream_t st);
+                     long long g_ld, float* e, double* e64, cudaStream_t st);
+// float32-accurate tensor-core gradient: 3-pass fp16 split (float32 state only)
+int logistic_grad_tcs(ehmc_ctx* c, const ehmc_potential* p, const float* theta, long long t_ld, long long P, float* g,
+                      long long g_ld, float* e, double* e64, cudaStream_t st);
 template <typename T>
 int eval_logistic(ehmc_ctx* c, const ehmc_potential* p, const T* q, long long q_ld, long long P, T* e, T* g,
                   long long g_ld, cudaStream_t st);

@@ -20,6 +20,11 @@ static int launch_tc3_c8(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<fl
   pa.inv_lscale = p->tc3_inv_lscale;
   pa.dbg = c->tc_debug;
   pa.prof = c->tc_prof ? static_cast<long long*>(c->tc_prof_buf.ptr) : nullptr;
+  if (!hmc && c->overflow.ptr == nullptr) {
+    TRY(c->overflow.ensure(sizeof(unsigned)));
+    CUDA_TRY(cudaMemsetAsync(c->overflow.ptr, 0, sizeof(unsigned), st));
+  }
+  pa.overflow = static_cast<unsigned*>(c->overflow.ptr);
   // persistent: one CTA per SM (the CTA takes the whole TMEM), tiles dealt in contiguous ranges
   const long long ntiles = (A.P + TC_M - 1) / TC_M;
   const unsigned grid = (unsigned)std::min<long long>(c->prop.multiProcessorCount, ntiles);

@@ -1,8 +1,8 @@
 // K2-TC3: dense-precision Gaussian trajectory kernel, tensor cores, fp16 split operands,
 // persistent CTAs.
 //
-// Same trajectory as k_dense_tc2.cuh (kick-drift-kick with G = X Lambda^T re-issued L+1 times on
-// on-chip state), with two changes that together halve the time per evaluation:
+// Kick-drift-kick trajectory with G = X Lambda^T re-issued L+1 times on on-chip state.  Two choices
+// (against the 3xTF32 kernels this replaced, 4.84 ms -> 2.6 ms per iteration at config 2):
 //
 //  * 3xFP16 split instead of 3xTF32.  tf32 and fp16 carry the same 11 significant bits, but
 //    tcgen05.mma kind::f16 consumes K = 16 per instruction where kind::tf32 consumes K = 8, at the
@@ -31,7 +31,8 @@
 
 #include <cuda_fp16.h>
 
-#include "k_dense_tc2.cuh"
+#include "k_dense.cuh"  // one_normal
+#include "tc_common.cuh"
 
 namespace ehmc {
 
@@ -61,128 +62,8 @@ struct DenseTc3Args {
   float inv_lscale;   // 1 / lscale (power of two)
   int dbg;            // 1: issue no MMAs (commit only); 2: skip the epilogue arithmetic
   long long* prof;    // optional clock64() trace of the second tile of CTA 0 / group 0 (ctx option "tc_prof")
+  unsigned* overflow; // counter of integrate() rows whose position saturated the fp16 operand range
 };
-
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
-  return (1u << 4)                      // D format F32; A, B format F16 (0); K-major A, B
-         | ((uint32_t)(N >> 3) << 17)   // N / 8
-         | ((uint32_t)(M >> 4) << 24);  // M / 16
-}
-
-// D[tmem] (+)= A[tmem] * B[smem]^T, fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// The evaluation loop is a serial chain per group (sync -> MMA issue -> wait -> epilogue); anything the
-// compiler re-materialises inside it (generic->shared address conversions with their S2UR CgaCtaId, descriptor
-// arithmetic, kick coefficients) lengthens the chain.  pin() makes a value opaque so that it is computed once and
-// kept in a register; the *_a helpers take precomputed 32-bit shared addresses.
-__device__ __forceinline__ void pin(uint32_t& x) { asm volatile("" : "+r"(x)); }
-__device__ __forceinline__ void pin(uint64_t& x) { asm volatile("" : "+l"(x)); }
-__device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
-__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar_addr), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&u)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld4(uint32_t (&u)[4]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]) : : "memory");
-}
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&u)[4]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(u[0]), "r"(u[1]),
-               "r"(u[2]), "r"(u[3])
-               : "memory");
-}
-
-// generic N-column wrappers (N = 16: G batch; N = 8 / 4: packed hi / lo of 16 / 8 dims)
-template <int N>
-__device__ __forceinline__ void tm_ld(uint32_t taddr, uint32_t* u) {
-  if constexpr (N == 16) tmem_ld16_issue(taddr, *reinterpret_cast<uint32_t(*)[16]>(u));
-  else if constexpr (N == 8) tmem_ld8_issue2(taddr, *reinterpret_cast<uint32_t(*)[8]>(u));
-  else tmem_ld4_issue(taddr, *reinterpret_cast<uint32_t(*)[4]>(u));
-}
-template <int N>
-__device__ __forceinline__ void tm_wait(uint32_t* u) {
-  if constexpr (N == 16) tmem_wait_ld16(*reinterpret_cast<uint32_t(*)[16]>(u));
-  else if constexpr (N == 8) tmem_wait_ld8(*reinterpret_cast<uint32_t(*)[8]>(u));
-  else tmem_wait_ld4(*reinterpret_cast<uint32_t(*)[4]>(u));
-}
-template <int N>
-__device__ __forceinline__ void tm_st(uint32_t taddr, const uint32_t* u) {
-  if constexpr (N == 16) tmem_st16(taddr, *reinterpret_cast<const uint32_t(*)[16]>(u));
-  else if constexpr (N == 8) tmem_st8(taddr, *reinterpret_cast<const uint32_t(*)[8]>(u));
-  else tmem_st4(taddr, *reinterpret_cast<const uint32_t(*)[4]>(u));
-}
-
-__device__ __forceinline__ float2 h2_unpack(uint32_t w) {
-  return __half22float2(*reinterpret_cast<const __half2*>(&w));
-}
-__device__ __forceinline__ uint32_t h2_pack(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-// sm_100 mixed-precision FADD / FFMA (SASS FHADD / FHFMA): an fp16 operand is widened inside the
-// instruction, so "float + half" and "float - half" cost one issue slot instead of two.
-__device__ __forceinline__ float add_h(unsigned short a, float c) {
-  float d;
-  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(a), "f"(c));
-  return d;
-}
-__device__ __forceinline__ float sub_h(float c, unsigned short a) {  // c - a
-  float d;
-  const unsigned short m1 = 0xBC00;  // -1.0
-  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(m1), "f"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned short h_lo(uint32_t w) { return (unsigned short)(w & 0xffffu); }
-__device__ __forceinline__ unsigned short h_hi(uint32_t w) { return (unsigned short)(w >> 16); }
-// (hi, lo) fp16 pair words of two consecutive dims: hi = rn16(x), lo = rn16(x - hi)
-__device__ __forceinline__ void split16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  hi = h2_pack(x0, x1);
-  lo = h2_pack(sub_h(x0, h_lo(hi)), sub_h(x1, h_hi(hi)));
-}
 
 // ---- software-pipelined epilogue: batches of 16 dims (a trailing batch of 8 when C8 is odd) ----
 struct Tc3Batch {
@@ -215,7 +96,7 @@ __device__ __forceinline__ void tc3_compute(float* w, Tc3Batch& b, uint32_t t_hi
     w[2 * i + 1] = fmaf(-ck, __uint_as_float(b.g[2 * i + 1]), w[2 * i + 1]);
     const float x0 = add_h(h_lo(b.hi[i]), add_h(h_lo(b.lo[i]), w[2 * i]));
     const float x1 = add_h(h_hi(b.hi[i]), add_h(h_hi(b.lo[i]), w[2 * i + 1]));
-    split16(x0, x1, b.hi[i], b.lo[i]);
+    split16_sat(x0, x1, b.hi[i], b.lo[i]);
   }
   if (store) {
     tm_st<NCOL / 2>(t_hi + (uint32_t)(col0 / 2), b.hi);
@@ -256,9 +137,11 @@ static __device__ __noinline__ void tc3_prefetch_rows(const float* row0, long lo
 
 // sum_d xs_d G_d of this row (first and last evaluation only: a rolled loop, kept out of the
 // unrolled epilogue so that the 49 middle evaluations do not pay for it)
+// Also reports whether a coordinate of the row sits at the fp16 saturation value (see split16_sat).
 template <int C8>
-__device__ __noinline__ float tc3_energy(uint32_t t_d, uint32_t t_hi, uint32_t t_lo) {
+__device__ __noinline__ float tc3_energy(uint32_t t_d, uint32_t t_hi, uint32_t t_lo, uint32_t* sat) {
   float2 acc = make_float2(0.f, 0.f);
+  uint32_t s = 0u;
 #pragma unroll 1
   for (int c = 0; c < C8; ++c) {
     uint32_t g[8], hh[4], ll[4];
@@ -273,8 +156,10 @@ __device__ __noinline__ float tc3_energy(uint32_t t_d, uint32_t t_hi, uint32_t t
       const float2 xh = h2_unpack(hh[i]);
       acc.x = fmaf(add_h(h_lo(ll[i]), xh.x), __uint_as_float(g[2 * i]), acc.x);
       acc.y = fmaf(add_h(h_hi(ll[i]), xh.y), __uint_as_float(g[2 * i + 1]), acc.y);
+      s |= h16_saturated(hh[i]);
     }
   }
+  *sat = s;
   return acc.x + acc.y;
 }
 
@@ -479,7 +364,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       tmem_wait_ld8(xx);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        split16(__uint_as_float(xx[2 * i]) * sc, __uint_as_float(xx[2 * i + 1]) * sc, hh[i], ll[i]);
+        split16_sat(__uint_as_float(xx[2 * i]) * sc, __uint_as_float(xx[2 * i + 1]) * sc, hh[i], ll[i]);
       tmem_st4(t_hi + (uint32_t)(4 * c), hh);
       tmem_st4(t_lo + (uint32_t)(4 * c), ll);
     }
@@ -500,6 +385,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
     pin(ckf);
     pin(ckh);
     float U0 = 0.f, U1 = 0.f;
+    uint32_t sat = 0u;  // the trajectory left the fp16 range of its row scale (diverged): never accepted
 
     // Leapfrog (src/integrator.py:105-120): evaluations 0 .. L; half kick, (L - 1) x [drift, kick], drift, half kick.
     // Stormer-Verlet (src/integrator.py:142-163) in displacement form d_n = q_n - q_{n-1} (w IS sc d_n):
@@ -535,9 +421,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       const bool first = ev == 0;
       const bool last = sv ? ev == L + 1 : ev == L;  // the evaluation that neither drifts nor stores
       if (k_hmc && (first || last)) {
-        const float Uev = tc3_energy<C8>(t_d, t_hi, t_lo);
+        uint32_t sat_ev;
+        const float Uev = tc3_energy<C8>(t_d, t_hi, t_lo, &sat_ev);
         if (first) U0 = Uev;
-        if (last) U1 = Uev;
+        if (last) {
+          U1 = Uev;
+          sat = sat_ev;
+        }
       }
       const float ck = sv ? (first ? ckh : (last ? 0.f : ckf)) : (L == 0 ? 0.f : ((first || last) ? ckh : ckf));
       if (!(k_dbg & 2u)) tc3_epilogue<C8>(v, t_d, t_hi, t_lo, ck, !last);
@@ -564,6 +454,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       if (valid)
         u = A.u != nullptr ? A.u[pc] : NormalBlock<float>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)pc);
       rej = metropolis_reject<float>(oldH, newH, u, A.flags, &accp);
+      // A row whose position ran more than 256x past its prologue scale saturates its fp16 operands (finite, but no
+      // longer the trajectory).  The exact kernels carry such a divergent trajectory to |q| ~ 1e38 and reject it
+      // with ratio exp(-huge) = 0; here it is rejected outright, whatever EHMC_FLAG_REJECT_NONFINITE says, so
+      // that nothing but a genuine trajectory end is ever written to q.
+      if (sat) {
+        rej = true;
+        accp = 0.f;
+      }
     }
     stamp();  // Metropolis decided
     const bool fast = A.p == nullptr;  // statistics are per-particle scalars here (A.partials = [P][3]), see below
@@ -578,6 +476,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
         tmem_ld4_issue(t_lo + (uint32_t)(4 * c), ll);
         tmem_wait_ld4(hh);
         tmem_wait_ld4(ll);
+        if (!hmc) sat |= h16_saturated(hh[0]) | h16_saturated(hh[1]) | h16_saturated(hh[2]) | h16_saturated(hh[3]);
         float* qd = A.q + (long long)(8 * c) * A.q_ld + pc;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -609,6 +508,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
         tmem_wait_ld4(hh);
         tmem_wait_ld4(ll);
         tmem_wait_ld8(pk);
+        if (!hmc) sat |= h16_saturated(hh[0]) | h16_saturated(hh[1]) | h16_saturated(hh[2]) | h16_saturated(hh[3]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int d = 8 * c + e;
@@ -634,6 +534,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
         }
       }
     }
+    // integrate() has no Metropolis step to absorb a saturated row: count it (ehmc_ctx_overflow_count)
+    if (!hmc && valid && sat && pa.overflow != nullptr) atomicAdd(pa.overflow, 1u);
     if (hmc && valid && A.accept != nullptr) A.accept[pc] = rej ? 0 : 1;
     // ensemble statistics: this kernel only reports the per-particle scalars; the coordinate sums are taken
     // from q by k_ens_stats_partial afterwards (a warp reduction of 2 D doubles per tile cost 1.3 ms per

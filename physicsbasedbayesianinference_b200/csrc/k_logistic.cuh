@@ -52,7 +52,8 @@ __device__ __forceinline__ T sigmoid_(T s) {
 template <typename T>
 __global__ void __launch_bounds__(LG_THREADS) k_logistic_grad(const T* __restrict__ theta, long long t_ld, long long P,
                                                               T* __restrict__ grad, long long g_ld,
-                                                              T* __restrict__ energy, const LogisticArgs<T> pa) {
+                                                              T* __restrict__ energy, double* __restrict__ energy64,
+                                                              const LogisticArgs<T> pa) {
   constexpr int PT = LogiTile<T>::PT, NC = LG_NC;
   constexpr int RPT = NC * PT / LG_THREADS;        // S rows per thread (phase 1)
   constexpr int GP = 4;                            // particles per thread (phase 2)
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_logistic_grad(const T* __restric
 #pragma unroll
     for (int t = 0; t < GP; ++t) acc[j][t] = T(0);
   T e_acc = T(0);
+  const bool want_e = energy != nullptr || energy64 != nullptr;
 
   for (int n0 = 0; n0 < N; n0 += NC) {
     __syncthreads();  // previous chunk fully consumed (also orders the Th fill on the first pass)
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_logistic_grad(const T* __restric
       if (n < N) {
         const T yn = pa.y[n];
         res = sigmoid_<T>(s[r]) - yn;
-        if (energy) e_acc += softplus_<T>(s[r]) - yn * s[r];
+        if (want_e) e_acc += softplus_<T>(s[r]) - yn * s[r];
       }
       Rs[(ng * RPT + r) * PT + pp1] = res;
     }
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_logistic_grad(const T* __restric
       }
     }
   }
-  if (energy) {
+  if (want_e) {
     __syncthreads();
     Es[ng * PT + pp1] = e_acc;
     __syncthreads();
@@ -150,7 +152,9 @@ __global__ void __launch_bounds__(LG_THREADS) k_logistic_grad(const T* __restric
       for (int g = 0; g < LG_THREADS / PT; ++g) e += Es[g * PT + tid];
       T t2 = T(0);
       for (int d = 0; d < D; ++d) t2 += Th[d * PT + tid] * Th[d * PT + tid];
-      energy[p0 + tid] = e + T(0.5) * t2 * pa.inv_s2;
+      const T ev = e + T(0.5) * t2 * pa.inv_s2;
+      if (energy) energy[p0 + tid] = ev;
+      if (energy64) energy64[p0 + tid] = (double)ev;
     }
   }
 }
@@ -232,9 +236,9 @@ __global__ void k_uf_sv_finish(const T* w, T* v, long long P, int D, T h) {
 
 // final: p = v * m ; newH ; Metropolis ; write q / p_out / accept / per-particle stats partials
 template <typename T>
-__global__ void k_uf_final(const IterArgs<T> A, const T* w, const T* v, const T* K0, const T* U0, const T* U1,
-                           int hmc, double* pstats /* [P][3] or null */, const T* g_start = nullptr,
-                           const T* g_end = nullptr, T* g_keep = nullptr, T* u_keep = nullptr) {
+__global__ void k_uf_final(const IterArgs<T> A, const T* w, const T* v, const T* K0, const double* U0,
+                           const double* U1, int hmc, double* pstats /* [P][3] or null */, const T* g_start = nullptr,
+                           const T* g_end = nullptr, T* g_keep = nullptr, double* u_keep = nullptr) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.P) return;
   const T m = A.mass[i];
@@ -250,14 +254,17 @@ __global__ void k_uf_final(const IterArgs<T> A, const T* w, const T* v, const T*
     const T p = v[d * A.P + i] * m;
     ks += p * p;
   }
-  const T oldH = K0[i] + U0[i], newH = T(0.5) * ks / m + U1[i];
+  // The potential of this family is a sum over N data rows (7e4 at config 3, where a float32 ulp is 0.008): the
+  // energies are carried in double and only the DIFFERENCE oldH - newH is rounded to T.  For T = double these are
+  // the reference's own expressions (src/HMC.py:108-115).
+  const double oldH = (double)K0[i] + U0[i], newH = (double)(T(0.5) * ks / m) + U1[i];
   T u;
   if (A.u != nullptr)
     u = A.u[i];
   else
     u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)i);
   T accp;
-  const bool rej = metropolis_reject<T>(oldH, newH, u, A.flags, &accp);
+  const bool rej = metropolis_reject<T>((T)(oldH - newH), T(0), u, A.flags, &accp);
   const T pstd = momentum_std<T>(m, A.kB, A.temp, A.pscale);
   constexpr int NB = NormalBlock<T>::N;
   for (int d = 0; d < A.D; ++d) {
@@ -289,7 +296,7 @@ __global__ void k_uf_final(const IterArgs<T> A, const T* w, const T* v, const T*
   if (pstats != nullptr) {
     pstats[i * 3 + 0] = rej ? 0.0 : 1.0;
     pstats[i * 3 + 1] = (double)accp;
-    pstats[i * 3 + 2] = (double)(rej ? oldH : newH);
+    pstats[i * 3 + 2] = rej ? oldH : newH;
   }
 }
 

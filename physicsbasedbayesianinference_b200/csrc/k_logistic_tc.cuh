@@ -33,10 +33,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
-#include "common.cuh"
-#include "k_dense_tc.cuh"
-#include "k_dense_tc2.cuh"
-#include "k_dense_tc3.cuh"  // tmem_st4
+#include "tc_common.cuh"
 
 namespace ehmc {
 
@@ -59,46 +56,6 @@ struct LogisticTcArgs {
   float inv_s2;
 };
 
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn_major) {
-  return (1u << 4)                           // D format F32
-         | (1u << 7) | (1u << 10)           // A, B format BF16
-         | ((uint32_t)b_mn_major << 16)     // B major: 0 = K, 1 = MN
-         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// generic no-swizzle descriptor: lbo / sbo in bytes
-__device__ __forceinline__ uint64_t umma_desc2(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
-__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -109,31 +66,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// D[tmem] (+)= A[tmem] * B[smem], bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // grad[D,P] (and energy[P] when WITH_E) at theta[D,P]
 template <bool WITH_E>
 __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __restrict__ theta, long long t_ld,
                                                                long long P, float* __restrict__ grad, long long g_ld,
-                                                               float* __restrict__ energy, const LogisticTcArgs pa) {
+                                                               float* __restrict__ energy,
+                                                               double* __restrict__ energy64, const LogisticTcArgs pa) {
   extern __shared__ __align__(128) unsigned char lt_smem[];
   const int DP = pa.DP, D = pa.D, NS = pa.stages;
   const int part = (int)(blockIdx.x % (unsigned)pa.split);
   const int cbeg = (int)((long long)pa.NC * part / pa.split);
   const int NC = (int)((long long)pa.NC * (part + 1) / pa.split) - cbeg;  // chunks of this CTA: cbeg .. cbeg + NC
   unsigned char* Xs0 = lt_smem;                                                     // NS stages of chunk_bytes
-  float* xch = reinterpret_cast<float*>(Xs0 + (size_t)NS * pa.chunk_bytes);         // [2][128] energy exchange
+  double* xch = reinterpret_cast<double*>(Xs0 + (size_t)NS * pa.chunk_bytes);       // [2][128] energy exchange
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * LT_M);
   uint64_t* x_full = bars;                      // [LT_MAX_STAGES]
   uint64_t* x_empty = bars + LT_MAX_STAGES;     // [LT_MAX_STAGES]
@@ -220,7 +165,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
         // first 16 columns of ITS 32-column half of the S buffer
 #pragma unroll
         for (int j = 0; j < LT_NB / 16; ++j)
-          umma_bf16_ts(t_g, t_s + (uint32_t)(b * 64 + (j >> 1) * 32 + (j & 1) * 8), dB2 + j * ((16u * 16u) >> 4), idesc2,
+          umma_f16_ts(t_g, t_s + (uint32_t)(b * 64 + (j >> 1) * 32 + (j & 1) * 8), dB2 + j * ((16u * 16u) >> 4), idesc2,
                        (cc > 0 || j > 0) ? 1u : 0u);
         umma_commit(&x_empty[s]);  // the X stage is free once these MMAs have executed
       };
@@ -232,7 +177,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
         // tensor pipe executes one thread's MMAs in order, no barrier needed
         const uint64_t dB1 = umma_desc2(smem_u32(Xs0 + (size_t)s * pa.chunk_bytes), LT_NB * 16, 128);
         for (int j = 0; j < DP / 16; ++j)
-          umma_bf16_ts(t_s + (uint32_t)((c & 1) * 64), tmem_base + 8u * j, dB1 + j * k_step, idesc1, j > 0 ? 1u : 0u);
+          umma_f16_ts(t_s + (uint32_t)((c & 1) * 64), tmem_base + 8u * j, dB1 + j * k_step, idesc1, j > 0 ? 1u : 0u);
         umma_commit(&s_full[c & 1]);
         if (c >= 1) gemm2(c - 1);
       }
@@ -241,7 +186,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
     }
   } else {
     // ===== epilogue warps: sigmoid-residual between the two GEMMs =====
-    float Uacc = 0.f;
+    double Uacc = 0.0;  // 32-term float sums per chunk, double across the chunks
     const uint32_t t_mine = t_s + lane_off + (uint32_t)(half * 32);
     for (int c = 0; c < NC; ++c) {
       const int s = c % NS, b = c & 1;
@@ -255,6 +200,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
       const unsigned char* tail = Xs0 + (size_t)s * pa.chunk_bytes + (size_t)DP * LT_NB * 2;
       const float* yv = reinterpret_cast<const float*>(tail) + half * 32;
       uint32_t rp[16];
+      float Uc = 0.f;
       if (WITH_E) {
         // energy evaluations (first / last gradient of a trajectory): exact exp / log per logit
 #pragma unroll
@@ -268,7 +214,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
               const float yn = yv[16 * bb + i + t];
               const float sig = fmaf(0.5f, tanh_approx(0.5f * sgm), 0.5f);
               r2[t] = sig - yn;
-              Uacc += fmaxf(sgm, 0.f) + __logf(1.f + __expf(-fabsf(sgm))) - yn * sgm;
+              Uc += fmaxf(sgm, 0.f) + __logf(1.f + __expf(-fabsf(sgm))) - yn * sgm;
             }
             rp[(16 * bb + i) / 2] = pack_bf16x2(r2[0], r2[1]);
           }
@@ -295,6 +241,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
           }
         }
       }
+      if (WITH_E) Uacc += (double)Uc;
       tmem_st16(t_mine + (uint32_t)(b * 64), rp);  // R over the first 16 of my 32 S columns
       tmem_wait_st();
       tc_fence_before();
@@ -347,18 +294,21 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_logistic_tc(const float* __re
         }
       }
     }
-    if (WITH_E) xch[half * LT_M + row] = Uacc + 0.5f * t2 * pa.inv_s2;
+    if (WITH_E) xch[half * LT_M + row] = Uacc + (double)(0.5f * t2 * pa.inv_s2);
   }
   tc_fence_before();
   __syncthreads();
   if (WITH_E && tid < LT_M && p0 + tid < P) {
     // the zero rows padding the LAST chunk each contributed softplus(0) = ln 2
-    const float pad = part == pa.split - 1 ? (float)pa.n_pad * 0.6931471805599453f : 0.f;
-    const float ev = xch[tid] + xch[LT_M + tid] - pad;
-    if (pa.split == 1)
-      energy[p0 + tid] = ev;
-    else
-      atomicAdd(&energy[p0 + tid], ev);
+    const double pad = part == pa.split - 1 ? (double)pa.n_pad * 0.6931471805599453 : 0.0;
+    const double ev = xch[tid] + xch[LT_M + tid] - pad;
+    if (pa.split == 1) {
+      if (energy) energy[p0 + tid] = (float)ev;
+      if (energy64) energy64[p0 + tid] = ev;
+    } else {
+      if (energy) atomicAdd(&energy[p0 + tid], (float)ev);
+      if (energy64) atomicAdd(&energy64[p0 + tid], ev);
+    }
   }
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }

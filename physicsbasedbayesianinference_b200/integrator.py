@@ -93,6 +93,15 @@ class Integrator:
         else:
             _lib.leapfrog(ctx, self.potential.handle(bits, ctx), q, p, m, self.stepSize, self.stepSize**2,
                           self.numSteps, stream, stormer=stormer)
+            if isinstance(q, np.ndarray) and bits == 32:
+                # host-backed calls are synchronous anyway: surface a divergent trajectory that left the fp16 operand
+                # range of the tensor-core dense kernel (device-backed callers poll Context.overflow_count themselves)
+                n = ctx.overflow_count()
+                if n:
+                    raise FloatingPointError(
+                        f"{n} particle trajectories diverged past the operand range of the float32 tensor-core "
+                        "kernel (step size above the stability limit?); their q, p are not valid. Re-run with "
+                        "Context.set_option('dense_path', 1) for the exact CUDA-core kernel")
         # positions and momenta of all particles at finalTime: the same objects, mutated in place
         return (self.q, self.p)
 

@@ -189,12 +189,17 @@ class LogisticPotential(Potential):
 
     family = _lib.FAMILY_LOGISTIC
 
-    def __init__(self, X, y, priorScale=1.0, precision="fp32"):
-        """precision="fp32": exact CUDA-core gradient (parity path).  precision="bf16": the
-        tcgen05 tensor-core GEMM chain (X and theta rounded to bf16, fp32 accumulation;
-        float32 ensembles only) -- the throughput path of BASELINE config 3."""
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+    PRECISIONS = {"fp32": 0.0, "bf16": 1.0, "fp16x3": 2.0, "auto": 3.0}
+
+    def __init__(self, X, y, priorScale=1.0, precision="auto"):
+        """precision selects the gradient kernel of float32 ensembles (float64 always runs the exact one):
+        "auto" (default): the tcgen05 tensor-core GEMM chain at float32 accuracy ("fp16x3") unless the fp16
+        split cannot represent X, then "fp32";  "fp16x3": force it -- every operand a 2-term fp16 split,
+        3 MMA passes per GEMM, trajectories within 1e-5 of the float64 oracle (BASELINE config 3);
+        "fp32": exact CUDA-core gradient;  "bf16": single-pass bf16 tensor-core chain, 2.7x faster than
+        "fp16x3" but 5e-3 gradient accuracy -- outside the tolerance, opt-in only."""
+        if precision not in self.PRECISIONS:
+            raise ValueError("precision must be one of " + ", ".join(sorted(self.PRECISIONS)))
         self.precision = precision
         self.X = np.ascontiguousarray(X, dtype=np.float64)
         self.y = np.ascontiguousarray(y, dtype=np.float64)
@@ -207,7 +212,7 @@ class LogisticPotential(Potential):
         return [self.X, self.y]
 
     def _scalars(self):
-        return [self.priorScale, 1.0 if self.precision == "bf16" else 0.0]
+        return [self.priorScale, self.PRECISIONS[self.precision]]
 
 
 def _descriptor(potential):

@@ -829,7 +829,7 @@ def test_config3_shape_logistic_reduced(E):
 
 
 # ---------------------------------------------------------------------------
-# dense Gaussian: tensor-core (3xTF32, tcgen05) path vs CUDA-core FP32 path vs oracle
+# dense Gaussian: tensor-core (3xFP16, tcgen05) path vs CUDA-core FP32 path vs oracle
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize("D,P,L", [(20, 300, 7), (40, 129, 9), (100, 1000, 50), (104, 257, 12), (17, 64, 0), (56, 200, 3),
                                    (112, 300, 10), (128, 513, 25), (100, 40000, 5)])
@@ -852,9 +852,8 @@ def test_dense_tensor_core_path_vs_cuda_core_path_vs_oracle(E, D, P, L):
     args = E._lib.make_args(h, h**2, L, KB, 1 / KB, flags=1)
     out = {}
     try:
-        # 1 = CUDA cores, 2 / 3 = 3xTF32 tensor cores (one tile SS / two tiles TS, D <= 104),
-        # 4 = 3xFP16 persistent tensor-core kernel (the default path, D <= 128)
-        paths = (1, 2, 3, 4) if D <= 104 else (1, 4)
+        # 1 = CUDA cores, 4 = 3xFP16 persistent tensor-core kernel (the default path, D <= 128)
+        paths = (1, 4)
         for path in paths:
             ctx.set_option("dense_path", path)
             q = torch.tensor(q0, dtype=torch.float32, device="cuda")
@@ -1003,7 +1002,112 @@ def test_dense_tensor_core_zero_step(E):
     np.testing.assert_allclose(q.cpu().numpy(), q0, rtol=3e-7, atol=1e-7)
 
 
-@pytest.mark.parametrize("case", ["diag2", "funnel10", "dense100", "dense40_cuda_cores", "nbody", "logistic", "logistic_tc"])
+def test_dense_tensor_core_divergent_trajectory_is_rejected(E):
+    """A step size far above the stability limit 2 / sqrt(lambda_max) makes |q| grow by orders of magnitude per
+    step.  The fp16 split operands of the tensor-core kernel saturate (instead of turning into inf - inf = NaN) and
+    the row is rejected outright: q stays finite and unchanged, exactly like the CUDA-core kernel, which carries the
+    trajectory to ~1e38 and rejects it with ratio 0.  With the reference's default flags a NaN ratio would have been
+    ACCEPTED (src/HMC.py:168-173) and written into q for good."""
+    import torch
+
+    D, P, L = 100, 700, 50
+    rng = np.random.RandomState(13)
+    A = rng.standard_normal((D, D))
+    prec = A @ A.T / D + np.eye(D)
+    lam_max = np.linalg.eigvalsh(prec).max()
+    h = 2.1 / np.sqrt(lam_max)  # 5 % above the stability limit: the stiffest mode grows 1.9x per step, 5e13 in all
+    q0 = rng.standard_normal((D, P)).astype(np.float32)
+    ctx = E._lib.Context.get()
+    hd = E.GaussianPotential(precision=prec).handle(32, ctx)
+    args = E._lib.make_args(h, h * h, L, KB, 1 / KB, seed=5, iteration=0, flags=1)  # reference default: NaN accepted
+    res = {}
+    try:
+        for path in (1, 4):
+            ctx.set_option("dense_path", path)
+            q = torch.tensor(q0, device="cuda")
+            acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+            st = torch.zeros(2 * D + 3, dtype=torch.float64, device="cuda")
+            E._lib.hmc_iter(ctx, hd, q, torch.ones(P, dtype=torch.float32, device="cuda"), args, accept=acc, stats=st)
+            torch.cuda.synchronize()
+            res[path] = (q.cpu().numpy(), acc.cpu().numpy(), st.cpu().numpy())
+    finally:
+        ctx.set_option("dense_path", 0)
+    for path in (1, 4):
+        q, acc, st = res[path]
+        assert np.isfinite(q).all(), f"path {path}"
+        assert acc.sum() == 0 and np.array_equal(q, q0), f"path {path}"
+        assert np.isfinite(st).all() and st[0] == 0 and st[1] == 0, f"path {path}"
+    # integrate() has no Metropolis step: the divergence is reported instead (host-backed call raises)
+    ens = E.Ensemble(D, P, dtype=np.float32)
+    ens.q[:] = q0
+    ens.p[:] = rng.standard_normal((D, P))
+    with pytest.raises(FloatingPointError):
+        E.Leapfrog(ens, h, L * h + 1e-9, E.GaussianPotential(precision=prec)).integrate()
+    assert ctx.overflow_count() == 0  # the counter was consumed by the check
+
+
+@pytest.mark.parametrize("kind", ["kappa1e6", "span2^30", "moderate"])
+def test_dense_ill_conditioned_precision_guard(E, kind):
+    """dense_path 0 (auto) on precision matrices that are hard for the fp16 split: entries far below max |Lambda|
+    flush in fp16, and coordinate scales spread past the 2^7 headroom of the per-row scale.  ehmc_potential_create
+    detects both and routes such potentials to the exact CUDA-core kernel.  float32 state itself limits what any
+    kernel can reach here (Lambda dx with |dx| = 6e-8 |x| is kappa^(1/2) times the gradient's own rounding), so
+    the bar is: the default path is within 1e-5, or within 4x of the exact float32 FMA kernel's own error."""
+    import torch
+
+    D, P, L = 64, 400, 20
+    rng = np.random.RandomState(21)
+    Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    if kind == "kappa1e6":
+        prec = (Q * np.logspace(0, 6, D)) @ Q.T
+    elif kind == "span2^30":
+        s = np.logspace(0, 4.5, D)  # coordinate scales over 2^15: diag(Lambda) spans 2^30
+        A = rng.standard_normal((D, D))
+        prec = (A @ A.T / D + np.eye(D)) * np.outer(s, s)
+    else:
+        prec = (Q * np.logspace(0, 2, D)) @ Q.T  # kappa = 100
+    prec = 0.5 * (prec + prec.T)
+    sd = 1.0 / np.sqrt(np.diag(prec))
+    q0 = rng.standard_normal((D, P)) * sd[:, None]
+    z = rng.standard_normal((D, P))
+    u = rng.uniform(size=P)
+    h = 0.3 / np.sqrt(np.linalg.eigvalsh(prec).max())
+    qr, pr, accr, oh, nh = O.hmc_iter(q0, z, u, np.ones(P), 1 / KB, h, L, O.DenseGaussian(prec, np.zeros(D)))
+    ctx = E._lib.Context.get()
+    hd = E.GaussianPotential(precision=prec).handle(32, ctx)
+    args = E._lib.make_args(h, h * h, L, KB, 1 / KB, flags=0)
+    with np.errstate(over="ignore"):
+        clear = np.abs(u - np.minimum(1, np.exp(oh - nh))) > TIE[np.float32]
+    res = {}
+    try:
+        for path in (0, 1):
+            ctx.set_option("dense_path", path)
+            q = torch.tensor(q0, dtype=torch.float32, device="cuda")
+            p = torch.empty_like(q)
+            acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+            E._lib.hmc_iter(ctx, hd, q, torch.ones(P, dtype=torch.float32, device="cuda"), args, p_out=p,
+                            z=torch.tensor(z, dtype=torch.float32, device="cuda"),
+                            u=torch.tensor(u, dtype=torch.float32, device="cuda"), accept=acc)
+            torch.cuda.synchronize()
+            a = acc.cpu().numpy().astype(bool)
+            same = a == accr
+            # every coordinate in units of its own scale
+            eq = np.abs(q.cpu().numpy()[:, same] - qr[:, same]) / sd[:, None]
+            res[path] = (a, float(eq.max() / np.abs(qr[:, same] / sd[:, None]).max()),
+                         rel_err(p.cpu().numpy()[:, same], pr[:, same]), q.cpu().numpy())
+    finally:
+        ctx.set_option("dense_path", 0)
+    print(kind, {k: v[1:3] for k, v in res.items()})
+    assert np.array_equal(res[0][0][clear], accr[clear])
+    assert res[0][1] < max(1e-5, 4 * res[1][1]) and res[0][2] < max(1e-5, 4 * res[1][2])
+    if kind == "span2^30":
+        assert np.array_equal(res[0][3], res[1][3])  # the guard chose the CUDA-core kernel: identical bits
+    if kind == "moderate":
+        assert res[0][1] < 1e-5 and res[0][2] < 1e-5
+
+
+@pytest.mark.parametrize("case", ["diag2", "funnel10", "dense100", "dense40_cuda_cores", "nbody", "logistic", "logistic_tc",
+                                  "logistic_tcs"])
 def test_no_out_of_bounds_writes_canary(E, case):
     """Every in/out tensor of ehmc_hmc_iter is a window into a larger canary-filled allocation (one guard row
     above and below, 37 guard columns left and right, ragged P): after the call every guard element still
@@ -1029,7 +1133,8 @@ def test_no_out_of_bounds_writes_canary(E, case):
         N, D = 300, 24
         X = rng.standard_normal((N, D)) / np.sqrt(D)
         y = (rng.uniform(size=N) < 0.5).astype(np.float64)
-        pot = E.LogisticPotential(X, y, 1.0, precision="bf16" if case.endswith("tc") else "fp32")
+        pot = E.LogisticPotential(X, y, 1.0, precision={"logistic": "fp32", "logistic_tc": "bf16",
+                                                         "logistic_tcs": "fp16x3"}[case])
     CAN, G = -777.25, 37
 
     def window(rows, dtype=torch.float32):
@@ -1172,7 +1277,100 @@ def test_logistic_tensor_core_gradient(E, N, D, P):
     assert rel_err(u, po.energy(th)) < 2e-3
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("N,D,P", [(1000, 256, 300), (128, 16, 128), (700, 40, 77), (5000, 256, 1024), (64, 3, 5),
+                                   (4096, 200, 513)])
+def test_logistic_split_tensor_core_gradient(E, N, D, P):
+    """k_logistic_tcs (tcgen05 GEMM chain, 3-pass fp16 split of X, theta and the residual) against the float64
+    oracle on the UNROUNDED inputs: float32-level accuracy, three orders of magnitude tighter than the bf16 chain."""
+    rng = np.random.RandomState(N + D)
+    X = rng.standard_normal((N, D)) / np.sqrt(D)
+    X[:, 0] *= 30.0  # a column on another scale (the guard of "auto" would still accept it)
+    y = (rng.uniform(size=N) < 0.5).astype(np.float64)
+    th = rng.standard_normal((D, P))
+    th[:, 0] *= 1e-3  # rows on very different scales: the per-row power-of-two scale
+    th[:, 1] *= 1e3
+    if P > 2:
+        th[:, 2] = 0.0
+    pe, po = E.LogisticPotential(X, y, 2.0, precision="fp16x3"), O.Logistic(X, y, 2.0)
+    g = pe.gradient(th.astype(np.float32))
+    u = pe(th.astype(np.float32))
+    th32 = th.astype(np.float32).astype(np.float64)
+    g_ref, u_ref = po.grad(th32), po.energy(th32)
+    # per particle: gradient error relative to that particle's largest gradient component
+    eg = np.max(np.abs(g - g_ref), axis=0) / np.max(np.abs(g_ref), axis=0)
+    eu = np.abs(u - u_ref) / np.abs(u_ref)
+    print("split gradient", N, D, P, "max rel grad err", eg.max(), "energy", eu.max())
+    # (the particle scaled by 1e3 has logits ~ 1e3: their float32 rounding alone moves sigmoid by 1e-5 near s = 0)
+    assert np.median(eg) < 1.5e-6 and eg.max() < 1e-5
+    assert eu.max() < 1e-6  # float32 output rounding (6e-8) plus the MUFU lg2 / ex2 of softplus
+
+
+def test_logistic_precision_auto_guard(E):
+    """precision="auto": the tensor-core split when X is representable, the exact CUDA-core kernel when a column sits
+    2^20 below the largest entry (its lo parts would be fp16 subnormals)."""
+    rng = np.random.RandomState(77)
+    N, D, P = 500, 32, 200
+    X = rng.standard_normal((N, D)) / np.sqrt(D)
+    y = (rng.uniform(size=N) < 0.5).astype(np.float64)
+    th = rng.standard_normal((D, P)).astype(np.float32)
+    ctx = E._lib.Context.get()
+    for bad in (False, True):
+        Xc = X.copy()
+        if bad:
+            Xc[:, 5] *= 2.0 ** -20
+            th[5] *= 2.0 ** 20
+        auto, exact = E.LogisticPotential(Xc, y, 1.0), E.LogisticPotential(Xc, y, 1.0, precision="fp32")
+        ga, ge = auto.gradient(th), exact.gradient(th)
+        ref = O.Logistic(Xc, y, 1.0).grad(th.astype(np.float64))
+        if bad:
+            assert np.array_equal(ga, ge)  # fell back: same kernel, same bits
+        else:
+            assert not np.array_equal(ga, ge)  # tensor cores: different rounding
+        scale = np.max(np.abs(ref), axis=1, keepdims=True)
+        assert np.max(np.abs(ga - ref) / scale) < 1e-5
+
+
+def test_config3_full_size(E):
+    """BASELINE config 3 at FULL size on the tensor-core path: X 100 000 x 256, 65 536 particles, L = 10, float32
+    state, fed momenta and uniforms; 128 random particles against the float64 oracle at the north_star's 1e-5.
+    Positions start around the generating parameter (the posterior's neighbourhood: sd ~ 0.1)."""
+    import torch
+
+    N, D, P, L, h = 100_000, 256, 65_536, 10, 0.1  # h omega_max = 1.04: 107 of the 128 oracle proposals are accepted
+    rng = np.random.RandomState(33)
+    X = rng.standard_normal((N, D)) / np.sqrt(D)
+    th_true = rng.standard_normal(D)
+    y = (rng.uniform(size=N) < 1 / (1 + np.exp(-X @ th_true))).astype(np.float64)
+    pe = E.LogisticPotential(X, y, 1.0, precision="fp16x3")
+    q0 = (th_true[:, None] + 0.1 * rng.standard_normal((D, P))).astype(np.float32)
+    z = rng.standard_normal((D, P)).astype(np.float32)
+    u = rng.uniform(size=P).astype(np.float32)
+    ens = E.Ensemble(D, P, dtype=np.float32, device="cuda")
+    ens.q.copy_(torch.tensor(q0))
+    hmc = E.HMC(ens, L * h + 1e-9, h, None, potential=pe)
+    assert hmc.integrator.numSteps == L
+    acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+    pout = torch.empty_like(ens.q)
+    hmc.step(1 / KB, accept=acc, z=torch.tensor(z, device="cuda"), u=torch.tensor(u, device="cuda"), p_out=pout)
+    torch.cuda.synchronize()
+    sel = np.sort(rng.choice(P, 128, replace=False))
+    po = O.Logistic(X, y, 1.0)
+    qr, pr, accr, oh, nh = O.hmc_iter(q0[:, sel].astype(np.float64), z[:, sel].astype(np.float64),
+                                      u[sel].astype(np.float64), np.ones(128), 1 / KB, h, L, po, bug_compat=False)
+    a = acc.cpu().numpy().astype(bool)[sel]
+    with np.errstate(over="ignore"):
+        clear = np.abs(u[sel] - np.minimum(1, np.exp(oh - nh))) > TIE[np.float32]
+    assert np.array_equal(a[clear], accr[clear])
+    assert 5 < a.sum() < 128  # both outcomes occur
+    same = a == accr
+    qg = ens.q.cpu().numpy()[:, sel]
+    print("config 3 full size: rel err q", rel_err(qg[:, same], qr[:, same]), "accepted", int(a.sum()), "of 128")
+    assert rel_err(qg[:, same], qr[:, same]) < 1e-5
+    acc_same = same & a
+    assert rel_err(pout.cpu().numpy()[:, sel][:, acc_same], pr[:, acc_same]) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16x3"])
 def test_logistic_endpoint_cache_is_exact(E, precision):
     """EHMC_FLAG_REUSE_ENDPOINT: starting every trajectory from the gradient / energy kept at the end of the
     previous one (accepted: the trajectory's end, rejected: its start) gives bit-identical chains with one
