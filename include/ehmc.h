@@ -267,6 +267,42 @@ EHMC_API int ehmc_hmc_run(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q,
                  const ehmc_hmc_args* args, int numIterations, DLTensor* samples_out, DLTensor* momenta_out,
                  int64_t sampleOffset, DLTensor* accepted_out, void* stream);
 
+/* ---- the adaptive ensemble run in ONE launch, with the statistics all-reduce inside the kernel -------------- */
+/* Peer-memory mailboxes: one process per GPU creates a communicator, the caller exchanges the opaque handles of
+ * all ranks (any transport; the Python binding uses torch.distributed all_gather) and connects.  Needs CUDA IPC /
+ * peer access between the GPUs (NVLink / NVSwitch on a B200 box). */
+#define EHMC_COMM_MAX_RANKS 16
+#define EHMC_COMM_HANDLE_BYTES 64
+typedef struct ehmc_comm ehmc_comm;
+EHMC_API int ehmc_comm_create(ehmc_ctx* ctx, int rank, int worldSize, ehmc_comm** out);
+EHMC_API int ehmc_comm_handle(ehmc_comm* comm, void* out /* EHMC_COMM_HANDLE_BYTES */);
+EHMC_API int ehmc_comm_connect(ehmc_comm* comm, const void* handles /* worldSize x EHMC_COMM_HANDLE_BYTES, by rank */);
+EHMC_API int ehmc_comm_destroy(ehmc_comm* comm);
+
+typedef struct {
+  uint32_t struct_size;      /* sizeof(ehmc_adapt_args) */
+  int32_t adaptIterations;   /* Robbins-Monro updates from the first adaptIterations iterations of the call */
+  double targetAccept, gain0, kappa, maxMove, minStep, maxStep; /* parallel.StepSizeAdapter */
+  double numParticlesTotal;  /* particles of ALL ranks */
+} ehmc_adapt_args;
+
+/* numIterations iterations of the loop of src/HMC.py:150-179 on the resident ensemble (Philox iterations
+ * args.iteration ..), as HMC.run drives it: every iteration's ensemble statistics {n_accept, sum acceptance
+ * probability, sum H, sum q_d, sum q_d^2} are summed over the CTAs and over all ranks of `comm` INSIDE the kernel
+ * (stores into the peers' mailboxes over NVLink, rank-ordered sum: identical bits on every rank), the step size
+ * follows log h += clip(gain0 / k^kappa (mean acceptance probability - target)) with the statistics of iteration
+ * k first used by iteration k + 2 (the all-reduce hides behind iteration k + 1), numSteps stays fixed.
+ *   state    float64[4] device, in/out: {step size, log step size, updates k, iterations run}
+ *   history  float64[S,4] device, optional: {accept rate, mean acceptance probability, mean H, step size used}
+ *   moments  float64[2D] device, optional, accumulated: sum q_d, sum q_d^2 over particles and iterations
+ *   trace    [D*traceParticles, S] device, optional: kept positions of the first traceParticles local particles,
+ *            iteration k in slot traceOffset + k
+ * Small-D families, device tensors, leapfrog; every rank of `comm` (NULL: single GPU) must make the same call. */
+EHMC_API int ehmc_hmc_run_ensemble(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, const DLTensor* mass,
+                          const ehmc_hmc_args* args, int numIterations, const ehmc_adapt_args* adapt, ehmc_comm* comm,
+                          DLTensor* state, DLTensor* history, DLTensor* moments, DLTensor* trace,
+                          int64_t traceParticles, int64_t traceOffset, void* stream);
+
 /* Consumes the (all-reduced) statistics of the iteration that just ran with the block `dynamic`:
  *   history[dynamic.row] = {acceptRate, meanAcceptProb, meanH, stepSize used}  (optional, float64 [S,4])
  *   moments[0:D] += sum q_d, moments[D:2D] += sum q_d^2                        (optional, float64 [2D])

@@ -217,7 +217,8 @@ class HMC:
 
     # ------------------------------------------------------------------------------------
     def run(self, numIterations, temperature, *, adapt=False, targetAccept=0.8, adaptIterations=None,
-            traceParticles=0, group=None, collectStats=True, keepNumSteps=False, deviceAdapt=False, graph=False):
+            traceParticles=0, group=None, collectStats=True, keepNumSteps=False, deviceAdapt=False, graph=False,
+            fused=None):
         """Production loop for device ensembles (build-defined; scales where getSamples'
         (D, P, S) arrays cannot, SURVEY.md section 7 hard part 7).
 
@@ -240,9 +241,22 @@ class HMC:
         287 us, graph 373 us -- the cross-stream edges a graph needs for the overlap cost more than the
         Python enqueue they save, so graph replay is off by default.
 
+        fused=True runs the WHOLE call as one persistent cooperative launch (ehmc_hmc_run_ensemble, small-D
+        families, Leapfrog, fixed numSteps): trajectory kernel, per-iteration statistics, their all-reduce across the
+        ranks of `group` (stores into the peers' mailboxes over NVLink, inside the kernel) and the step-size update,
+        with the same one-iteration-stale schedule as the loop below -- no launch, no NCCL call and no host work per
+        iteration.  fused=None (default) picks it whenever it applies (statistics wanted, numSteps fixed: adapt=False
+        or keepNumSteps=True); it needs CUDA IPC / peer access between the GPUs of `group`.
+
         Returns dict(acceptRate[S], meanAcceptProb[S], meanH[S], stepSize[S], mean[D], var[D],
         trace (D, traceParticles, S) or None).
         """
+        if fused is None:
+            fused = (collectStats and not deviceAdapt and self.ensemble.onDevice and self.method == "Leapfrog"
+                     and self._fused_loop_ok() and (keepNumSteps or not adapt) and numIterations > 0)
+        if fused:
+            return self._run_fused(numIterations, temperature, adapt, targetAccept, adaptIterations, traceParticles,
+                                   group)
         if deviceAdapt:
             return self._run_device_adapt(numIterations, temperature, adapt, targetAccept, adaptIterations,
                                           traceParticles, group, graph)
@@ -262,7 +276,10 @@ class HMC:
             t = torch.tensor([P], dtype=torch.float64, device=dev)
             reducer.dist.all_reduce(t, group=group)
             Ptot = float(t.item())
-        adapter = StepSizeAdapter(self.stepSize, targetAccept) if adapt else None
+        # without keepNumSteps the trajectory length is fixed and numSteps follows the step size: a step size above
+        # simulTime would mean numSteps = 0 (nothing moves, acceptance 1, the adapter runs away), so it is capped
+        adapter = (StepSizeAdapter(self.stepSize, targetAccept, maxStep=1e3 if keepNumSteps else min(1e3, self.simulTime))
+                   if adapt else None)
         adaptIterations = numIterations if adaptIterations is None else adaptIterations
         # Two statistics slots (device vector + pinned host copy + "copy done" event).  Iteration k
         # writes slot k & 1; a side stream all-reduces it and copies it to the host behind an event,
@@ -300,7 +317,7 @@ class HMC:
                 if keepNumSteps:
                     self.simulTime = self.integrator.finalTime = self.integrator.numSteps * self.stepSize
                 else:
-                    self.integrator.numSteps = int(self.simulTime / self.stepSize)  # src/integrator.py:51
+                    self.integrator.numSteps = max(1, int(self.simulTime / self.stepSize))  # src/integrator.py:51
 
         for it in range(numIterations):
             slot = it & 1
@@ -328,6 +345,58 @@ class HMC:
         out.update(mean=mean, var=sum2 / n - mean * mean, trace=trace, worldSize=world)
         return out
 
+
+    def _run_fused(self, numIterations, temperature, adapt, targetAccept, adaptIterations, traceParticles, group):
+        """HMC.run as ONE launch: see run(fused=True) and csrc/k_small_ens.cuh."""
+        import math
+
+        import torch
+
+        from .parallel import ensemble_comm
+
+        ens = self.ensemble
+        if not ens.onDevice:
+            raise TypeError("HMC.run needs a device-backed Ensemble (device='cuda')")
+        if self.method != "Leapfrog" or not self._fused_loop_ok():
+            raise ValueError("fused=True needs method='Leapfrog' and a small-D potential family (D <= 32)")
+        D, P, dev = ens.numDimensions, ens.numParticles, ens.device
+        ctx = _lib.Context.get(dev.index)
+        comm = ensemble_comm(ctx, group, dev)
+        world, Ptot = 1, float(P)
+        if comm is not None:
+            import torch.distributed as dist
+
+            world = dist.get_world_size(group)
+            t = torch.tensor([P], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, group=group)
+            Ptot = float(t.item())
+        n = int(numIterations)
+        adaptRows = 0 if not adapt else (n if adaptIterations is None else min(n, int(adaptIterations)))
+        state = torch.tensor([self.stepSize, math.log(self.stepSize), 0.0, 0.0], dtype=torch.float64, device=dev)
+        hist = torch.zeros((n, 4), dtype=torch.float64, device=dev)
+        mom = torch.zeros(2 * D, dtype=torch.float64, device=dev)
+        ntrace = int(traceParticles)
+        trace = torch.empty((D, ntrace, n), dtype=ens.dtype, device=dev) if ntrace else None
+        self.integrator.q = ens.q
+        numSteps = self.integrator.numSteps
+        q = ens.q
+        bits = q.element_size() * 8
+        _lib.hmc_run_ensemble(ctx, self.potential.handle(bits, ctx), q, self.integrator.mass, self._args(temperature), n,
+                              _lib.make_adapt_args(Ptot, adaptRows, target=targetAccept), state, comm=comm, history=hist,
+                              moments=mom, trace=None if trace is None else trace.view(D * ntrace, n),
+                              trace_particles=ntrace, stream=_lib.current_stream_ptr(q))
+        self.iteration += n
+        st = state.cpu().numpy()  # synchronises
+        self.stepSize = float(st[0])
+        self.integrator.stepSize = self.stepSize
+        self.simulTime = self.integrator.finalTime = numSteps * self.stepSize
+        h = hist.cpu().numpy()
+        m = mom.cpu().numpy()
+        cnt = float(max(n, 1)) * Ptot
+        mean = torch.from_numpy(m[:D] / cnt)
+        return dict(acceptRate=list(h[:, 0]), meanAcceptProb=list(h[:, 1]), meanH=list(h[:, 2]), stepSize=list(h[:, 3]),
+                    numSteps=[numSteps] * n, mean=mean, var=torch.from_numpy(m[D:] / cnt) - mean * mean,
+                    trace=trace, worldSize=world, fused=True)
 
     def _run_device_adapt(self, numIterations, temperature, adapt, targetAccept, adaptIterations, traceParticles,
                           group, graph, graphIterations=10):

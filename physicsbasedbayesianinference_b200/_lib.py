@@ -36,7 +36,10 @@ SYMBOLS = (
     "ehmc_ctx_device_info", "ehmc_ctx_set_option", "ehmc_measure_fp32_peak", "ehmc_potential_create", "ehmc_potential_destroy",
     "ehmc_potential_eval", "ehmc_set_position", "ehmc_set_momentum", "ehmc_philox_fill", "ehmc_leapfrog",
     "ehmc_stormer_verlet", "ehmc_integrate_nbody_mode", "ehmc_hmc_iter", "ehmc_hmc_run", "ehmc_adapt_step",
+    "ehmc_comm_create", "ehmc_comm_handle", "ehmc_comm_connect", "ehmc_comm_destroy", "ehmc_hmc_run_ensemble",
 )
+COMM_HANDLE_BYTES = 64
+COMM_MAX_RANKS = 16
 
 
 class EhmcError(RuntimeError):
@@ -73,6 +76,22 @@ class Dynamic(ctypes.Structure):
         ("iteration", ctypes.c_uint64),
         ("updates", ctypes.c_uint64),
         ("row", ctypes.c_uint64),
+    ]
+
+
+class AdaptArgs(ctypes.Structure):
+    """struct ehmc_adapt_args (include/ehmc.h)."""
+
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("adaptIterations", ctypes.c_int32),
+        ("targetAccept", ctypes.c_double),
+        ("gain0", ctypes.c_double),
+        ("kappa", ctypes.c_double),
+        ("maxMove", ctypes.c_double),
+        ("minStep", ctypes.c_double),
+        ("maxStep", ctypes.c_double),
+        ("numParticlesTotal", ctypes.c_double),
     ]
 
 
@@ -115,6 +134,12 @@ def load():
             "ehmc_hmc_iter": [vp, vp, vp, vp, vp, ctypes.POINTER(HmcArgs), vp, vp, vp, vp, vp],
             "ehmc_hmc_run": [vp, vp, vp, vp, ctypes.POINTER(HmcArgs), ci, vp, vp, ctypes.c_int64, vp, vp],
             "ehmc_adapt_step": [vp, vp, cd, cd, cd, cd, cd, cd, cd, u64, vp, vp, u64, vp, vp, vp],
+            "ehmc_comm_create": [vp, ci, ci, ctypes.POINTER(vp)],
+            "ehmc_comm_handle": [vp, vp],
+            "ehmc_comm_connect": [vp, vp],
+            "ehmc_comm_destroy": [vp],
+            "ehmc_hmc_run_ensemble": [vp, vp, vp, vp, ctypes.POINTER(HmcArgs), ci, ctypes.POINTER(AdaptArgs), vp, vp, vp,
+                                      vp, vp, ctypes.c_int64, ctypes.c_int64, vp],
         }
         for name, args in sigs.items():
             fn = getattr(lib, name)
@@ -343,6 +368,58 @@ def hmc_run(ctx, pot, q, mass, args, num_iterations, samples=None, momenta=None,
     vs, vmo, va = dl(samples), dl(momenta), dl(accepted)
     check(ctx.lib.ehmc_hmc_run(ctx.handle, pot.handle, vq.ptr, vm.ptr, ctypes.byref(args), int(num_iterations), _p(vs),
                                _p(vmo), int(sample_offset), _p(va), stream))
+
+
+class Comm:
+    """ehmc_comm: this rank's mailbox plus the mapped mailboxes of its peers (CUDA IPC over NVLink)."""
+
+    def __init__(self, ctx, rank, world):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        h = ctypes.c_void_p()
+        check(ctx.lib.ehmc_comm_create(ctx.handle, self.rank, self.world, ctypes.byref(h)))
+        self.handle = h
+
+    def local_handle(self):
+        buf = (ctypes.c_ubyte * COMM_HANDLE_BYTES)()
+        check(self.ctx.lib.ehmc_comm_handle(self.handle, buf))
+        return bytes(buf)
+
+    def connect(self, handles):
+        """handles: world x COMM_HANDLE_BYTES bytes, ordered by rank."""
+        blob = b"".join(handles) if not isinstance(handles, (bytes, bytearray)) else bytes(handles)
+        if len(blob) != self.world * COMM_HANDLE_BYTES:
+            raise ValueError("need one handle per rank")
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self.ctx.lib.ehmc_comm_connect(self.handle, buf))
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self.ctx.lib.ehmc_comm_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+
+def make_adapt_args(num_particles_total, adapt_iterations, target=0.8, gain0=1.5, kappa=0.5, max_move=0.7,
+                    min_step=1e-6, max_step=1e3):
+    a = AdaptArgs()
+    a.struct_size = ctypes.sizeof(AdaptArgs)
+    a.adaptIterations = int(adapt_iterations)
+    a.targetAccept, a.gain0, a.kappa, a.maxMove = float(target), float(gain0), float(kappa), float(max_move)
+    a.minStep, a.maxStep = float(min_step), float(max_step)
+    a.numParticlesTotal = float(num_particles_total)
+    return a
+
+
+def hmc_run_ensemble(ctx, pot, q, mass, args, num_iterations, adapt, state, comm=None, history=None, moments=None,
+                     trace=None, trace_particles=0, trace_offset=0, stream=None):
+    vq, vm, vs = dl(q), dl(mass), dl(state)
+    vh, vmo, vt = dl(history), dl(moments), dl(trace)
+    check(ctx.lib.ehmc_hmc_run_ensemble(ctx.handle, pot.handle, vq.ptr, vm.ptr, ctypes.byref(args), int(num_iterations),
+                                        ctypes.byref(adapt), None if comm is None else comm.handle, vs.ptr, _p(vh),
+                                        _p(vmo), _p(vt), int(trace_particles), int(trace_offset), stream))
 
 
 def philox_fill(ctx, z=None, u=None, seed=0, iteration=0, particle_offset=0, stream=None):

@@ -14,6 +14,7 @@
 
 #include "host_defs.h"
 #include "k_misc.cuh"
+#include "k_small_ens.cuh"
 
 // NVTX range around a C-ABI call (the reference's only tracing is cProfile around integrate())
 struct NvtxRange {
@@ -158,6 +159,7 @@ extern "C" int ehmc_ctx_destroy(ehmc_ctx* c) {
   c->pstats.release();
   c->tc_prof_buf.release();
   c->overflow.release();
+  c->ens_ctl.release();
   for (int k = 0; k < 2; ++k) {
     c->ep_grad[k].release();
     c->ep_energy[k].release();
@@ -1026,6 +1028,94 @@ extern "C" int ehmc_hmc_run(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* 
                                 sampleOffset, S, accepted, st);
   return hmc_run_typed<double>(ctx, pot, v, a, numIterations, samples_out ? &vs : nullptr, momenta_out ? &vm : nullptr,
                                sampleOffset, S, accepted, st);
+}
+
+// ---------------------------------------------------------------------------
+// the adaptive ensemble run in one launch
+// ---------------------------------------------------------------------------
+extern "C" int ehmc_hmc_run_ensemble(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* q, const DLTensor* mass,
+                                     const ehmc_hmc_args* a, int numIterations, const ehmc_adapt_args* ad,
+                                     ehmc_comm* comm, DLTensor* state, DLTensor* history, DLTensor* moments,
+                                     DLTensor* trace, int64_t traceParticles, int64_t traceOffset, void* stream) {
+  if (ctx) ctx->ep_valid = false;
+  NvtxRange nvtx_range("ehmc_hmc_run_ensemble");
+  const char* fn = "ehmc_hmc_run_ensemble";
+  CallViews v;
+  TRY(common_checks(ctx, pot, q, mass, &v, fn));
+  if (!a || !ad || !state) return fail(EHMC_ERR_INVALID, "%s: args, adapt and state are required", fn);
+  if (a->struct_size != sizeof(ehmc_hmc_args) || ad->struct_size != sizeof(ehmc_adapt_args))
+    return fail(EHMC_ERR_INVALID, "%s: struct_size mismatch", fn);
+  if (a->numSteps < 0 || numIterations < 0 || traceParticles < 0 || traceOffset < 0)
+    return fail(EHMC_ERR_INVALID, "%s: negative count", fn);
+  if (a->integrator != EHMC_LEAPFROG) return fail(EHMC_ERR_UNSUPPORTED, "%s: leapfrog only", fn);
+  if (a->dynamic != nullptr) return fail(EHMC_ERR_UNSUPPORTED, "%s: args.dynamic is not supported here", fn);
+  const bool small = pot->family == EHMC_FAMILY_DIAG_GAUSSIAN || pot->family == EHMC_FAMILY_FUNNEL ||
+                     pot->family == EHMC_FAMILY_COIN_TOSS || (pot->family == EHMC_FAMILY_DENSE_GAUSSIAN && pot->D <= 16);
+  if (v.q.host || !small)
+    return fail(EHMC_ERR_UNSUPPORTED, "%s: device tensors and a small-D potential family are required", fn);
+  if (!(ad->numParticlesTotal > 0) || !(ad->minStep > 0) || !(ad->maxStep >= ad->minStep))
+    return fail(EHMC_ERR_INVALID, "%s: bad adaptation scalars", fn);
+  if (comm && (comm->ctx != ctx || !comm->connected)) return fail(EHMC_ERR_INVALID, "%s: communicator not connected on this context", fn);
+  View vs, vh, vm, vt;
+  TRY(parse_float(state, "state", 1, 64, &vs));
+  if (vs.host || vs.shape[0] != 4) return fail(EHMC_ERR_INVALID, "%s: state must be a device float64[4]", fn);
+  if (history) {
+    TRY(parse_float(history, "history", 2, 64, &vh));
+    if (vh.host || vh.shape[1] != 4 || vh.ld != 4 || vh.shape[0] < numIterations)
+      return fail(EHMC_ERR_INVALID, "%s: history must be a contiguous device float64[>= numIterations, 4]", fn);
+  }
+  if (moments) {
+    TRY(parse_float(moments, "moments", 1, 64, &vm));
+    if (vm.host || vm.shape[0] != 2 * v.D) return fail(EHMC_ERR_INVALID, "%s: moments must be a device float64[2D]", fn);
+  }
+  long long S = 0;
+  if (trace) {
+    TRY(parse_float(trace, "trace", 2, v.bits, &vt));
+    if (vt.host || vt.shape[0] != v.D * traceParticles || vt.ld != vt.shape[1] || traceParticles > v.P ||
+        traceOffset + numIterations > vt.shape[1])
+      return fail(EHMC_ERR_INVALID, "%s: trace must be a contiguous device [D*traceParticles, S] view with room for the iterations", fn);
+    S = vt.shape[1];
+  }
+  if (numIterations == 0 || v.P == 0) return EHMC_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto run = [&](auto tag) -> int {
+    typedef decltype(tag) T;
+    IterArgs<T> A = base_args<T>(v, a->stepSize, a->stepSizeSq, a->numSteps);
+    A.flags = a->flags;
+    A.kB = a->boltzmann;
+    A.temp = a->temperature;
+    A.pscale = std::sqrt(a->boltzmann * a->temperature);
+    A.seed = a->seed;
+    A.iter = a->iteration;
+    A.offset = a->particleOffset;
+    EnsRunArgs<T> R;
+    memset(&R, 0, sizeof(R));
+    R.nIter = numIterations;
+    R.adaptIters = std::max(0, std::min(numIterations, ad->adaptIterations));
+    R.target = ad->targetAccept;
+    R.gain0 = ad->gain0;
+    R.kappa = ad->kappa;
+    R.maxMove = ad->maxMove;
+    R.logLo = std::log(ad->minStep);
+    R.logHi = std::log(ad->maxStep);
+    R.Ptot = ad->numParticlesTotal;
+    R.state = reinterpret_cast<double*>(vs.data);
+    R.history = history ? reinterpret_cast<double*>(vh.data) : nullptr;
+    R.moments = moments ? reinterpret_cast<double*>(vm.data) : nullptr;
+    R.trace = (trace && traceParticles > 0) ? reinterpret_cast<T*>(vt.data) : nullptr;
+    R.ntrace = traceParticles;
+    R.S = S;
+    R.s0 = traceOffset;
+    R.rank = comm ? comm->rank : 0;
+    R.world = comm ? comm->world : 1;
+    R.peers = comm ? comm->peers_dev : nullptr;
+    R.seq0 = comm ? comm->seq : 0;
+    return run_small_ens<T>(ctx, pot, A, R, st);
+  };
+  const int rc = v.bits == 32 ? run(float()) : run(double());
+  if (rc == EHMC_OK && comm) comm->seq += (unsigned long long)numIterations;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------

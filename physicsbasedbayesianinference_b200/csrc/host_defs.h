@@ -68,6 +68,7 @@ struct ehmc_ctx {
   long long host_chunk_bytes = 32LL << 20;
   int tc_prof = 0;                // 1: record a clock64 trace of CTA 0 into tc_prof_buf (64 x int64)
   DevBuf tc_prof_buf;
+  DevBuf ens_ctl;                 // control block of the fused ensemble run: step-size schedule, tickets, partial rows
   DevBuf overflow;                // unsigned: integrate() rows that saturated the fp16 operand range of k_dense_tc3
   int tc_debug = 0;               // profiling knobs of the tensor-core kernels (see DenseTcArgs::dbg)
 };
@@ -99,6 +100,19 @@ struct ehmc_potential {
   int N = 0;           // logistic: data rows
 };
 
+// peer-memory mailboxes of the fused ensemble run (comm.cu)
+struct ehmc_comm {
+  ehmc_ctx* ctx = nullptr;
+  int rank = 0, world = 1;
+  size_t bytes = 0;
+  void* mailbox = nullptr;                       // [2][world][ENS_MB_STRIDE] doubles, local
+  double* peers[EHMC_COMM_MAX_RANKS] = {};       // every rank's mailbox as mapped into this process
+  bool opened[EHMC_COMM_MAX_RANKS] = {};
+  double** peers_dev = nullptr;                  // device copy of peers[]
+  bool connected = false;
+  unsigned long long seq = 0;                    // iterations reduced so far (identical on all ranks)
+};
+
 // ---- launchers (explicitly instantiated for float / double in inst_*.cu) ----------
 namespace ehmc {
 
@@ -111,6 +125,11 @@ int launch_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int
 // getSamples' whole loop in one launch (small-D families, Philox draws)
 template <typename T>
 int run_small(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, const RunArgs<T>& R, cudaStream_t st);
+// the adaptive ensemble run as one persistent launch (k_small_ens.cuh)
+template <typename T>
+struct EnsRunArgs;
+template <typename T>
+int run_small_ens(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, const EnsRunArgs<T>& R, cudaStream_t st);
 // dense Gaussian, 16 < D <= 128
 template <typename T>
 int launch_dense(ehmc_ctx* c, const ehmc_potential* p, const IterArgs<T>& A, int integ, bool hmc, cudaStream_t st);

@@ -373,7 +373,8 @@ __device__ __forceinline__ void block_partials(double* out_row, int D, const dou
 // consumed the loaded values at once, so every warp waited for HBM BEFORE its ~300 instructions of Philox work
 // instead of behind them (profiles/r01_k1_dbg_probe.txt, r01_ncu_full_k1l4_before.txt).
 template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT>
-__device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& pot, double* k1_smem) {
+__device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& pot, double* k1_smem, unsigned blk,
+                                             unsigned nblk) {  // this CTA is number blk of nblk walking the particles
   const int Dn = EXACT ? DT : A.D;
   constexpr int NA = 2 * DT + 3;
   const bool want_stats = HMC && A.partials != nullptr;
@@ -383,9 +384,9 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
 #pragma unroll 1
     for (int j = 0; j < NA; ++j) sacc[j * K1_THREADS] = 0.0;
   }
-  const long long stride = (long long)gridDim.x * K1_THREADS;
+  const long long stride = (long long)nblk * K1_THREADS;
 
-  for (long long base = (long long)blockIdx.x * K1_THREADS; base < A.P; base += stride) {
+  for (long long base = (long long)blk * K1_THREADS; base < A.P; base += stride) {
     const long long i = base + threadIdx.x;
     const bool active = i < A.P;
     const long long ic = active ? i : 0;  // inactive threads shadow particle 0, never store
@@ -476,7 +477,7 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
     }
   }
   if (want_stats)
-    block_partials<K1_THREADS, DT>(A.partials + (size_t)blockIdx.x * (2 * Dn + 3), Dn, k1_smem, sred);
+    block_partials<K1_THREADS, DT>(A.partials + (size_t)blk * (2 * Dn + 3), Dn, k1_smem, sred);
 }
 
 // Two kernels (picked on the host by D == DT) rather than one with both bodies: a kernel gets the register
@@ -486,7 +487,7 @@ template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT>
 __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, const Pot pot) {
   extern __shared__ double k1_smem[];
   const IterArgs<T> A = resolve_dynamic(Ain);
-  k_small_body<T, DT, Pot, INTEG, HMC, EXACT>(A, pot, k1_smem);
+  k_small_body<T, DT, Pot, INTEG, HMC, EXACT>(A, pot, k1_smem, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

@@ -52,6 +52,44 @@ class StatsReducer:
             self.work = None
 
 
+def exchange_handles(local, group=None, device=None):
+    """All-gather one fixed-size opaque handle (bytes) per rank; returns the list ordered by rank.  Works with
+    NCCL (pass the CUDA `device`) and gloo (CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    mine = torch.frombuffer(bytearray(local), dtype=torch.uint8).clone()
+    if device is not None:
+        mine = mine.to(device)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+
+_comms = {}
+
+
+def ensemble_comm(ctx, group=None, device=None):
+    """The ehmc communicator (peer-memory mailboxes) of this process for `group`, created and connected on first
+    use: the in-kernel all-reduce of the fused ensemble run (ehmc_hmc_run_ensemble).  None for a single rank."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    key = (id(ctx), id(group))
+    comm = _comms.get(key)
+    if comm is None:
+        from . import _lib
+
+        nccl = dist.get_backend(group) == "nccl"
+        comm = _lib.Comm(ctx, dist.get_rank(group), dist.get_world_size(group))
+        comm.connect(exchange_handles(comm.local_handle(), group, device if nccl else None))
+        dist.barrier(group)  # every rank has mapped every mailbox before anyone launches
+        _comms[key] = comm
+    return comm
+
+
 class StepSizeAdapter:
     """Ensemble-based step-size adaptation (build-defined; the reference has none, SURVEY.md
     section 2).  The acceptance statistic is an average over the WHOLE ensemble (all GPUs), so a

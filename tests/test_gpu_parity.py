@@ -1224,7 +1224,7 @@ def test_run_device_adaptation_matches_host_adaptation(E, case):
         return ens, E.HMC(ens, L * 0.02 + 1e-9, 0.02, None, potential=pot, seed=5, bugCompat=False)
 
     ens_h, hmc_h = fresh()
-    rh = hmc_h.run(S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=20, keepNumSteps=True)
+    rh = hmc_h.run(S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=20, keepNumSteps=True, fused=False)
     outs = {}
     for graph in (False, True):
         ens_d, hmc_d = fresh()
@@ -1242,6 +1242,119 @@ def test_run_device_adaptation_matches_host_adaptation(E, case):
     assert torch.equal(outs[False], outs[True])
     # and the chain itself follows the host-adapted one (step sizes agree to ~1e-7 relative)
     assert rel_err(outs[True].cpu().numpy(), ens_h.q.cpu().numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("case", ["funnel10", "diag3", "dense8", "coin2"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_run_fused_matches_host_loop(E, case, dt):
+    """HMC.run(fused=True): trajectory kernel, statistics, step-size update in ONE persistent cooperative launch
+    (ehmc_hmc_run_ensemble) against the iteration-by-iteration host loop: same Philox stream, same
+    one-iteration-stale Robbins-Monro schedule.  The statistics are float64 sums in a different (fixed) order, so the
+    step sizes agree to 1e-12 and the chains to the float rounding of h."""
+    import torch
+
+    P, S, L = 5000, 31, 5
+    rng = np.random.RandomState(22)
+    if case == "funnel10":
+        D, pot, h0 = 10, E.FunnelPotential(10, 3.0), 0.02
+    elif case == "diag3":
+        D, pot, h0 = 3, E.HarmonicPotential([1.0, 4.0, 0.25]), 0.1
+    elif case == "coin2":
+        D, pot, h0 = 2, E.CoinTossPotential([10, 15], [20, 20]), 0.01
+    else:
+        D = 8
+        A = rng.standard_normal((D, D))
+        pot, h0 = E.GaussianPotential(precision=A @ A.T / D + np.eye(D), mean=rng.standard_normal(D)), 0.05
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    q0 = rng.uniform(0.3, 0.7, (D, P)) if case == "coin2" else rng.standard_normal((D, P))
+    q0 = torch.tensor(q0, dtype=tdt, device="cuda")
+    ctx = E._lib.Context.get()
+
+    def fresh():
+        ens = E.Ensemble(D, P, dtype=dt, device="cuda", seed=5)
+        ens.q.copy_(q0)
+        return ens, E.HMC(ens, L * h0 + 1e-9, h0, None, potential=pot, seed=5, bugCompat=False)
+
+    ens_h, hmc_h = fresh()
+    rh = hmc_h.run(S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=24, keepNumSteps=True, fused=False,
+                   traceParticles=7)
+    ens_f, hmc_f = fresh()
+    n0 = ctx.launch_count()
+    rf = hmc_f.run(S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=24, keepNumSteps=True, traceParticles=7)
+    assert rf.get("fused") and ctx.launch_count() - n0 == 1  # the default picks the fused path: ONE launch
+    assert hmc_f.iteration == S and hmc_f.integrator.numSteps == L
+    np.testing.assert_allclose(rf["stepSize"], rh["stepSize"], rtol=1e-12)
+    assert rf["stepSize"][0] == h0 and rf["stepSize"][1] == h0 and rf["stepSize"][2] != h0  # one iteration stale
+    assert rf["stepSize"][26] == rf["stepSize"][30]  # adaptation stops after adaptIterations
+    assert abs(hmc_f.stepSize - hmc_h.stepSize) <= 1e-12 * hmc_h.stepSize
+    np.testing.assert_array_equal(rf["acceptRate"], rh["acceptRate"])
+    np.testing.assert_allclose(rf["meanAcceptProb"], rh["meanAcceptProb"], rtol=1e-12)
+    np.testing.assert_allclose(rf["meanH"], rh["meanH"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(rf["mean"].numpy(), rh["mean"].numpy(), rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(rf["var"].numpy(), rh["var"].numpy(), rtol=1e-10)
+    def same_chain(a, b):
+        if dt == np.float32:
+            return torch.equal(a, b)  # (float) h is the same number: identical bits
+        # float64: exp(log h) on the device and in libm differ in the last bit, and the chain follows h exactly
+        return bool(np.allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-9, atol=1e-11, equal_nan=True))
+
+    assert same_chain(ens_f.q, ens_h.q)
+    assert same_chain(rf["trace"], rh["trace"])
+    # a second call continues the chain (Philox iteration counter, adapted step size) without adaptation
+    r2h = hmc_h.run(5, 1 / KB, fused=False)
+    r2f = hmc_f.run(5, 1 / KB)
+    assert same_chain(ens_f.q, ens_h.q)
+    np.testing.assert_allclose(r2f["stepSize"], r2h["stepSize"], rtol=1e-12)  # device exp() vs libm: 1 ulp
+
+
+def test_run_fused_two_ranks(E, tmp_path):
+    """The in-kernel all-reduce of the fused ensemble run: two processes (sharing this GPU: CUDA IPC mailboxes work
+    within one device and the time-sliced persistent kernels still make progress), each with half of the ensemble,
+    against one process with all of it.  Philox ids are global, so the ensemble statistics -- and with them the
+    adapted step sizes -- agree to the rounding of the float64 sums, and every shard walks the single-process
+    chain."""
+    import socket
+    import subprocess
+    import sys
+
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fused_rank_worker.py")
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+
+    def launch(rank, world, out):
+        return subprocess.Popen([sys.executable, worker, "--rank", str(rank), "--world", str(world), "--port", str(port),
+                                 "--out", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+    single = str(tmp_path / "single.npz")
+    p = launch(0, 1, single)
+    out, _ = p.communicate(timeout=300)
+    assert p.returncode == 0, out
+    procs = [launch(r, 2, str(tmp_path / f"rank{r}.npz")) for r in range(2)]
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            for k in procs:
+                k.kill()
+            pytest.fail("the two-rank fused run did not finish (mailbox all-reduce stuck)")
+        outs.append(o)
+        assert p.returncode == 0, o
+    ref = np.load(single)
+    shards = [np.load(str(tmp_path / f"rank{r}.npz")) for r in range(2)]
+    for sh in shards:
+        np.testing.assert_allclose(sh["stepSize"], ref["stepSize"], rtol=1e-12)
+        np.testing.assert_array_equal(sh["acceptRate"], ref["acceptRate"])
+        np.testing.assert_allclose(sh["meanH"], ref["meanH"], rtol=1e-12)
+        np.testing.assert_allclose(sh["var"], ref["var"], rtol=1e-10)
+        assert abs(sh["final"] - ref["final"]) <= 1e-12 * ref["final"]
+        np.testing.assert_array_equal(sh["q"], ref["q"][:, int(sh["lo"]):int(sh["hi"])])
+    # both ranks hold the SAME reduced numbers bit for bit (rank-ordered sum)
+    np.testing.assert_array_equal(shards[0]["stepSize"], shards[1]["stepSize"])
+    np.testing.assert_array_equal(shards[0]["meanH"], shards[1]["meanH"])
+    np.testing.assert_array_equal(shards[0]["trace"], ref["trace"])
 
 
 # ---------------------------------------------------------------------------
