@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the ensemble-HMC leapfrog hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c5|c5l4|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c1|c3|c4|c5|c5l4]
+                    [--no-others] [--no-sustained] [--no-e2e] [--no-cpu-baseline] [--ess-iters I]
 
-Workload at every N: BASELINE config 2 -- 100-D correlated Gaussian (dense precision
-Lambda = A A^T / D + I), ensemble of 2^20 particles, L = 50 leapfrog steps per HMC
-iteration, float32, Philox in-kernel RNG, synthetic data.  A "step" is ONE HMC
-iteration of the whole ensemble (momentum refresh + L leapfrog steps + Metropolis),
-i.e. P*L particle-leapfrog-steps in one fused kernel launch.  The 2^20 particles are
+Headline workload at every N: BASELINE config 2 -- 100-D correlated Gaussian (dense precision
+Lambda = A A^T / D + I), ensemble of 2^20 particles, L = 50 leapfrog steps per HMC iteration, float32 state,
+Philox in-kernel RNG, synthetic data.  A "step" is ONE HMC iteration of the whole ensemble (momentum refresh +
+L leapfrog steps + Metropolis), i.e. P*L particle-leapfrog-steps in one fused kernel launch.  The 2^20 particles are
 sharded over the N ranks (strong scaling, no data-path collective).
 
-value  : particle-leapfrog-steps/s with the ensemble resident in HBM (device path).
-e2e    : the same metric through the public drop-in API on HOST buffers
-         (HMC.step on a host-backed Ensemble -> ehmc_hmc_iter host path): every step
-         copies q from pinned host memory, runs the kernel and copies q (+accept) back.
+value     : particle-leapfrog-steps/s with the ensemble resident in HBM (device path), K timed steps.
+sustained : the same loop for >= 700 iterations (>= 2 s at one GPU) with >= 100 NVML samples: the number the roofline
+            claims in DESIGN.md quote (`value` over K = 20 steps is a burst number).
+e2e       : the same metric through the public drop-in API on HOST buffers (HMC.step on a host-backed Ensemble ->
+            ehmc_hmc_iter host path): every step copies q from pinned host memory, runs the kernel, copies q back.
+other_configs : short legs of the other BASELINE configs on the same ranks (c1 at one GPU only), each with value,
+            ms_per_step, roofline and clocks; c5 / c5l4 run the fused adaptive ensemble run whose statistics
+            all-reduce happens inside the kernel over NVLink.
+cpu_baseline     : the NumPy float64 oracle port on the host cores (bounded sample), timed in this run.
+cpu_baseline_ref : the UNMODIFIED reference under the jax.numpy stand-in at config 1, timed in the build container
+            (it is Python and cannot travel to the GPU box; profiles/r02_ref_standin_c1.json).
 """
 from __future__ import annotations
 
@@ -36,7 +43,7 @@ SEED = 20221018
 CONFIGS = {
     # name: D, P, L, h, description
     "c2": dict(D=100, P=1 << 20, L=50, h=0.05, desc="config2: 100-D dense-precision Gaussian, P=2^20, L=50"),
-    "c5": dict(D=10, P=1 << 22, L=20, h=0.05, desc="config5: Neal's funnel 10-D, P=2^22, L=20"),
+    "c5": dict(D=10, P=1 << 22, L=20, h=0.05, desc="config5: Neal's funnel 10-D, P=2^22, L=20, ensemble step-size adaptation"),
     "c5l4": dict(D=10, P=1 << 22, L=4, h=0.05, desc="config5 HBM-bound variant: funnel 10-D, P=2^22, L=4"),
     "c1": dict(D=2, P=1024, L=20, h=0.05, desc="config1: 2-D isotropic Gaussian, P=1024, L=20"),
     "c3": dict(D=256, P=65536, L=10, h=0.01, N=100000,
@@ -44,6 +51,8 @@ CONFIGS = {
     "c4": dict(D=3 * 4096, P=1024, L=10, h=0.01, B=4096,
                desc="config4: pairwise gravitational N-body, 4096 bodies x 3-D per particle, P=1024, L=10, eps=0.05"),
 }
+OTHER_STEPS = {"c1": 50, "c3": 3, "c4": 4, "c5": 200, "c5l4": 200}
+LOGI_PREC = os.environ.get("EHMC_LOGISTIC_PRECISION", "fp16x3")
 
 
 def flops_per_unit(name, D):
@@ -81,7 +90,7 @@ def make_logistic_data(D, N):
 def make_potential(E, name, D):
     if name == "c3":
         X, y = make_logistic_data(D, CONFIGS["c3"]["N"])
-        return E.LogisticPotential(X, y, 1.0, precision=os.environ.get("EHMC_LOGISTIC_PRECISION", "fp16x3"))
+        return E.LogisticPotential(X, y, 1.0, precision=LOGI_PREC)
     if name == "c4":
         B = D // 3
         return E.NBodyPotential(np.ones(B) / B, G=1.0, eps=0.05)
@@ -131,9 +140,10 @@ class ClockSampler:
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
         except Exception:
             self.nvml = None
-            return
+            return self
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
+        return self
 
     def _run(self):
         n = self.nvml
@@ -148,7 +158,7 @@ class ClockSampler:
                 self.samples.append((sm, pw, rs))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.004)
 
     def stop(self):
         if self.nvml is None:
@@ -169,7 +179,8 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
                 "sm_max_mhz": float(mx) if mx else None,
                 "power_w_max": max(x[1] for x in self.samples) if self.samples else None,
-                "samples": len(sm), "reasons": sorted(reasons), "source": "nvml, 5 ms sleep between queries, during the timed region"}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvml, 4 ms sleep between queries, during the timed region"}
 
     def _smi_once(self):
         try:
@@ -205,23 +216,33 @@ def cpu_port_rate(name, cfg, sample_particles, iters):
     return sample_particles * L / float(np.median(times)), times
 
 
-def run_reference_arm(args, cfg, rank):
+CPU_SAMPLE = {"c2": 1 << 16, "c3": 64, "c4": 1}
+
+
+def config_dict(cfg, D, P, L, h, Pl, world, L_mean=None):
+    return {"workload": cfg["desc"], "D": D, "P": P, "L": L, "L_executed_mean": L if L_mean is None else L_mean, "h": h,
+            "particles_per_gpu": Pl, "rng": "philox in-kernel",
+            "l2": "inputs_exceed_l2" if D * Pl * 4 > 126e6 else "resident",
+            "parallelism": f"particle-shard x{world}, no data-path collective"}
+
+
+def run_reference_arm(args, cfg, rank, world):
     if rank != 0:
         return
     name = args.config
-    sample = min(cfg["P"], {"c2": 1 << 14, "c3": 64, "c4": 1}.get(name, 1 << 17))
-    rng_iters = args.warmup + args.steps
-    rate, times = cpu_port_rate(name, cfg, sample, rng_iters)
+    sample = min(cfg["P"], CPU_SAMPLE.get(name, 1 << 17))
+    rate, times = cpu_port_rate(name, cfg, sample, args.warmup + args.steps)
     times = times[args.warmup:]
     ms = 1e3 * float(np.mean(times))
     value = sample * cfg["L"] / (ms * 1e-3)
     threads = os.cpu_count()
+    D, P, L, h = cfg["D"], cfg["P"], cfg["L"], cfg["h"]
     line = {
         "impl": "reference", "metric": "particle-leapfrog-steps/sec", "value": value,
         "unit": "particle-leapfrog-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": cfg["desc"], "D": cfg["D"], "P": cfg["P"], "L": cfg["L"], "h": cfg["h"]},
+        "config": config_dict(cfg, D, P, L, h, (P + world - 1) // world, world),
         "cpu_baseline": {"value": value, "unit": "particle-leapfrog-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} of {cfg['P']} particles per step (NumPy float64 oracle port of "
                                    "src/integrator.py:105-120 + src/HMC.py:154-176, BLAS threads = host cores); "
@@ -233,8 +254,166 @@ def run_reference_arm(args, cfg, rank):
 
 
 # ---------------------------------------------------------------------------
-# main arm
+# roofline of one measured leg
 # ---------------------------------------------------------------------------
+def roofline(name, D, Pl, L, kern_ms, fp32_peak, peaks, ctx, world, sustained=False):
+    fl = flops_per_unit(name, D)
+    ach_tf = Pl * L * fl / (kern_ms * 1e-3) / 1e12
+    by = bytes_per_particle_iter(D) * Pl
+    ach_gbs = by / (kern_ms * 1e-3) / 1e9
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
+    info = ctx.device_info()
+    nominal_fp32 = info["sm_count"] * 128 * 2 * info["sm_clock_mhz"] * 1e6 / 1e12
+    dense_tc = name == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1"
+    logi_tc = name == "c3" and LOGI_PREC in ("bf16", "fp16x3", "auto")
+    compute_bound = ach_tf / fp32_peak > ach_gbs / hbm_peak
+    if dense_tc:
+        # the gradient GEMM runs on tcgen05 as a 3-pass fp16 split (float32 accuracy from 11-bit operands):
+        # tensor-pipe roofline against the measured dense bf16 peak (burst for a short timed region, sustained for
+        # the long one).  Executed tensor flops per algorithmic flop = 3 passes x padding to K = N = 112.
+        key = "bf16_tflops_sustained" if sustained else "bf16_tflops"
+        tpeak = peaks.get(key, peaks.get("bf16_tflops", 1590.0))
+        kp = (D + 15) // 16 * 16
+        exec_factor = 3.0 * kp * kp / (D * D)
+        roof = {"bound": "tensor", "achieved": ach_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_tf / tpeak,
+                "traffic": None, "peak_source": f"MEASURED_PEAKS.json {key}" if key in peaks else "fallback",
+                "flops_per_unit": fl, "units_per_launch": Pl * L,
+                "executed_tensor_tflops": ach_tf * exec_factor, "formulation_ceiling_frac": 1.0 / exec_factor,
+                "note": "algorithmic fp32 flops (2 D^2 + 7 D per particle-step) over the measured bf16 peak; the "
+                        f"3xFP16 split executes {exec_factor:.2f}x those flops (3 passes x padding to K = N = {kp}), "
+                        "so `frac` cannot exceed formulation_ceiling_frac"}
+    elif logi_tc:
+        tpeak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+        split = LOGI_PREC != "bf16"
+        roof = {"bound": "tensor", "achieved": ach_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_tf / tpeak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside "
+                "a long step)", "flops_per_unit": fl, "units_per_launch": Pl * L,
+                "executed_tensor_tflops": ach_tf * (3.0 if split else 1.0),
+                "formulation_ceiling_frac": 1.0 / 3.0 if split else 1.0,
+                "note": ("tcgen05 GEMM chain at float32 accuracy (trajectories within 1e-5 of the float64 oracle at "
+                         "full size): every operand a 2-term fp16 split, 3 MMA passes per GEMM = 3x the algorithmic "
+                         "flops, so `frac` cannot exceed formulation_ceiling_frac" if split else
+                         "bf16 tcgen05 GEMM chain, operands rounded to bf16: OUTSIDE the 1e-5 tolerance, opt-in only") +
+                        "; kernel_ms is the whole iteration (L gradient launches + kick/drift launches)"}
+    elif compute_bound:
+        roof = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ach_tf / fp32_peak, "traffic": None,
+                "peak_source": "measured in this run (ehmc_measure_fp32_peak, register-only FFMA kernel); "
+                               f"nominal {nominal_fp32:.1f} = SMs*128*2*max clock",
+                "flops_per_unit": fl, "units_per_launch": Pl * L}
+    else:
+        roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                "bytes_per_unit": bytes_per_particle_iter(D) / L, "units_per_launch": Pl * L}
+    for fname in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", fname))).get(name)
+        except (OSError, ValueError):
+            tr = None
+        if tr and world == 1:
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr["source"]
+            for k_src, k_dst in (("tensor_pipe_active_pct", "ncu_tensor_pipe_active_pct"),
+                                 ("issue_active_pct", "ncu_issue_active_pct"), ("fma_pipe_active_pct", "ncu_fma_pipe_active_pct")):
+                if tr.get(k_src) is not None:
+                    roof[k_dst] = tr[k_src]
+            break
+    roof["algorithmic_bytes_per_launch"] = by
+    roof["kernel_ms"] = kern_ms
+    roof["other"] = {"hbm_GBps": ach_gbs, "hbm_frac": ach_gbs / hbm_peak, "fp32_TFLOPs": ach_tf,
+                     "fp32_frac": ach_tf / fp32_peak}
+    return roof
+
+
+def dtype_of(name):
+    if name == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1":
+        return "f32 (3xFP16 tensor-core split, fp32 accumulate)"
+    if name == "c3":
+        return {"bf16": "f32 state, bf16 tensor-core gradient GEMMs (fp32 accumulate)",
+                "fp32": "f32"}.get(LOGI_PREC, "f32 (3xFP16 tensor-core split of both gradient GEMMs, fp32 accumulate)")
+    return "f32"
+
+
+# ---------------------------------------------------------------------------
+# one device-resident leg of one config
+# ---------------------------------------------------------------------------
+class Leg:
+    """Ensemble + driver of one config on this rank, and its timed loop."""
+
+    def __init__(self, E, name, rank, world, dev):
+        self.E, self.name, self.rank, self.world, self.dev = E, name, rank, world, dev
+        cfg = CONFIGS[name]
+        self.cfg = cfg
+        self.D, self.P, self.L, self.h = cfg["D"], cfg["P"], cfg["L"], cfg["h"]
+        self.p_lo = rank * self.P // world
+        self.Pl = (rank + 1) * self.P // world - self.p_lo
+        self.pot = make_potential(E, name, self.D)
+        self.ens = E.Ensemble(self.D, self.Pl, dtype=np.float32, device=dev, seed=SEED, particleOffset=self.p_lo)
+        self.ens.setPosition(1.0)
+        self.hmc = E.HMC(self.ens, self.L * self.h + 1e-9, self.h, None, potential=self.pot, seed=SEED, bugCompat=False)
+        assert self.hmc.integrator.numSteps == self.L
+        self.adaptive = name.startswith("c5")  # config 5: ensemble statistics all-reduced every iteration
+        self.run_out = None
+
+    def loop(self, n, group):
+        """n iterations enqueued on the current stream (config 5: ONE fused launch with the in-kernel all-reduce)."""
+        if n <= 0:
+            return
+        if self.adaptive:
+            self.run_out = self.hmc.run(n, 1 / KB, adapt=True, group=group, keepNumSteps=True)
+        else:
+            for _ in range(n):
+                self.hmc.step(1 / KB, reuseEndpoint=True)  # q is only touched by the step itself
+
+    def timed(self, steps, warmup, group, barrier, ctx, sample_clocks=True):
+        import torch
+        import torch.distributed as dist
+
+        self.loop(warmup, group)
+        barrier()
+        sampler = ClockSampler(self.dev.index).start() if (self.rank == 0 and sample_clocks) else None
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.loop(steps, group)
+        e1.record()
+        barrier()
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        # leapfrog steps actually executed per iteration (fixed here: the adaptive legs keep numSteps)
+        L_mean = float(np.mean(self.run_out["numSteps"])) if self.adaptive else float(self.L)
+        return dict(total_ms=total_ms, ms_per_step=total_ms / steps, launches=int(launches), clocks=clocks,
+                    value=self.P * L_mean * steps / (total_ms * 1e-3), L_mean=L_mean)
+
+
+def fused_get_samples(E, leg, dev):
+    """The reference's own call on its own runnable configuration: HMC.getSamples, 1000 iterations, whose whole loop is
+    one launch for the small-D families (ehmc_hmc_run)."""
+    import contextlib
+    import io
+
+    import torch
+
+    D, P, L, h = leg.D, leg.P, leg.L, leg.h
+    ens_f = E.Ensemble(D, P, dtype=np.float32, device=dev, seed=SEED)
+    hmc_f = E.HMC(ens_f, L * h + 1e-9, h, None, potential=leg.pot, seed=SEED)
+    with contextlib.redirect_stdout(io.StringIO()):
+        hmc_f.getSamples(10, 1 / KB, 1.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hmc_f.getSamples(1000, 1 / KB, 1.0)
+        torch.cuda.synchronize()
+        tf = time.perf_counter() - t0
+    return {"value": P * L * 1000 / tf, "unit": "particle-leapfrog-steps/s", "ms_total": 1e3 * tf,
+            "iterations": 1000, "api": "HMC.getSamples(1000, ...) on a device ensemble -> ehmc_hmc_run, "
+            "one launch, samples and momenta (D, P, S) written by the kernel"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,6 +424,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short legs of the other BASELINE configs")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-iters", type=int, default=0, help="0 = enough iterations for ~2.2 s (>= 700)")
     ap.add_argument("--ess-iters", type=int, default=150, help="iterations of the ESS/s phase (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -255,7 +437,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference_arm(args, cfg, rank)
+        run_reference_arm(args, cfg, rank, world)
         return
 
     import torch
@@ -276,71 +458,41 @@ def main():
         ctx.set_option("tc_debug", float(os.environ["EHMC_TC_DEBUG"]))
     if os.environ.get("EHMC_DENSE_OCC"):
         ctx.set_option("dense_occupancy", float(os.environ["EHMC_DENSE_OCC"]))
-
-    D, P, L, h = cfg["D"], cfg["P"], cfg["L"], cfg["h"]
-    # strong scaling: contiguous particle ranges per rank
-    p_lo = rank * P // world
-    p_hi = (rank + 1) * P // world
-    Pl = p_hi - p_lo
-    pot = make_potential(E, args.config, D)
-
-    ens = E.Ensemble(D, Pl, dtype=np.float32, device=dev, seed=SEED, particleOffset=p_lo)
-    ens.setPosition(1.0)
-    hmc = E.HMC(ens, L * h + 1e-9, h, None, potential=pot, seed=SEED, bugCompat=False)
-    assert hmc.integrator.numSteps == L
-
-    fp32_peak = ctx.measure_fp32_peak(60.0) if rank == 0 else None
+    group = dist.group.WORLD if world > 1 else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    adaptive = args.config.startswith("c5")  # config 5: ensemble statistics all-reduced every iteration
-    # EHMC_DEVICE_ADAPT=1: step size / iteration counter in device-resident control blocks (HMC.run(deviceAdapt=True));
-    # default is the host-side adapter fed through a side stream -- measured equally fast (profiles/r01_adapt_probe.txt)
-    dev_adapt = os.environ.get("EHMC_DEVICE_ADAPT", "0") == "1"
-    group = dist.group.WORLD if world > 1 else None
-    if adaptive:
-        hmc.run(args.warmup, 1 / KB, adapt=True, group=group, keepNumSteps=True, deviceAdapt=dev_adapt)
-    else:
-        for _ in range(args.warmup):
-            hmc.step(1 / KB, reuseEndpoint=True)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = ctx.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
-    if adaptive:
-        run_out = hmc.run(args.steps, 1 / KB, adapt=True, group=group, keepNumSteps=True, deviceAdapt=dev_adapt)
-        for i in range(args.steps):
-            ev[i + 1] = ev[0]
-        ev[-1] = torch.cuda.Event(enable_timing=True)
-        ev[-1].record()
-    else:
-        for i in range(args.steps):
-            hmc.step(1 / KB, reuseEndpoint=True)  # q is only touched by the step itself
-            ev[i + 1].record()
-    barrier()
-    launches = ctx.launch_count() - launches0
+    fp32_peak = ctx.measure_fp32_peak(60.0)
 
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_step = [total_ms / args.steps] if adaptive else [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    # leapfrog steps actually executed per iteration: with step-size adaptation the trajectory LENGTH
-    # (simulTime) is fixed and numSteps = int(simulTime / stepSize) follows the step size
-    # (src/integrator.py:51), so the units of work are counted, not assumed
-    L_cfg = L
-    if adaptive:
-        L = float(np.mean(run_out["numSteps"]))
-    value = P * L * args.steps / (total_ms * 1e-3)
+    # ---- headline leg --------------------------------------------------------------------------
+    leg = Leg(E, args.config, rank, world, dev)
+    D, P, L, h, Pl = leg.D, leg.P, leg.L, leg.h, leg.Pl
+    main_t = leg.timed(args.steps, args.warmup, group, barrier, ctx)
+    value, ms_per_step = main_t["value"], main_t["ms_per_step"]
+    main_adapt = leg.run_out
+
+    # ---- sustained: the same loop for >= 2 s -----------------------------------------------------
+    sustained = None
+    if not args.no_sustained:
+        n_sus = args.sustained_iters or max(700, int(2200.0 / max(ms_per_step, 1e-3)))
+        n_sus = min(n_sus, 100000)
+        st = leg.timed(n_sus, 0, group, barrier, ctx)
+        if rank == 0:
+            ck = st["clocks"] or {}
+            sustained = {"iters": n_sus, "ms_per_step": st["ms_per_step"], "value": st["value"],
+                         "seconds": st["total_ms"] * 1e-3, "sm_mhz_median": ck.get("sm_mhz"),
+                         "power_w_max": ck.get("power_w_max"), "nvml_samples": ck.get("samples"),
+                         "reasons": ck.get("reasons"),
+                         "roofline": roofline(args.config, D, Pl, st["L_mean"], st["ms_per_step"], fp32_peak, peaks, ctx,
+                                              world, sustained=True)}
 
     # ---- ESS/s: min over dimensions of the ESS of traced chains, scaled to the ensemble ------
     ess = None
@@ -348,12 +500,11 @@ def main():
         from physicsbasedbayesianinference_b200 import diagnostics
 
         ntrace = min(256, Pl)
-        burn = 30
-        hmc.run(burn, 1 / KB, collectStats=False)
+        leg.hmc.run(30, 1 / KB, collectStats=False)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        r = hmc.run(args.ess_iters, 1 / KB, traceParticles=ntrace, collectStats=False)
+        r = leg.hmc.run(args.ess_iters, 1 / KB, traceParticles=ntrace, collectStats=False)
         e1.record()
         barrier()
         tsec = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
@@ -370,11 +521,11 @@ def main():
     e2e = None
     if not args.no_e2e:
         qh_t = torch.empty((D, Pl), dtype=torch.float32, pin_memory=True)
-        qh_t.copy_(ens.q)
-        ens_h = E.Ensemble(D, Pl, dtype=np.float32, seed=SEED, particleOffset=p_lo)
+        qh_t.copy_(leg.ens.q)
+        ens_h = E.Ensemble(D, Pl, dtype=np.float32, seed=SEED, particleOffset=leg.p_lo)
         ens_h.q = qh_t.numpy()
         ens_h.mass = torch.ones(Pl, dtype=torch.float32, pin_memory=True).numpy()
-        hmc_h = E.HMC(ens_h, L * h + 1e-9, h, None, potential=pot, rng="philox", seed=SEED, bugCompat=False)
+        hmc_h = E.HMC(ens_h, L * h + 1e-9, h, None, potential=leg.pot, rng="philox", seed=SEED, bugCompat=False)
         acc_h = torch.empty(Pl, dtype=torch.uint8, pin_memory=True).numpy()
         hmc_h.step(1 / KB, accept=acc_h)
         barrier()
@@ -387,129 +538,72 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
-        e2e = {"value": P * L_cfg * args.e2e_steps / e2e_s, "unit": "particle-leapfrog-steps/s",
+        e2e = {"value": P * L * args.e2e_steps / e2e_s, "unit": "particle-leapfrog-steps/s",
                "h2d_bytes_per_step": int(D * Pl * 4 + Pl * 4), "d2h_bytes_per_step": int(D * Pl * 4 + Pl),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
                "api": "HMC.step on a host-backed Ensemble -> ehmc_hmc_iter (host path, pinned buffers)"}
+        del ens_h, hmc_h, qh_t
+
+    fused = fused_get_samples(E, leg, dev) if (args.config == "c1" and world == 1 and rank == 0) else None
+
+    # ---- the other BASELINE configs, short legs ---------------------------------------------------
+    others = None
+    if not args.no_others:
+        others = {}
+        for name in ("c1", "c3", "c4", "c5", "c5l4"):
+            if name == args.config:
+                continue
+            if name == "c1" and world > 1:
+                others[name] = {"skipped": "1024 particles: measured at one GPU only"}
+                continue
+            try:
+                lg = Leg(E, name, rank, world, dev)
+                steps = OTHER_STEPS[name]
+                t = lg.timed(steps, 3, group, barrier, ctx)
+                if rank == 0:
+                    o = {"workload": lg.cfg["desc"], "value": t["value"], "unit": "particle-leapfrog-steps/s",
+                         "ms_per_step": t["ms_per_step"], "steps": steps, "warmup": 3, "dtype": dtype_of(name),
+                         "particles_per_gpu": lg.Pl, "gpu_launches": t["launches"], "clocks": t["clocks"],
+                         "roofline": roofline(name, lg.D, lg.Pl, t["L_mean"], t["ms_per_step"], fp32_peak, peaks, ctx, world)}
+                    if lg.adaptive:
+                        ro = lg.run_out
+                        o["adaptation"] = {"final_step_size": ro["stepSize"][-1], "accept_rate_last": ro["acceptRate"][-1],
+                                           "fused_launch": bool(ro.get("fused")),
+                                           "collective": ("statistics all-reduce inside the kernel: 2D+3 float64 stored into "
+                                                          f"each of {world - 1} peer mailboxes over NVLink per iteration"
+                                                          if world > 1 else "single GPU: no collective")}
+                    if name == "c1":
+                        o["getSamples_fused_loop"] = fused_get_samples(E, lg, dev)
+                    others[name] = o
+                del lg
+                torch.cuda.empty_cache()
+            except Exception as exc:  # one leg must not take the headline down
+                others[name] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
-        kern_ms = float(np.mean(per_step))  # one kernel per step on this stream
-        fl = flops_per_unit(args.config, D)
-        ach_tf = Pl * L * fl / (kern_ms * 1e-3) / 1e12
-        by = bytes_per_particle_iter(D) * Pl
-        ach_gbs = by / (kern_ms * 1e-3) / 1e9
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"
-        info = ctx.device_info()
-        nominal_fp32 = info["sm_count"] * 128 * 2 * info["sm_clock_mhz"] * 1e6 / 1e12
-        dense_tc = args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1"
-        logi_prec = os.environ.get("EHMC_LOGISTIC_PRECISION", "fp16x3")
-        logi_tc = args.config == "c3" and logi_prec in ("bf16", "fp16x3", "auto")
-        compute_bound = ach_tf / fp32_peak > ach_gbs / hbm_peak
-        if dense_tc:
-            # the gradient GEMM runs on tcgen05 as a 3-pass split (float32 accuracy from 11-bit operands):
-            # tensor-pipe roofline against the measured dense bf16 peak.  Executed tensor flops per
-            # algorithmic flop = 3 passes x padding; kind::f16 (default kernel k_dense_tc3) runs at the
-            # bf16 rate, kind::tf32 (k_dense_tc2, EHMC_DENSE_PATH=3) at half of it.
-            tpeak = peaks.get("bf16_tflops", 1590.0)
-            tf32 = os.environ.get("EHMC_DENSE_PATH", "0") in ("2", "3")
-            kp = (D + 7) // 8 * 8 if tf32 else (D + 15) // 16 * 16
-            npad = (D + 15) // 16 * 16
-            exec_factor = 3.0 * kp * npad / (D * D)
-            rate = 0.5 if tf32 else 1.0
-            roof = {"bound": "tensor", "achieved": ach_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_tf / tpeak,
-                    "traffic": None,
-                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback"),
-                    "flops_per_unit": fl, "units_per_launch": Pl * L,
-                    "executed_tensor_tflops": ach_tf * exec_factor,
-                    "tensor_pipe_busy_frac_est": ach_tf * exec_factor / (rate * tpeak),
-                    "formulation_ceiling_frac": rate / exec_factor,
-                    "note": "algorithmic fp32 flops (2 D^2 + 7 D per particle-step) over the measured bf16 peak; the "
-                            f"{'3xTF32' if tf32 else '3xFP16'} split executes {exec_factor:.2f}x those flops (3 passes x "
-                            f"padding to K={kp}, N={npad}) at {'half the' if tf32 else 'the'} bf16 rate, so `frac` cannot "
-                            "exceed formulation_ceiling_frac; tensor_pipe_busy_frac_est = frac / ceiling"}
-        elif logi_tc:
-            tpeak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
-            roof = {"bound": "tensor", "achieved": ach_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": ach_tf / tpeak,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside "
-                    "a long step)", "flops_per_unit": fl, "units_per_launch": Pl * L,
-                    "executed_tensor_tflops": ach_tf * (1.0 if logi_prec == "bf16" else 3.0),
-                    "formulation_ceiling_frac": 1.0 if logi_prec == "bf16" else 1.0 / 3.0,
-                    "note": ("bf16 tcgen05 GEMM chain (X theta^T -> sigmoid-residual -> R^T X), operands rounded to bf16: "
-                             "OUTSIDE the 1e-5 tolerance, opt-in only" if logi_prec == "bf16" else
-                             "tcgen05 GEMM chain at float32 accuracy: every operand a 2-term fp16 split, 3 MMA passes per "
-                             "GEMM = 3x the algorithmic flops, so `frac` cannot exceed formulation_ceiling_frac") +
-                            "; kernel_ms is the whole iteration (L gradient launches + kick/drift launches)"}
-        elif compute_bound:
-            roof = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": ach_tf / fp32_peak, "traffic": None,
-                    "peak_source": "measured in this run (ehmc_measure_fp32_peak, register-only FFMA kernel); "
-                                   f"nominal {nominal_fp32:.1f} = SMs*128*2*max clock",
-                    "flops_per_unit": fl, "units_per_launch": Pl * L}
-        else:
-            roof = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
-                    "bytes_per_unit": bytes_per_particle_iter(D) / L, "units_per_launch": Pl * L}
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.config[:2])
-            if tr and world == 1:
-                roof["traffic"] = tr["dram_bytes_per_launch"]
-                roof["traffic_source"] = tr["source"]
-                roof["ncu_tensor_pipe_active_pct"] = tr.get("tensor_pipe_active_pct")
-                roof["ncu_issue_active_pct"] = tr.get("issue_active_pct")
-                roof["ncu_fma_pipe_active_pct"] = tr.get("fma_pipe_active_pct")
-        except (OSError, ValueError):
-            pass
-        roof["algorithmic_bytes_per_launch"] = by
-        roof["kernel_ms"] = kern_ms
-        roof["other"] = {"hbm_GBps": ach_gbs, "hbm_frac": ach_gbs / hbm_peak, "fp32_TFLOPs": ach_tf,
-                         "fp32_frac": ach_tf / fp32_peak}
+        roof = roofline(args.config, D, Pl, main_t["L_mean"], ms_per_step, fp32_peak, peaks, ctx, world)
         cpu = None
         if not args.no_cpu_baseline:
-            sample = min(P, {"c2": 1 << 14, "c3": 64, "c4": 1}.get(args.config, 1 << 17))
+            sample = min(P, CPU_SAMPLE.get(args.config, 1 << 17))
             rate, times = cpu_port_rate(args.config, cfg, sample, 3)
             cpu = {"value": rate, "unit": "particle-leapfrog-steps/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{sample} of {P} particles x 3 iterations, median (NumPy float64 oracle port, "
                              f"BLAS on all host cores; {sum(times):.1f} s of CPU wall time)"}
-        fused = None
-        if args.config == "c1" and world == 1:
-            # the reference's own call on its own runnable configuration: HMC.getSamples, 1000 iterations, whose
-            # whole loop is one launch for the small-D families (ehmc_hmc_run)
-            import contextlib
-            import io
-
-            ens_f = E.Ensemble(D, P, dtype=np.float32, device=dev, seed=SEED)
-            hmc_f = E.HMC(ens_f, L * h + 1e-9, h, None, potential=pot, seed=SEED)
-            with contextlib.redirect_stdout(io.StringIO()):
-                hmc_f.getSamples(10, 1 / KB, 1.0)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                hmc_f.getSamples(1000, 1 / KB, 1.0)
-                torch.cuda.synchronize()
-                tf = time.perf_counter() - t0
-            fused = {"value": P * L * 1000 / tf, "unit": "particle-leapfrog-steps/s", "ms_total": 1e3 * tf,
-                     "iterations": 1000, "api": "HMC.getSamples(1000, ...) on a device ensemble -> ehmc_hmc_run, "
-                     "one launch, samples and momenta (D, P, S) written by the kernel"}
+        cpu_ref = None
+        try:
+            cpu_ref = json.load(open(os.path.join(ROOT, "profiles", "r02_ref_standin_c1.json")))
+        except (OSError, ValueError):
+            pass
         line = {
             "metric": "particle-leapfrog-steps/sec", "value": value, "unit": "particle-leapfrog-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": (("f32 (3xTF32 tensor-core split, fp32 accumulate)" if os.environ.get("EHMC_DENSE_PATH", "0") in ("2", "3")
-                       else "f32 (3xFP16 tensor-core split, fp32 accumulate)")
-                      if (args.config == "c2" and os.environ.get("EHMC_DENSE_PATH", "0") != "1")
-                      else ("f32 state, bf16 tensor-core gradient GEMMs (fp32 accumulate)" if os.environ.get("EHMC_LOGISTIC_PRECISION", "fp16x3") == "bf16"
-                            else "f32 (3xFP16 tensor-core split of both gradient GEMMs, fp32 accumulate)" if os.environ.get("EHMC_LOGISTIC_PRECISION", "fp16x3") != "fp32" else "f32") if args.config == "c3" else "f32"),
-            "data": "synthetic",
-            "config": {"workload": cfg["desc"], "D": D, "P": P, "L": L_cfg, "L_executed_mean": L, "h": h, "particles_per_gpu": Pl,
-                       "rng": "philox in-kernel", "l2": "inputs_exceed_l2" if D * Pl * 4 > 126e6 else "resident",
-                       "parallelism": f"particle-shard x{world}, no data-path collective"},
-            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-            "ess": ess, "getSamples_fused_loop": fused, "adaptation": ({"final_step_size": run_out["stepSize"][-1],
-                                        "accept_rate_last": run_out["acceptRate"][-1]} if adaptive else None),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_of(args.config),
+            "data": "synthetic", "config": config_dict(cfg, D, P, L, h, Pl, world, main_t["L_mean"]),
+            "gpu_launches": main_t["launches"], "clocks": main_t["clocks"], "e2e": e2e, "roofline": roof,
+            "sustained": sustained, "cpu_baseline": cpu, "cpu_baseline_ref": cpu_ref, "ess": ess,
+            "other_configs": others, "getSamples_fused_loop": fused,
+            "adaptation": ({"final_step_size": main_adapt["stepSize"][-1], "accept_rate_last": main_adapt["acceptRate"][-1],
+                            "fused_launch": bool(main_adapt.get("fused"))} if main_adapt else None),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
