@@ -456,6 +456,8 @@ def main():
         ctx.set_option("dense_path", float(os.environ["EHMC_DENSE_PATH"]))
     if os.environ.get("EHMC_TC_DEBUG"):
         ctx.set_option("tc_debug", float(os.environ["EHMC_TC_DEBUG"]))
+    if os.environ.get("EHMC_ENS_DEBUG"):  # phase stamps of the fused ensemble run (dumped to stderr after the headline leg)
+        ctx.set_option("ens_debug", float(os.environ["EHMC_ENS_DEBUG"]))
     if os.environ.get("EHMC_DENSE_OCC"):
         ctx.set_option("dense_occupancy", float(os.environ["EHMC_DENSE_OCC"]))
     group = dist.group.WORLD if world > 1 else None
@@ -478,6 +480,8 @@ def main():
     main_t = leg.timed(args.steps, args.warmup, group, barrier, ctx)
     value, ms_per_step = main_t["value"], main_t["ms_per_step"]
     main_adapt = leg.run_out
+    if os.environ.get("EHMC_ENS_DEBUG") and rank == 0:
+        ctx.set_option("ens_debug_dump", max(0.0, float(os.environ["EHMC_ENS_DEBUG"]) - 24))
 
     # ---- sustained: the same loop for >= 2 s -----------------------------------------------------
     sustained = None

@@ -160,6 +160,7 @@ extern "C" int ehmc_ctx_destroy(ehmc_ctx* c) {
   c->tc_prof_buf.release();
   c->overflow.release();
   c->ens_ctl.release();
+  c->ens_dbg_buf.release();
   for (int k = 0; k < 2; ++k) {
     c->ep_grad[k].release();
     c->ep_energy[k].release();
@@ -235,6 +236,25 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
   } else if (!strcmp(name, "nbody_ti")) {
     if (value != 0 && value != 4 && value != 8) return fail(EHMC_ERR_INVALID, "nbody_ti must be 0, 4 or 8");
     c->nbody_ti = (int)value;
+  } else if (!strcmp(name, "ens_lockstep")) {
+    c->ens_lockstep = value != 0 ? 1 : 0;
+  } else if (!strcmp(name, "ens_debug")) {
+    if (!(value >= 0 && value <= 65536)) return fail(EHMC_ERR_INVALID, "ens_debug must be in [0, 65536]");
+    c->ens_debug = (int)value;
+  } else if (!strcmp(name, "ens_debug_dump")) {
+    // debugging aid: phase stamps of the last fused ensemble run (ns relative to the first), to stderr
+    if (c->ens_dbg_buf.ptr && c->ens_debug > 0) {
+      std::vector<long long> hbuf((size_t)8 * c->ens_debug);
+      CUDA_TRY(cudaMemcpy(hbuf.data(), c->ens_dbg_buf.ptr, sizeof(long long) * hbuf.size(), cudaMemcpyDeviceToHost));
+      const int first = (int)value;
+      for (int it = first; it < c->ens_debug && hbuf[(size_t)8 * it]; ++it) {
+        const long long* r = &hbuf[(size_t)8 * it];
+        fprintf(stderr, "ens_debug it %d: master: tickets of it at %lld, +reduce %lld +push %lld +peers %lld +publish %lld | "
+                "cta0: start %lld, waited %lld for h, end %lld | master period %lld\n", it, r[0] - hbuf[0], r[1] - r[0],
+                r[2] ? r[2] - r[1] : 0LL, r[2] ? r[3] - r[2] : 0LL, r[4] - (r[2] ? r[3] : r[1]), r[5] - hbuf[0], r[6],
+                r[7] - hbuf[0], it > 0 ? r[0] - r[-8] : 0LL);
+      }
+    }
   } else if (!strcmp(name, "tc_debug")) {
     c->tc_debug = (int)value;
   } else if (!strcmp(name, "host_chunk_mb")) {
@@ -1079,6 +1099,13 @@ extern "C" int ehmc_hmc_run_ensemble(ehmc_ctx* ctx, const ehmc_potential* pot, D
   if (numIterations == 0 || v.P == 0) return EHMC_OK;
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // Robbins-Monro gains of this call's updates, k continuing from state[2] (read back: one small synchronous copy)
+  double st_host[4];
+  CUDA_TRY(cudaMemcpyAsync(st_host, vs.data, sizeof(st_host), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const int n_adapt = std::max(0, std::min(numIterations, ad->adaptIterations));
+  std::vector<double> gains((size_t)std::max(1, n_adapt));
+  for (int i = 0; i < n_adapt; ++i) gains[i] = ad->gain0 / std::pow(st_host[2] + 1.0 + i, ad->kappa);
   auto run = [&](auto tag) -> int {
     typedef decltype(tag) T;
     IterArgs<T> A = base_args<T>(v, a->stepSize, a->stepSizeSq, a->numSteps);
@@ -1092,11 +1119,10 @@ extern "C" int ehmc_hmc_run_ensemble(ehmc_ctx* ctx, const ehmc_potential* pot, D
     EnsRunArgs<T> R;
     memset(&R, 0, sizeof(R));
     R.nIter = numIterations;
-    R.adaptIters = std::max(0, std::min(numIterations, ad->adaptIterations));
+    R.adaptIters = n_adapt;
     R.target = ad->targetAccept;
-    R.gain0 = ad->gain0;
-    R.kappa = ad->kappa;
     R.maxMove = ad->maxMove;
+    R.gains = gains.data();  // host array; the launcher uploads it
     R.logLo = std::log(ad->minStep);
     R.logHi = std::log(ad->maxStep);
     R.Ptot = ad->numParticlesTotal;

@@ -17,24 +17,48 @@ static int ens_launch(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, EnsRunA
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, K1_THREADS, sm));
   CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
   if (!coop || occ < 1) return fail(EHMC_ERR_UNSUPPORTED, "fused ensemble run: cooperative launch unavailable");
-  // one resident wave of compute CTAs plus the service CTA
+  // one resident wave: compute CTAs plus the service CTAs
   const long long need = (A.P + K1_THREADS - 1) / K1_THREADS;
   const long long cap = (long long)occ * c->prop.multiProcessorCount;
-  const unsigned ncompute = (unsigned)std::max<long long>(1, std::min<long long>(need, cap - 1));
+  if (cap <= ENS_SERVICE_CTAS) return fail(EHMC_ERR_UNSUPPORTED, "fused ensemble run: device too small");
+  const unsigned ncompute = (unsigned)std::max<long long>(1, std::min<long long>(need, cap - ENS_SERVICE_CTAS));
   const int NS = 2 * A.D + 3;
-  // control block: hsched [nIter + 2] | published | ticket [2] (+pad) | rows [2][ncompute][NS]
-  const size_t n_h = (size_t)R.nIter + 2;
-  const size_t bytes = sizeof(double) * (n_h + 1 + 1 + (size_t)2 * ncompute * NS);
+  // control block: hsched [nIter + 2] | published | ticket [2] | group tickets [2][ngroups] | rows [2][ncompute][NS] |
+  // group rows [2][ngroups][NS] | gains [adaptIters]
+  const size_t n_h = ((size_t)R.nIter + 2 + 15) / 16 * 16;  // (every section starts on a 128-byte line)
+  const size_t n_pub = (size_t)ENS_PUB_COPIES * 16;
+  const size_t n_tk = 32 + (size_t)ENS_PUB_COPIES * 16;  // ticket[0], ticket[1] on lines of their own | arrival counters
+  const unsigned ngroups = (ncompute + ENS_GROUP - 1) / ENS_GROUP;
+  const size_t n_gt = ((size_t)2 * ngroups / 2 + 16) / 16 * 16;  // group tickets (unsigned) in units of doubles
+  const size_t n_rows = ((size_t)2 * ncompute * NS + 15) / 16 * 16;
+  const size_t n_grows = ((size_t)2 * ngroups * NS + 15) / 16 * 16;
+  const size_t bytes = sizeof(double) * (n_h + n_pub + n_tk + n_gt + n_rows + n_grows + (size_t)std::max(1, R.adaptIters)) + 128;
   TRY(c->ens_ctl.ensure(bytes));
-  double* base = static_cast<double*>(c->ens_ctl.ptr);
+  double* base = reinterpret_cast<double*>(((uintptr_t)c->ens_ctl.ptr + 127) & ~(uintptr_t)127);
   R.hsched = base;
   R.published = reinterpret_cast<long long*>(base + n_h);
-  R.ticket = reinterpret_cast<unsigned*>(base + n_h + 1);
-  R.rows = base + n_h + 2;
-  CUDA_TRY(cudaMemsetAsync(base + n_h, 0, 2 * sizeof(double), st));  // published = 0, tickets = 0
+  R.ticket = reinterpret_cast<unsigned*>(base + n_h + n_pub);  // ticket[par] at R.ticket[32 * par] (see the kernel)
+  R.arrived = reinterpret_cast<unsigned long long*>(base + n_h + n_pub + 32);
+  R.lockstep = c->ens_lockstep;
+  R.gticket = reinterpret_cast<unsigned*>(base + n_h + n_pub + n_tk);
+  R.rows = base + n_h + n_pub + n_tk + n_gt;
+  R.grows = R.rows + n_rows;
+  double* gains = R.grows + n_grows;
+  CUDA_TRY(cudaMemsetAsync(base + n_h, 0, (n_pub + n_tk + n_gt) * sizeof(double), st));  // published = 0, all tickets = 0
+  if (R.adaptIters > 0)  // R.gains arrives as a HOST array
+    CUDA_TRY(cudaMemcpyAsync(gains, R.gains, sizeof(double) * R.adaptIters, cudaMemcpyHostToDevice, st));
+  R.gains = gains;
+  R.dbg = nullptr;
+  R.dbg_iters = 0;
+  if (c->ens_debug > 0) {
+    TRY(c->ens_dbg_buf.ensure(sizeof(long long) * 8 * (size_t)c->ens_debug));
+    CUDA_TRY(cudaMemsetAsync(c->ens_dbg_buf.ptr, 0, sizeof(long long) * 8 * (size_t)c->ens_debug, st));
+    R.dbg = static_cast<long long*>(c->ens_dbg_buf.ptr);
+    R.dbg_iters = c->ens_debug;
+  }
   IterArgs<T> Ac = A;
   void* args[] = {(void*)&Ac, (void*)&pot, (void*)&R};
-  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kernel, dim3(ncompute + 1), dim3(K1_THREADS), args, sm, st));
+  CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kernel, dim3(ncompute + ENS_SERVICE_CTAS), dim3(K1_THREADS), args, sm, st));
   c->launches++;
   return EHMC_OK;
 }

@@ -331,24 +331,28 @@ __device__ __forceinline__ T kinetic(const T (&p)[DT], T m, T inv_m) {
 }
 
 // Block-level reduction of the per-thread statistics accumulators -> one row of partials.
-// Accumulators live in shared memory, sacc[j][thread] (registers are better spent on occupancy):
-// j in [0..2] scalars, [3 .. 3+DT) sum q_d, [3+DT .. 3+2DT) sum q_d^2 (DT = padded D);
+// Accumulators live in shared memory, sacc[j][thread] with a leading dimension of NTHREADS + 1 doubles (registers
+// are better spent on occupancy): j in [0..2] scalars, [3 .. 3+DT) sum q_d, [3+DT .. 3+2DT) sum q_d^2 (DT = padded D);
 // output row layout uses the true D: [0..2], [3 .. 3+D), [3+D .. 3+2D).
+// Thread j adds the NTHREADS entries of column j straight from shared memory (fixed order, four partial sums; the
+// odd leading dimension spreads the columns over the banks): ~250 issue slots of one warp, against ~1500 for the
+// tree of 2D+3 warp-shuffle reductions in every warp that this replaced -- the fused ensemble run pays it every
+// iteration.
 template <int NTHREADS, int DT>
-__device__ __forceinline__ void block_partials(double* out_row, int D, const double* sacc /*[2DT+3][NTHREADS]*/,
-                                               double* sred /*[NTHREADS/32][2DT+3]*/) {
-  constexpr int NA = 2 * DT + 3;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll 1
-  for (int j = 0; j < NA; ++j) {
-    const double s = warp_sum(sacc[j * NTHREADS + threadIdx.x]);
-    if (lane == 0) sred[w * NA + j] = s;
-  }
+__device__ __forceinline__ void block_partials(double* out_row, int D, const double* sacc /*[2DT+3][NTHREADS + 1]*/) {
+  constexpr int NA = 2 * DT + 3, LD = NTHREADS + 1;
   __syncthreads();
   for (int j = threadIdx.x; j < NA; j += NTHREADS) {
-    double s = 0.0;
-#pragma unroll
-    for (int ww = 0; ww < NTHREADS / 32; ++ww) s += sred[ww * NA + j];
+    const double* col = sacc + j * LD;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < NTHREADS; t += 4) {
+      s0 += col[t];
+      s1 += col[t + 1];
+      s2 += col[t + 2];
+      s3 += col[t + 3];
+    }
+    const double s = (s0 + s1) + (s2 + s3);
     int o = j;
     if (j >= 3 + DT) {
       const int d = j - 3 - DT;
@@ -372,17 +376,24 @@ __device__ __forceinline__ void block_partials(double* out_row, int D, const dou
 // config 5 cost 140 instructions (predicated address arithmetic, selects against zero) and -- worse -- the selects
 // consumed the loaded values at once, so every warp waited for HBM BEFORE its ~300 instructions of Philox work
 // instead of behind them (profiles/r01_k1_dbg_probe.txt, r01_ncu_full_k1l4_before.txt).
-template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT>
+struct NoStepHook {};  // k_small_body: the step size is A.h
+
+template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT, class StepHook = NoStepHook>
 __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& pot, double* k1_smem, unsigned blk,
-                                             unsigned nblk) {  // this CTA is number blk of nblk walking the particles
+                                             unsigned nblk,  // this CTA is number blk of nblk walking the particles
+                                             const StepHook& hook = StepHook()) {
+  // the fused ensemble run (k_small_ens) learns the step size of the iteration from `hook`, called once, behind the
+  // first momentum draw (work that does not depend on h)
+  T h = A.h, h2 = A.h2;
+  bool h_known = std::is_same<StepHook, NoStepHook>::value;
   const int Dn = EXACT ? DT : A.D;
   constexpr int NA = 2 * DT + 3;
   const bool want_stats = HMC && A.partials != nullptr;
-  double* sacc = k1_smem + threadIdx.x;          // [NA][K1_THREADS], this thread's column
-  double* sred = k1_smem + NA * K1_THREADS;      // [K1_THREADS / 32][NA]
+  constexpr int LD = K1_THREADS + 1;
+  double* sacc = k1_smem + threadIdx.x;          // [NA][LD], this thread's column
   if (want_stats) {
 #pragma unroll 1
-    for (int j = 0; j < NA; ++j) sacc[j * K1_THREADS] = 0.0;
+    for (int j = 0; j < NA; ++j) sacc[j * LD] = 0.0;
   }
   const long long stride = (long long)nblk * K1_THREADS;
 
@@ -413,7 +424,13 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
     const T inv_m = Ar<T>::rcp_(m);
     if (HMC) K0 = kinetic<T, DT>(p, m, inv_m);
     T U0;
-    const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, A.h, A.h2, A.L, HMC, &U0);
+    if constexpr (!std::is_same<StepHook, NoStepHook>::value) {
+      if (!h_known) {
+        hook(h, h2);
+        h_known = true;
+      }
+    }
+    const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, h, h2, A.L, HMC, &U0);
 
     if (!HMC) {
       if (active) {
@@ -465,19 +482,19 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
 #pragma unroll
         for (int d = 0; d < DT; ++d) q[d] = d < Dn ? A.q[d * A.q_ld + i] : T(0);
       }
-      sacc[0 * K1_THREADS] += rej ? 0.0 : 1.0;
-      sacc[1 * K1_THREADS] += (double)accp;
-      sacc[2 * K1_THREADS] += (double)(rej ? oldH : newH);
+      sacc[0 * LD] += rej ? 0.0 : 1.0;
+      sacc[1 * LD] += (double)accp;
+      sacc[2 * LD] += (double)(rej ? oldH : newH);
 #pragma unroll
       for (int d = 0; d < DT; ++d) {
         const double qd = (double)q[d];
-        sacc[(3 + d) * K1_THREADS] += qd;
-        sacc[(3 + DT + d) * K1_THREADS] = fma(qd, qd, sacc[(3 + DT + d) * K1_THREADS]);
+        sacc[(3 + d) * LD] += qd;
+        sacc[(3 + DT + d) * LD] = fma(qd, qd, sacc[(3 + DT + d) * LD]);
       }
     }
   }
   if (want_stats)
-    block_partials<K1_THREADS, DT>(A.partials + (size_t)blk * (2 * Dn + 3), Dn, k1_smem, sred);
+    block_partials<K1_THREADS, DT>(A.partials + (size_t)blk * (2 * Dn + 3), Dn, k1_smem);
 }
 
 // Two kernels (picked on the host by D == DT) rather than one with both bodies: a kernel gets the register
