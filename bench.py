@@ -55,6 +55,9 @@ OTHER_STEPS = {"c1": 50, "c3": 3, "c4": 4, "c5": 200, "c5l4": 200}
 LOGI_PREC = os.environ.get("EHMC_LOGISTIC_PRECISION", "fp16x3")
 
 
+ADAPT_LAG = int(os.environ.get("EHMC_ADAPT_LAG", "2"))
+
+
 def flops_per_unit(name, D):
     """Algorithmic flops per particle-leapfrog-step: grad U + 7 D."""
     if name == "c2":
@@ -361,7 +364,9 @@ class Leg:
         if n <= 0:
             return
         if self.adaptive:
-            self.run_out = self.hmc.run(n, 1 / KB, adapt=True, group=group, keepNumSteps=True)
+            # adaptLag = 2 at every N (results must not depend on the GPU count): the reductions and the all-reduce get
+            # two iterations, see HMC.run
+            self.run_out = self.hmc.run(n, 1 / KB, adapt=True, group=group, keepNumSteps=True, adaptLag=ADAPT_LAG)
         else:
             for _ in range(n):
                 self.hmc.step(1 / KB, reuseEndpoint=True)  # q is only touched by the step itself
@@ -572,7 +577,7 @@ def main():
                     if lg.adaptive:
                         ro = lg.run_out
                         o["adaptation"] = {"final_step_size": ro["stepSize"][-1], "accept_rate_last": ro["acceptRate"][-1],
-                                           "fused_launch": bool(ro.get("fused")),
+                                           "fused_launch": bool(ro.get("fused")), "adapt_lag": ADAPT_LAG,
                                            "collective": ("statistics all-reduce inside the kernel: 2D+3 float64 stored into "
                                                           f"each of {world - 1} peer mailboxes over NVLink per iteration"
                                                           if world > 1 else "single GPU: no collective")}

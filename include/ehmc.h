@@ -85,7 +85,8 @@ typedef enum {
    * params: Lambda[D,D] (row-major), optional mu[D].  scalars: none. */
   EHMC_FAMILY_DENSE_GAUSSIAN = 2,
   /* Neal's funnel, v = q[0]: U = v^2/(2 s^2) + 0.5 e^{-v} sum_{k>=1} q_k^2 + 0.5 (D-1) v.
-   * params: none.  scalars: {D, s}. */
+   * params: none.  scalars: {D, s} or {D, s, scaleV, scaleX}: the same potential of v = scaleV q[0],
+   * x_k = scaleX q[k] (rescaled coordinates = diagonal mass matrix, HMC.run(adaptMass=True)). */
   EHMC_FAMILY_FUNNEL = 3,
   /* Each ensemble particle is a B-body system, coordinates d = c*B + b (src/potential.py:83-84):
    * U = -G sum_{i<j} m_i m_j / sqrt(|r_i-r_j|^2 + eps^2); -grad_i U / m_i is getAccelNBody
@@ -284,6 +285,10 @@ typedef struct {
   int32_t adaptIterations;   /* Robbins-Monro updates from the first adaptIterations iterations of the call */
   double targetAccept, gain0, kappa, maxMove, minStep, maxStep; /* parallel.StepSizeAdapter */
   double numParticlesTotal;  /* particles of ALL ranks */
+  int32_t lag;               /* the statistics of iteration k set the step size of iteration k + 1 + lag: 1 (0 means 1:
+                              * the one-iteration-stale pipeline of HMC.run) or 2 (two iterations for the reduction
+                              * and the all-reduce; what the 8-GPU runs of small shards need) */
+  int32_t reserved;
 } ehmc_adapt_args;
 
 /* numIterations iterations of the loop of src/HMC.py:150-179 on the resident ensemble (Philox iterations
@@ -291,7 +296,8 @@ typedef struct {
  * probability, sum H, sum q_d, sum q_d^2} are summed over the CTAs and over all ranks of `comm` INSIDE the kernel
  * (stores into the peers' mailboxes over NVLink, rank-ordered sum: identical bits on every rank), the step size
  * follows log h += clip(gain0 / k^kappa (mean acceptance probability - target)) with the statistics of iteration
- * k first used by iteration k + 2 (the all-reduce hides behind iteration k + 1), numSteps stays fixed.
+ * k first used by iteration k + 1 + adapt.lag (the all-reduce hides behind the iterations in between), numSteps
+ * stays fixed.
  *   state    float64[4] device, in/out: {step size, log step size, updates k, iterations run}
  *   history  float64[S,4] device, optional: {accept rate, mean acceptance probability, mean H, step size used}
  *   moments  float64[2D] device, optional, accumulated: sum q_d, sum q_d^2 over particles and iterations

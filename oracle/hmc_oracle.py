@@ -85,26 +85,31 @@ class Funnel:
     """Neal's funnel: v = q[0] ~ N(0, s^2), q[k] ~ N(0, e^v), k = 1..D-1.
 
     U = v^2/(2 s^2) + 0.5 e^{-v} sum_k q_k^2 + 0.5 (D-1) v   (build-defined)
+    scale_v, scale_x: the same potential in rescaled coordinates, v = scale_v q[0], x_k = scale_x q[k]
+    (what the build's mass adaptation produces; both 1 = the plain funnel).
     """
 
     family = 3
 
-    def __init__(self, num_dims, sigma_v=3.0):
+    def __init__(self, num_dims, sigma_v=3.0, scale_v=1.0, scale_x=1.0):
         self.D = int(num_dims)
         self.s = float(sigma_v)
+        self.a = float(scale_v)
+        self.c = float(scale_x)
 
     def energy(self, q):
-        v = q[0]
-        s2 = np.sum(q[1:] ** 2, axis=0)
+        v = self.a * q[0]
+        s2 = np.sum((self.c * q[1:]) ** 2, axis=0)
         return v * v / (2.0 * self.s**2) + 0.5 * np.exp(-v) * s2 + 0.5 * (self.D - 1) * v
 
     def grad(self, q):
-        v = q[0]
+        v = self.a * q[0]
         ev = np.exp(-v)
-        s2 = np.sum(q[1:] ** 2, axis=0)
+        x = self.c * q[1:]
+        s2 = np.sum(x**2, axis=0)
         g = np.empty_like(q)
-        g[0] = v / self.s**2 - 0.5 * ev * s2 + 0.5 * (self.D - 1)
-        g[1:] = ev * q[1:]
+        g[0] = self.a * (v / self.s**2 - 0.5 * ev * s2 + 0.5 * (self.D - 1))
+        g[1:] = self.c * (ev * x)
         return g
 
 
@@ -320,6 +325,29 @@ def hmc_iter(q, z, u, mass, temperature, step_size, n_steps, pot,
     # so the stored momentum is the UN-flipped p.
     p_store = np.where(reject[None, :], q if bug_compat else p0, p1)
     return q_next, p_store, ~reject, old_h, new_h
+
+
+def hmc_iter_diag_mass(q, z, u, mass, mass_diag, temperature, step_size, n_steps, pot, boltzmann=BOLTZMANN):
+    """One HMC iteration with the DIAGONAL mass matrix M[d, i] = mass[i] * mass_diag[d], written out in the original
+    coordinates (build-defined: the reference's mass is one scalar per particle, src/ensemble.py:42; this is the
+    independent statement of what HMC.run(adaptMass=True) computes through rescaled coordinates, where
+    mass_diag = 1 / massScale**2).  Leapfrog in kick-drift-kick form; momentum p = sqrt(M kT) z.
+    Returns (q_next, accept, oldH, newH)."""
+    M = mass[None, :] * np.asarray(mass_diag, dtype=np.float64)[:, None]
+    p = z * np.sqrt(M * boltzmann * temperature)
+    old_h = 0.5 * np.sum(p * p / M, axis=0) + pot.energy(q)
+    x = q.copy()
+    g = pot.grad(x)
+    for _ in range(int(n_steps)):
+        p = p - 0.5 * step_size * g
+        x = x + step_size * p / M
+        g = pot.grad(x)
+        p = p - 0.5 * step_size * g
+    new_h = 0.5 * np.sum(p * p / M, axis=0) + pot.energy(x)
+    with np.errstate(over="ignore", invalid="ignore"):
+        acc_prob = np.minimum(1, np.exp(old_h - new_h))
+    reject = u > acc_prob
+    return np.where(reject[None, :], q, x), ~reject, old_h, new_h
 
 
 def get_samples(num_dims, num_particles, mass, pot, num_samples, temperature, q_std,

@@ -79,6 +79,7 @@ class HMC:
         self.bugCompat = bool(bugCompat)
         self.rejectNonFinite = bool(rejectNonFinite)
         self.iteration = 0  # Philox iteration counter (persists across getSamples calls)
+        self.massScale = None  # per-dimension coordinate scales of run(adaptMass=True): M_d = mass / massScale_d^2
         self.lastAccept = None
 
     # U(x) = -log(p(x))
@@ -218,7 +219,7 @@ class HMC:
     # ------------------------------------------------------------------------------------
     def run(self, numIterations, temperature, *, adapt=False, targetAccept=0.8, adaptIterations=None,
             traceParticles=0, group=None, collectStats=True, keepNumSteps=False, deviceAdapt=False, graph=False,
-            fused=None):
+            fused=None, adaptLag=1, adaptMass=False, massWindows=3):
         """Production loop for device ensembles (build-defined; scales where getSamples'
         (D, P, S) arrays cannot, SURVEY.md section 7 hard part 7).
 
@@ -248,15 +249,43 @@ class HMC:
         iteration.  fused=None (default) picks it whenever it applies (statistics wanted, numSteps fixed: adapt=False
         or keepNumSteps=True); it needs CUDA IPC / peer access between the GPUs of `group`.
 
+        adaptLag: the statistics of iteration k set the step size of iteration k + 1 + adaptLag.  1 (default) is the
+        one-iteration-stale pipeline described above; 2 leaves two iterations for the reductions and the all-reduce,
+        which is what small shards on many GPUs need (at 2^19 particles per GPU an iteration is 30 us and the chain
+        last slice -> reductions -> slowest of 8 GPUs -> publish measured 20-30 us).  The host loop and the fused
+        launch implement the same schedule for either value; results do not depend on the number of GPUs.
+
+        adaptMass=True adds ensemble-based diagonal MASS adaptation to the warm-up (the first adaptIterations
+        iterations; needs adapt=True): at the end of each of `massWindows` windows of doubling length the all-reduced
+        moments sum q_d, sum q_d^2 of the window give per-dimension scales s_d = sqrt(var_d) (parallel.MassAdapter:
+        the same numbers, hence the same masses, on every rank), the ensemble is rescaled to q / s and the potential
+        replaced by the same family in those coordinates (Potential.rescaled) -- HMC with the diagonal mass matrix
+        M_d = mass / s_d^2, the kernels untouched.  The accumulated scales are kept in self.massScale and applied by
+        later run() calls; ensemble.q is in the original coordinates whenever run() returns, and so are the returned
+        mean, var (those of the last phase: after the warm-up if the call goes beyond it) and trace.  See
+        _run_mass_adapt.
+
         Returns dict(acceptRate[S], meanAcceptProb[S], meanH[S], stepSize[S], mean[D], var[D],
         trace (D, traceParticles, S) or None).
         """
+        if adaptLag not in (1, 2):
+            raise ValueError("adaptLag must be 1 or 2")
+        if adaptMass or getattr(self, "massScale", None) is not None:
+            if adaptMass and not adapt:
+                raise ValueError("adaptMass=True needs adapt=True (the step size must follow the mass)")
+            return self._run_mass_adapt(numIterations, temperature, adaptMass=adaptMass, massWindows=massWindows,
+                                        adapt=adapt, targetAccept=targetAccept, adaptIterations=adaptIterations,
+                                        traceParticles=traceParticles, group=group, collectStats=collectStats,
+                                        keepNumSteps=keepNumSteps, deviceAdapt=deviceAdapt, graph=graph, fused=fused,
+                                        adaptLag=adaptLag)
+        if deviceAdapt and adaptLag != 1:
+            raise ValueError("deviceAdapt=True implements adaptLag=1 only")
         if fused is None:
             fused = (collectStats and not deviceAdapt and self.ensemble.onDevice and self.method == "Leapfrog"
                      and self._fused_loop_ok() and (keepNumSteps or not adapt) and numIterations > 0)
         if fused:
             return self._run_fused(numIterations, temperature, adapt, targetAccept, adaptIterations, traceParticles,
-                                   group)
+                                   group, adaptLag)
         if deviceAdapt:
             return self._run_device_adapt(numIterations, temperature, adapt, targetAccept, adaptIterations,
                                           traceParticles, group, graph)
@@ -281,14 +310,15 @@ class HMC:
         adapter = (StepSizeAdapter(self.stepSize, targetAccept, maxStep=1e3 if keepNumSteps else min(1e3, self.simulTime))
                    if adapt else None)
         adaptIterations = numIterations if adaptIterations is None else adaptIterations
-        # Two statistics slots (device vector + pinned host copy + "copy done" event).  Iteration k
-        # writes slot k & 1; a side stream all-reduces it and copies it to the host behind an event,
-        # so the host only ever waits for iteration k - 1 while iteration k is already running:
-        # the GPU never idles on the statistics (they are consumed one iteration late).
-        stats = [torch.zeros(2 * D + 3, dtype=torch.float64, device=dev) for _ in range(2)]
-        hosts = [torch.zeros(2 * D + 3, dtype=torch.float64).pin_memory() for _ in range(2)]
+        # adaptLag + 1 statistics slots (device vector + pinned host copy + "copy done" event).  Iteration k
+        # writes slot k % nslot; a side stream all-reduces it and copies it to the host behind an event,
+        # so the host only ever waits for iteration k - adaptLag while iteration k is already running:
+        # the GPU never idles on the statistics (they are consumed adaptLag iterations late).
+        nslot = adaptLag + 1
+        stats = [torch.zeros(2 * D + 3, dtype=torch.float64, device=dev) for _ in range(nslot)]
+        hosts = [torch.zeros(2 * D + 3, dtype=torch.float64).pin_memory() for _ in range(nslot)]
         hosts_np = [h.numpy() for h in hosts]
-        done = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(nslot)]
         main = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
         out = dict(acceptRate=[], meanAcceptProb=[], meanH=[], stepSize=[], numSteps=[])
@@ -298,7 +328,7 @@ class HMC:
         trace = (torch.empty((D, traceParticles, numIterations), dtype=ens.dtype, device=dev)
                  if traceParticles else None)
         self.integrator.q = ens.q
-        pending = None  # slot whose statistics are in flight
+        pending = []  # slots whose statistics are in flight, oldest first (at most adaptLag of them)
 
         def consume(slot, it):
             nonlocal nstat
@@ -320,7 +350,7 @@ class HMC:
                     self.integrator.numSteps = max(1, int(self.simulTime / self.stepSize))  # src/integrator.py:51
 
         for it in range(numIterations):
-            slot = it & 1
+            slot = it % nslot
             out["stepSize"].append(self.stepSize)
             out["numSteps"].append(self.integrator.numSteps)
             self.step(temperature, stats=stats[slot] if collectStats else None, reuseEndpoint=it > 0)
@@ -332,11 +362,11 @@ class HMC:
                     reducer.reduce(stats[slot])
                     hosts[slot].copy_(stats[slot], non_blocking=True)
                     done[slot].record(side)
-                if pending is not None:
-                    consume(*pending)  # statistics of the PREVIOUS iteration (one iteration stale)
-                pending = (slot, it)
-        if pending is not None:
-            consume(*pending)
+                if len(pending) >= adaptLag:
+                    consume(*pending.pop(0))  # statistics of iteration it - adaptLag
+                pending.append((slot, it))
+        for pd in pending:
+            consume(*pd)
         main.wait_stream(side)
         sum1 = torch.from_numpy(sum1)
         sum2 = torch.from_numpy(sum2)
@@ -346,7 +376,72 @@ class HMC:
         return out
 
 
-    def _run_fused(self, numIterations, temperature, adapt, targetAccept, adaptIterations, traceParticles, group):
+    def _run_mass_adapt(self, numIterations, temperature, *, adaptMass, massWindows, adapt, adaptIterations,
+                        traceParticles, **kw):
+        """run() in rescaled coordinates (see run(adaptMass=True)).
+
+        The call is cut into phases -- parallel.mass_windows during the warm-up, one phase for the rest -- and every
+        phase is an ordinary run() (one fused launch where that applies) on the ensemble in the coordinates
+        q' = q / massScale with the potential Potential.rescaled(massScale).  A window's var (returned by its run(),
+        all-reduced over ranks, pooled over the window's iterations) is the variance in the CURRENT coordinates, so
+        the scales compose multiplicatively.  Step-size adaptation restarts its gain sequence in every phase (each
+        run() call starts at k = 1), which lets the step size follow a new mass quickly, as Stan does."""
+        import torch
+
+        from .parallel import MassAdapter, mass_windows
+
+        ens = self.ensemble
+        if not ens.onDevice:
+            raise TypeError("HMC.run needs a device-backed Ensemble (device='cuda')")
+        D = ens.numDimensions
+        n = int(numIterations)
+        nAdapt = 0 if not adapt else (n if adaptIterations is None else min(n, int(adaptIterations)))
+        phases = mass_windows(nAdapt, massWindows) if adaptMass else ([(nAdapt, False)] if nAdapt else [])
+        phases = [(k, upd, True) for k, upd in phases]
+        if n - nAdapt > 0:
+            phases.append((n - nAdapt, False, False))
+        base = self.potential
+        scale = np.ones(D) if getattr(self, "massScale", None) is None else np.asarray(self.massScale, dtype=np.float64)
+        self.massScale = None  # (the phases below are plain run() calls)
+        adapter = MassAdapter(D)
+
+        def enter(s):
+            self.potential = base if np.all(s == 1.0) else base.rescaled(s)
+            return torch.as_tensor(s, dtype=ens.q.dtype, device=ens.device)[:, None]
+
+        st = enter(scale)
+        ens.q.div_(st)  # into the rescaled coordinates
+        out = dict(acceptRate=[], meanAcceptProb=[], meanH=[], stepSize=[], numSteps=[], massScale=[])
+        traces = []
+        r = None
+        try:
+            for k, updateMass, adaptive in phases:
+                r = self.run(k, temperature, adapt=adaptive, adaptIterations=k if adaptive else 0,
+                             traceParticles=traceParticles, **kw)
+                for key in ("acceptRate", "meanAcceptProb", "meanH", "stepSize", "numSteps"):
+                    out[key].extend(r[key])
+                out["massScale"].extend([scale.copy()] * k)
+                if r["trace"] is not None:
+                    traces.append(r["trace"] * st[:, :, None])  # original coordinates
+                if updateMass:
+                    cnt = float(k) * float(r.get("numParticlesTotal", ens.numParticles * r.get("worldSize", 1)))
+                    s_new = base.projectScales(adapter.scales(r["mean"].numpy(), r["var"].numpy(), cnt))
+                    ens.q.div_(torch.as_tensor(s_new, dtype=ens.q.dtype, device=ens.device)[:, None])
+                    scale = scale * s_new
+                    st = enter(scale)
+        finally:
+            ens.q.mul_(st)  # back to the original coordinates
+            self.potential = base
+        self.massScale = None if np.all(scale == 1.0) else scale
+        if r is not None:
+            sc = torch.from_numpy(scale)
+            out.update(mean=r["mean"] * sc, var=r["var"] * sc * sc, worldSize=r.get("worldSize", 1),
+                       fused=r.get("fused", False))
+        out["trace"] = torch.cat(traces, dim=2) if traces else None
+        return out
+
+    def _run_fused(self, numIterations, temperature, adapt, targetAccept, adaptIterations, traceParticles, group,
+                   adaptLag=1):
         """HMC.run as ONE launch: see run(fused=True) and csrc/k_small_ens.cuh."""
         import math
 
@@ -382,7 +477,8 @@ class HMC:
         q = ens.q
         bits = q.element_size() * 8
         _lib.hmc_run_ensemble(ctx, self.potential.handle(bits, ctx), q, self.integrator.mass, self._args(temperature), n,
-                              _lib.make_adapt_args(Ptot, adaptRows, target=targetAccept), state, comm=comm, history=hist,
+                              _lib.make_adapt_args(Ptot, adaptRows, target=targetAccept, lag=adaptLag), state, comm=comm,
+                              history=hist,
                               moments=mom, trace=None if trace is None else trace.view(D * ntrace, n),
                               trace_particles=ntrace, stream=_lib.current_stream_ptr(q))
         self.iteration += n

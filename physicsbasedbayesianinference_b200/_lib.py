@@ -92,6 +92,8 @@ class AdaptArgs(ctypes.Structure):
         ("minStep", ctypes.c_double),
         ("maxStep", ctypes.c_double),
         ("numParticlesTotal", ctypes.c_double),
+        ("lag", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -403,8 +405,9 @@ class Comm:
 
 
 def make_adapt_args(num_particles_total, adapt_iterations, target=0.8, gain0=1.5, kappa=0.5, max_move=0.7,
-                    min_step=1e-6, max_step=1e3):
+                    min_step=1e-6, max_step=1e3, lag=1):
     a = AdaptArgs()
+    a.lag = int(lag)
     a.struct_size = ctypes.sizeof(AdaptArgs)
     a.adaptIterations = int(adapt_iterations)
     a.targetAccept, a.gain0, a.kappa, a.maxMove = float(target), float(gain0), float(kappa), float(max_move)

@@ -236,8 +236,6 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
   } else if (!strcmp(name, "nbody_ti")) {
     if (value != 0 && value != 4 && value != 8) return fail(EHMC_ERR_INVALID, "nbody_ti must be 0, 4 or 8");
     c->nbody_ti = (int)value;
-  } else if (!strcmp(name, "ens_lockstep")) {
-    c->ens_lockstep = value != 0 ? 1 : 0;
   } else if (!strcmp(name, "ens_debug")) {
     if (!(value >= 0 && value <= 65536)) return fail(EHMC_ERR_INVALID, "ens_debug must be in [0, 65536]");
     c->ens_debug = (int)value;
@@ -390,10 +388,11 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
       break;
     }
     case EHMC_FAMILY_FUNNEL: {
-      if (nscalars != 2) { rc = fail(EHMC_ERR_INVALID, "funnel: scalars = {D, sigma_v}"); break; }
+      if (nscalars != 2 && nscalars != 4) { rc = fail(EHMC_ERR_INVALID, "funnel: scalars = {D, sigma_v [, scaleV, scaleX]}"); break; }
       p->D = (int)scalars[0];
       if (p->D < 2 || p->D > 32) { rc = fail(EHMC_ERR_UNSUPPORTED, "funnel: 2 <= D <= 32 (got %d)", p->D); break; }
       if (!(scalars[1] > 0)) rc = fail(EHMC_ERR_INVALID, "funnel: sigma_v must be > 0");
+      else if (nscalars == 4 && !(scalars[2] > 0 && scalars[3] > 0)) rc = fail(EHMC_ERR_INVALID, "funnel: scales must be > 0");
       break;
     }
     case EHMC_FAMILY_COIN_TOSS: {
@@ -1076,6 +1075,7 @@ extern "C" int ehmc_hmc_run_ensemble(ehmc_ctx* ctx, const ehmc_potential* pot, D
   if (!(ad->numParticlesTotal > 0) || !(ad->minStep > 0) || !(ad->maxStep >= ad->minStep))
     return fail(EHMC_ERR_INVALID, "%s: bad adaptation scalars", fn);
   if (comm && (comm->ctx != ctx || !comm->connected)) return fail(EHMC_ERR_INVALID, "%s: communicator not connected on this context", fn);
+  if (ad->lag < 0 || ad->lag > ENS_MAX_LAG) return fail(EHMC_ERR_INVALID, "%s: adapt.lag must be 0 (= 1), 1 or %d", fn, ENS_MAX_LAG);
   View vs, vh, vm, vt;
   TRY(parse_float(state, "state", 1, 64, &vs));
   if (vs.host || vs.shape[0] != 4) return fail(EHMC_ERR_INVALID, "%s: state must be a device float64[4]", fn);
@@ -1119,6 +1119,7 @@ extern "C" int ehmc_hmc_run_ensemble(ehmc_ctx* ctx, const ehmc_potential* pot, D
     EnsRunArgs<T> R;
     memset(&R, 0, sizeof(R));
     R.nIter = numIterations;
+    R.lag = ad->lag == 0 ? 1 : ad->lag;
     R.adaptIters = n_adapt;
     R.target = ad->targetAccept;
     R.maxMove = ad->maxMove;

@@ -27,8 +27,12 @@ static DenseSmallPot<T, DT> make_dense_small(const ehmc_potential* p) {
 template <typename T, int DT>
 static FunnelPot<T, DT> make_funnel(const ehmc_potential* p) {
   FunnelPot<T, DT> f;
-  f.inv_s2 = (T)(1.0 / (p->scalars[1] * p->scalars[1]));
-  f.half_dm1 = (T)(0.5 * (p->D - 1));
+  // scalars {D, sigma_v [, scaleV, scaleX]}: the funnel of v = scaleV q[0], x_k = scaleX q[k]
+  const double a = p->scalars.size() >= 4 ? p->scalars[2] : 1.0, cx = p->scalars.size() >= 4 ? p->scalars[3] : 1.0;
+  f.inv_s2 = (T)(a * a / (p->scalars[1] * p->scalars[1]));
+  f.half_dm1 = (T)(0.5 * a * (p->D - 1));
+  f.a = (T)a;
+  f.lnb = (T)(2.0 * std::log(cx));
   return f;
 }
 
@@ -60,8 +64,8 @@ static CoinPot<T, DT> make_coin(const ehmc_potential* p) {
 template <typename T, int DT, class Pot>
 static int launch_small_pot(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, int integ, bool hmc, cudaStream_t st) {
   static_assert(K1_THREADS == K1_THREADS_HOST, "K1 block size");
-  // statistics: per-thread accumulators [2DT+3][128] + per-warp rows [4][2DT+3] (doubles)
-  const size_t sm = A.partials != nullptr ? sizeof(double) * (K1_THREADS + K1_THREADS / 32) * (2 * DT + 3) : 0;
+  // statistics: per-warp value tiles + per-warp rows (WarpStats, k_small.cuh)
+  const size_t sm = A.partials != nullptr ? WarpStats<T, DT>::kSmemBytes : 0;
   unsigned grid = 1;
   auto go = [&](auto kernel) -> int {
     TRY(small_grid(c, kernel, sm, A.P, &grid));

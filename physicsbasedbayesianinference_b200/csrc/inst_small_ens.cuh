@@ -11,7 +11,7 @@ namespace ehmc {
 template <typename T, int DT, class Pot, bool EXACT>
 static int ens_launch(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, EnsRunArgs<T> R, cudaStream_t st) {
   auto kernel = k_small_ens<T, DT, Pot, INTEG_LEAPFROG, EXACT>;
-  const size_t sm = sizeof(double) * (K1_THREADS + K1_THREADS / 32) * (2 * DT + 3);
+  const size_t sm = std::max(WarpStats<T, DT>::kSmemBytes, ENS_SERVICE_SMEM);
   if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   int occ = 0, coop = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, K1_THREADS, sm));
@@ -23,28 +23,47 @@ static int ens_launch(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, EnsRunA
   if (cap <= ENS_SERVICE_CTAS) return fail(EHMC_ERR_UNSUPPORTED, "fused ensemble run: device too small");
   const unsigned ncompute = (unsigned)std::max<long long>(1, std::min<long long>(need, cap - ENS_SERVICE_CTAS));
   const int NS = 2 * A.D + 3;
-  // control block: hsched [nIter + 2] | published | ticket [2] | group tickets [2][ngroups] | rows [2][ncompute][NS] |
-  // group rows [2][ngroups][NS] | gains [adaptIters]
-  const size_t n_h = ((size_t)R.nIter + 2 + 15) / 16 * 16;  // (every section starts on a 128-byte line)
+  // batches of 32 particles, tied into groups of 2^bshift consecutive batches (one float64 row each): about 2048
+  // groups per iteration, at most ENS_MAX_GROUPS
+  const long long nbatch = (A.P + 31) / 32;
+  int bshift = 0;
+  while ((nbatch >> bshift) > 2048) ++bshift;
+  R.bshift = bshift;
+  R.nbatch = (unsigned)nbatch;
+  R.nvirt = (unsigned)((nbatch + (1LL << bshift) - 1) >> bshift);
+  static_assert(ENS_MAX_GROUPS >= 4096, "group count");
+  if (nbatch > 0x3FFFFFFFLL || ((long long)R.nIter << bshift) > 0x7FFFFFFFLL)
+    return fail(EHMC_ERR_UNSUPPORTED, "fused ensemble run: too many particles or iterations for one launch");
+  const unsigned V = R.nvirt, ngroups = (V + ENS_GROUP - 1) / ENS_GROUP;
+  // control block (every section on a 128-byte line): hsched [nIter + 1 + lag] | published replicas | ticket [ENS_RING]
+  // lines, cursor | group tickets [ENS_RING][ngroups] | done [V], arrived [V] | rows [ENS_RING][V][NS] | group rows
+  // [ENS_RING][ngroups][NS] | gains [adaptIters] | batch rows [nbatch][2 DT + 3] (state precision)
+  auto up = [](size_t n) { return (n + 15) / 16 * 16; };
+  const size_t n_h = up((size_t)R.nIter + 1 + ENS_MAX_LAG);
   const size_t n_pub = (size_t)ENS_PUB_COPIES * 16;
-  const size_t n_tk = 32 + (size_t)ENS_PUB_COPIES * 16;  // ticket[0], ticket[1] on lines of their own | arrival counters
-  const unsigned ngroups = (ncompute + ENS_GROUP - 1) / ENS_GROUP;
-  const size_t n_gt = ((size_t)2 * ngroups / 2 + 16) / 16 * 16;  // group tickets (unsigned) in units of doubles
-  const size_t n_rows = ((size_t)2 * ncompute * NS + 15) / 16 * 16;
-  const size_t n_grows = ((size_t)2 * ngroups * NS + 15) / 16 * 16;
-  const size_t bytes = sizeof(double) * (n_h + n_pub + n_tk + n_gt + n_rows + n_grows + (size_t)std::max(1, R.adaptIters)) + 128;
+  const size_t n_tk = 16 * (ENS_RING + 1);  // the tickets of the ring and the cursor: one line each
+  const size_t n_gt = up(((size_t)ENS_RING * ngroups + 1) / 2);   // ENS_RING * ngroups unsigned
+  const size_t n_done = 2 * up((size_t)V / 2 + 1);   // done [V], arrived [V] (unsigned)
+  const size_t n_rows = up((size_t)ENS_RING * V * NS);
+  const size_t n_grows = up((size_t)ENS_RING * ngroups * NS);
+  const size_t n_gains = up((size_t)std::max(1, R.adaptIters));
+  const size_t n_brows = up(((size_t)nbatch * (2 * DT + 3) * sizeof(T) + 7) / 8);
+  const size_t bytes = sizeof(double) * (n_h + n_pub + n_tk + n_gt + n_done + n_rows + n_grows + n_gains + n_brows) + 128;
   TRY(c->ens_ctl.ensure(bytes));
   double* base = reinterpret_cast<double*>(((uintptr_t)c->ens_ctl.ptr + 127) & ~(uintptr_t)127);
   R.hsched = base;
   R.published = reinterpret_cast<long long*>(base + n_h);
   R.ticket = reinterpret_cast<unsigned*>(base + n_h + n_pub);  // ticket[par] at R.ticket[32 * par] (see the kernel)
-  R.arrived = reinterpret_cast<unsigned long long*>(base + n_h + n_pub + 32);
-  R.lockstep = c->ens_lockstep;
+  R.cursor = reinterpret_cast<unsigned long long*>(base + n_h + n_pub + 16 * ENS_RING);
   R.gticket = reinterpret_cast<unsigned*>(base + n_h + n_pub + n_tk);
-  R.rows = base + n_h + n_pub + n_tk + n_gt;
+  R.done = reinterpret_cast<unsigned*>(base + n_h + n_pub + n_tk + n_gt);
+  R.arrived = reinterpret_cast<unsigned*>(base + n_h + n_pub + n_tk + n_gt + n_done / 2);
+  R.rows = base + n_h + n_pub + n_tk + n_gt + n_done;
   R.grows = R.rows + n_rows;
   double* gains = R.grows + n_grows;
-  CUDA_TRY(cudaMemsetAsync(base + n_h, 0, (n_pub + n_tk + n_gt) * sizeof(double), st));  // published = 0, all tickets = 0
+  R.brows = gains + n_gains;
+  // published = 0, tickets = 0, cursor = 0, group tickets = 0, done = 0, arrived = 0
+  CUDA_TRY(cudaMemsetAsync(base + n_h, 0, (n_pub + n_tk + n_gt + n_done) * sizeof(double), st));
   if (R.adaptIters > 0)  // R.gains arrives as a HOST array
     CUDA_TRY(cudaMemcpyAsync(gains, R.gains, sizeof(double) * R.adaptIters, cudaMemcpyHostToDevice, st));
   R.gains = gains;

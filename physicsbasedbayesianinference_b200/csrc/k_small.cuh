@@ -81,12 +81,16 @@ struct DenseSmallPot {  // U = 0.5 x^T Lambda x, x = q - mu;  grad = Lambda x
 };
 
 template <typename T, int DT>
-struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL)
-  T inv_s2;         // 1 / sigma_v^2
-  T half_dm1;       // 0.5 (D - 1) with the TRUE D
+struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL), optionally in rescaled coordinates:
+                    // v = a q[0], x_k = c q[k]:  U = inv_s2 q0^2 / 2 + 0.5 e^{lnb - a q0} sum q_k^2 + half_dm1 q0
+  T inv_s2;         // a^2 / sigma_v^2
+  T half_dm1;       // 0.5 a (D - 1) with the TRUE D
+  T a;              // scale of v (1 for the plain funnel)
+  T lnb;            // ln c^2   (0 for the plain funnel; a = 1, lnb = 0 reproduce the plain funnel bit for bit:
+                    //           0 - 1 * v and 1 * hs are exact)
   __device__ __forceinline__ T grad(const T (&q)[DT], T (&g)[DT], bool wantE) const {
     const T v = q[0];
-    const T ev = Ar<T>::exp_(-v);
+    const T ev = Ar<T>::exp_(Ar<T>::sub(lnb, Ar<T>::mul(a, v)));
     T s2 = T(0);
 #pragma unroll
     for (int d = 1; d < DT; ++d) {
@@ -94,14 +98,15 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL)
       g[d] = ev * q[d];
     }
     const T hs = T(0.5) * ev * s2;
-    g[0] = v * inv_s2 - hs + half_dm1;
+    const T ahs = a * hs;
+    g[0] = v * inv_s2 - ahs + half_dm1;
     return T(0.5) * v * v * inv_s2 + hs + half_dm1 * v;
   }
   static constexpr bool kPacked = true;
   // pair 0 = (v, q_1); padded dims hold q = 0 and contribute nothing
   __device__ __forceinline__ float grad2(const f32x2 (&Q)[(DT + 1) / 2], f32x2 (&G)[(DT + 1) / 2], bool) const {
     const float v = pk_lo(Q[0]), q1 = pk_hi(Q[0]);
-    const float ev = expf(-v);
+    const float ev = expf((float)lnb - (float)a * v);
     const f32x2 ev2 = pk2(ev, ev);
     f32x2 S = 0ull;
 #pragma unroll
@@ -111,7 +116,8 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL)
     }
     const float s2 = fmaf(q1, q1, pk_lo(S) + pk_hi(S));
     const float hs = 0.5f * ev * s2;
-    G[0] = pk2(v * (float)inv_s2 - hs + (float)half_dm1, ev * q1);
+    const float ahs = (float)a * hs;
+    G[0] = pk2(v * (float)inv_s2 - ahs + (float)half_dm1, ev * q1);
     return 0.5f * v * v * (float)inv_s2 + hs + (float)half_dm1 * v;
   }
   // Gradient and kick in one: V += c * grad U(Q).  For the pairs above the first, grad = e^{-v} q, so the kick is
@@ -120,7 +126,7 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL)
   static constexpr bool kFusedKick = true;
   __device__ __forceinline__ float kick2(const f32x2 (&Q)[(DT + 1) / 2], f32x2 (&V)[(DT + 1) / 2], float c) const {
     const float v = pk_lo(Q[0]), q1 = pk_hi(Q[0]);
-    const float ev = expf(-v);
+    const float ev = expf((float)lnb - (float)a * v);
     const float cev = c * ev;
     const f32x2 cev2 = pk2(cev, cev);
     f32x2 S = 0ull;
@@ -131,7 +137,8 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL)
     }
     const float s2 = fmaf(q1, q1, pk_lo(S) + pk_hi(S));
     const float hs = 0.5f * ev * s2;
-    V[0] = fma2(pk2(v * (float)inv_s2 - hs + (float)half_dm1, ev * q1), pk2(c, c), V[0]);
+    const float ahs = (float)a * hs;
+    V[0] = fma2(pk2(v * (float)inv_s2 - ahs + (float)half_dm1, ev * q1), pk2(c, c), V[0]);
     return 0.5f * v * v * (float)inv_s2 + hs + (float)half_dm1 * v;
   }
 };
@@ -330,39 +337,135 @@ __device__ __forceinline__ T kinetic(const T (&p)[DT], T m, T inv_m) {
   return Ar<T>::divm(Ar<T>::mul(T(0.5), s), m, inv_m);
 }
 
-// Block-level reduction of the per-thread statistics accumulators -> one row of partials.
-// Accumulators live in shared memory, sacc[j][thread] with a leading dimension of NTHREADS + 1 doubles (registers
-// are better spent on occupancy): j in [0..2] scalars, [3 .. 3+DT) sum q_d, [3+DT .. 3+2DT) sum q_d^2 (DT = padded D);
-// output row layout uses the true D: [0..2], [3 .. 3+D), [3+D .. 3+2D).
-// Thread j adds the NTHREADS entries of column j straight from shared memory (fixed order, four partial sums; the
-// odd leading dimension spreads the columns over the banks): ~250 issue slots of one warp, against ~1500 for the
-// tree of 2D+3 warp-shuffle reductions in every warp that this replaced -- the fused ensemble run pays it every
-// iteration.
-template <int NTHREADS, int DT>
-__device__ __forceinline__ void block_partials(double* out_row, int D, const double* sacc /*[2DT+3][NTHREADS + 1]*/) {
-  constexpr int NA = 2 * DT + 3, LD = NTHREADS + 1;
-  __syncthreads();
-  for (int j = threadIdx.x; j < NA; j += NTHREADS) {
-    const double* col = sacc + j * LD;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 8
-    for (int t = 0; t < NTHREADS; t += 4) {
-      s0 += col[t];
-      s1 += col[t + 1];
-      s2 += col[t + 2];
-      s3 += col[t + 3];
-    }
-    const double s = (s0 + s1) + (s2 + s3);
-    int o = j;
-    if (j >= 3 + DT) {
-      const int d = j - 3 - DT;
-      o = d < D ? 3 + D + d : -1;
-    } else if (j >= 3) {
-      o = (j - 3) < D ? j : -1;
-    }
-    if (o >= 0) out_row[o] = s;
+// Ensemble statistics {n_accept, sum acceptance probability, sum H, sum q_d, sum q_d^2}: one row of 2D+3 float64
+// partial sums per CTA (or per slice of the fused ensemble run).
+//
+// Every warp hands the DT+3 values of its 32 particles {accepted, acceptance probability, H, q_0 .. q_DT-1} through a
+// warp-private shared-memory tile in the state's own precision; lane j then owns value j: it reads the 32 entries of
+// its tile row with 16-byte loads, adds them and their squares in the state's precision (fixed order, four partial
+// sums), and adds the two results to its float64 REGISTER accumulators.  So a statistic is a float64 sum of
+// per-warp sums over 32 consecutive particles; in float32 mode those inner sums are float32 (relative error of a
+// statistic over 2^22 particles ~1e-9, far below its Monte-Carlo error, and independent of timing and -- for shards
+// that are multiples of 32 particles -- of the number of GPUs); in float64 mode everything is float64.
+// Measured on B200 (profiles/microbench/op_rates_r02.txt): the scheme this replaced -- 2DT+3 float64 accumulators
+// per THREAD in shared memory -- moved 16 B through shared memory per particle and statistic, 92 cycles of the SM's
+// 128 B/clk per warp of particles: 40 us per iteration of 2^22 particles whatever the trajectory length, a fifth of
+// config 5.  Summing exactly in float64 from the tile was no better (F2F.F64.F32 issues at a quarter rate: 32
+// conversions per lane and warp of particles).  This form moves 4 B in and 4 B out per value (29 cycles) and converts
+// twice per lane.
+template <typename T, int DT>
+struct WarpStats {
+  static constexpr int NV = DT + 3;                    // values per particle
+  static constexpr int NA = 2 * DT + 3;                // statistics columns
+  static constexpr int LD = 32 + 16 / (int)sizeof(T);  // tile row: 32 particles + 16 bytes (conflict-free 16-byte reads)
+  static constexpr int NSLOT = (NV + 31) / 32;         // values per lane
+  static constexpr int PER16 = 16 / (int)sizeof(T);
+  static constexpr size_t kTileBytes = sizeof(T) * NV * LD;                             // per warp
+  static constexpr size_t kSmemBytes = (K1_THREADS / 32) * (kTileBytes + sizeof(double) * NA);  // tiles | warp rows
+  double sum[NSLOT], sq[NSLOT];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int n = 0; n < NSLOT; ++n) sum[n] = sq[n] = 0.0;
   }
-}
+  // all 32 lanes call this together; lanes without a particle (on = false) contribute zeros.  Afterwards lane j holds
+  // in s[n], r[n] the sum and the sum of squares of value v = j + 32 n over the warp's 32 particles.
+  static __device__ __forceinline__ void reduce32(unsigned char* smem, bool on, T accepted, T accp, T H, const T (&q)[DT],
+                                                  T (&s)[NSLOT], T (&r)[NSLOT]) {
+    const int lane = threadIdx.x & 31;
+    T* tile = reinterpret_cast<T*>(smem + (threadIdx.x >> 5) * kTileBytes);
+    __syncwarp();  // the reads of the previous batch are done
+    tile[0 * LD + lane] = on ? accepted : T(0);
+    tile[1 * LD + lane] = on ? accp : T(0);
+    tile[2 * LD + lane] = on ? H : T(0);
+#pragma unroll
+    for (int d = 0; d < DT; ++d) tile[(3 + d) * LD + lane] = on ? q[d] : T(0);
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < NSLOT; ++n) {
+      const int v = lane + 32 * n;
+      s[n] = r[n] = T(0);
+      if (v < NV) {
+        const T* row = tile + v * LD;
+        T ps[PER16], pr[PER16];
+#pragma unroll
+        for (int t = 0; t < PER16; ++t) ps[t] = pr[t] = T(0);
+        // (not unrolled further: with all 32 values of the row in registers at once the trajectory kernel loses
+        // resident CTAs)
+#pragma unroll 2
+        for (int k = 0; k < 32; k += PER16) {
+          alignas(16) T x[PER16];
+          *reinterpret_cast<uint4*>(x) = *reinterpret_cast<const uint4*>(row + k);
+#pragma unroll
+          for (int t = 0; t < PER16; ++t) {
+            ps[t] += x[t];
+            pr[t] = x[t] * x[t] + pr[t];
+          }
+        }
+        if constexpr (PER16 == 4) {
+          s[n] = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+          r[n] = (pr[0] + pr[1]) + (pr[2] + pr[3]);
+        } else {
+          s[n] = ps[0] + ps[1];
+          r[n] = pr[0] + pr[1];
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void add(unsigned char* smem, bool on, T accepted, T accp, T H, const T (&q)[DT]) {
+    T s[NSLOT], r[NSLOT];
+    reduce32(smem, on, accepted, accp, H, q, s, r);
+#pragma unroll
+    for (int n = 0; n < NSLOT; ++n) {
+      sum[n] += (double)s[n];
+      sq[n] += (double)r[n];
+    }
+  }
+  // The warp's 32 particles as ONE row of NA values in the state's precision, padded layout ([0..2], [3 .. 3+DT) sums,
+  // [3+DT .. 3+2DT) squares): the fused ensemble run's per-batch rows.
+  static __device__ __forceinline__ void batch_row(unsigned char* smem, T* out, bool on, T accepted, T accp, T H,
+                                                   const T (&q)[DT]) {
+    T s[NSLOT], r[NSLOT];
+    reduce32(smem, on, accepted, accp, H, q, s, r);
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int n = 0; n < NSLOT; ++n) {
+      const int v = lane + 32 * n;
+      if (v < NV) {
+        out[v] = s[n];
+        if (v >= 3) out[DT + v] = r[n];
+      }
+    }
+  }
+  // the CTA's row: warp sums through shared memory, added in warp order; padded dimensions are dropped
+  // (row layout with the true D: [0..2], [3 .. 3+D) sum q_d, [3+D .. 3+2D) sum q_d^2).  Contains block-wide barriers.
+  __device__ __forceinline__ void store_row(unsigned char* smem, double* out_row, int D) const {
+    constexpr int NWARP = K1_THREADS / 32;
+    double* wrows = reinterpret_cast<double*>(smem + NWARP * kTileBytes);  // [NWARP][NA]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int n = 0; n < NSLOT; ++n) {
+      const int v = lane + 32 * n;
+      if (v < NV) {
+        wrows[w * NA + v] = sum[n];
+        if (v >= 3) wrows[w * NA + DT + v] = sq[n];
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < NA; j += K1_THREADS) {
+      double t = wrows[j];
+#pragma unroll
+      for (int k = 1; k < NWARP; ++k) t += wrows[k * NA + j];
+      int o = j;
+      if (j >= 3 + DT) {
+        const int d = j - 3 - DT;
+        o = d < D ? 3 + D + d : -1;
+      } else if (j >= 3) {
+        o = (j - 3) < D ? j : -1;
+      }
+      if (o >= 0) out_row[o] = t;
+    }
+  }
+};
 
 // ---------------------------------------------------------------------------
 // Kernel.  HMC = false: Leapfrog/StormerVerlet.integrate on (q, p) in place.
@@ -378,27 +481,26 @@ __device__ __forceinline__ void block_partials(double* out_row, int D, const dou
 // instead of behind them (profiles/r01_k1_dbg_probe.txt, r01_ncu_full_k1l4_before.txt).
 struct NoStepHook {};  // k_small_body: the step size is A.h
 
-template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT, class StepHook = NoStepHook>
+// WARP: the calling WARP runs particles 0 .. A.P - 1 (A.P <= 32: one batch) on its own -- no block-wide barrier
+// anywhere, A.partials is the batch's row of statistics in the state's precision (WarpStats::batch_row); otherwise the
+// CTA is number blk of nblk CTAs walking the particles, 128 at a time, and A.partials holds one float64 row per CTA.
+template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT, class StepHook = NoStepHook, bool WARP = false>
 __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& pot, double* k1_smem, unsigned blk,
-                                             unsigned nblk,  // this CTA is number blk of nblk walking the particles
-                                             const StepHook& hook = StepHook()) {
+                                             unsigned nblk, const StepHook& hook = StepHook()) {
   // the fused ensemble run (k_small_ens) learns the step size of the iteration from `hook`, called once, behind the
   // first momentum draw (work that does not depend on h)
   T h = A.h, h2 = A.h2;
   bool h_known = std::is_same<StepHook, NoStepHook>::value;
   const int Dn = EXACT ? DT : A.D;
-  constexpr int NA = 2 * DT + 3;
   const bool want_stats = HMC && A.partials != nullptr;
-  constexpr int LD = K1_THREADS + 1;
-  double* sacc = k1_smem + threadIdx.x;          // [NA][LD], this thread's column
-  if (want_stats) {
-#pragma unroll 1
-    for (int j = 0; j < NA; ++j) sacc[j * LD] = 0.0;
-  }
-  const long long stride = (long long)nblk * K1_THREADS;
+  unsigned char* stats_smem = reinterpret_cast<unsigned char*>(k1_smem);
+  WarpStats<T, DT> ws;
+  ws.clear();
+  const long long stride = WARP ? 32 : (long long)nblk * K1_THREADS;
+  const int t_in = WARP ? (threadIdx.x & 31) : threadIdx.x;
 
-  for (long long base = (long long)blk * K1_THREADS; base < A.P; base += stride) {
-    const long long i = base + threadIdx.x;
+  for (long long base = WARP ? 0 : (long long)blk * K1_THREADS; base < A.P; base += stride) {
+    const long long i = base + t_in;
     const bool active = i < A.P;
     const long long ic = active ? i : 0;  // inactive threads shadow particle 0, never store
 
@@ -476,25 +578,22 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
       if (A.accept != nullptr) A.accept[i] = rej ? 0 : 1;
     }
 
-    if (want_stats && active) {
-      // kept state for the statistics
-      if (rej) {
+    if (want_stats) {
+      // kept state for the statistics (lanes without a particle add zeros)
+      if (rej && active) {
 #pragma unroll
         for (int d = 0; d < DT; ++d) q[d] = d < Dn ? A.q[d * A.q_ld + i] : T(0);
       }
-      sacc[0 * LD] += rej ? 0.0 : 1.0;
-      sacc[1 * LD] += (double)accp;
-      sacc[2 * LD] += (double)(rej ? oldH : newH);
-#pragma unroll
-      for (int d = 0; d < DT; ++d) {
-        const double qd = (double)q[d];
-        sacc[(3 + d) * LD] += qd;
-        sacc[(3 + DT + d) * LD] = fma(qd, qd, sacc[(3 + DT + d) * LD]);
-      }
+      if constexpr (WARP)
+        WarpStats<T, DT>::batch_row(stats_smem, reinterpret_cast<T*>(A.partials), active, rej ? T(0) : T(1), accp,
+                                    rej ? oldH : newH, q);
+      else
+        ws.add(stats_smem, active, rej ? T(0) : T(1), accp, rej ? oldH : newH, q);
     }
   }
-  if (want_stats)
-    block_partials<K1_THREADS, DT>(A.partials + (size_t)blk * (2 * Dn + 3), Dn, k1_smem);
+  if constexpr (!WARP) {
+    if (want_stats) ws.store_row(stats_smem, A.partials + (size_t)blk * (2 * Dn + 3), Dn);
+  }
 }
 
 // Two kernels (picked on the host by D == DT) rather than one with both bodies: a kernel gets the register
@@ -502,7 +601,7 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
 // measured 7 % slower at config 5: the Philox rounds of the three blocks no longer interleave.)
 template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT>
 __global__ void __launch_bounds__(K1_THREADS) k_small(const IterArgs<T> Ain, const Pot pot) {
-  extern __shared__ double k1_smem[];
+  extern __shared__ __align__(16) double k1_smem[];
   const IterArgs<T> A = resolve_dynamic(Ain);
   k_small_body<T, DT, Pot, INTEG, HMC, EXACT>(A, pot, k1_smem, blockIdx.x, gridDim.x);
 }

@@ -9,43 +9,71 @@
 // particles) against 33 us of kernel (profiles/r01_adapt_probe.txt).
 //
 // Structure (grid = one resident wave, cooperative launch so that every CTA is co-resident):
-//   * COMPUTE CTAs run k_small_body for iteration `it` over their grid-stride share of the particles (the same
-//     particles every iteration: q round-trips through HBM, nothing crosses CTAs), deposit their row of 2D+3 partial
-//     sums and release a ticket (fire and forget).  They never wait for the statistics: iteration `it` only needs
-//     the step size h[it], published two iterations earlier, and even that wait sits behind the momentum draw.
-//   * 8 SERVICE CTAs = 32 independent reducer warps: warp w adds the rows of compute CTAs 32 w .. 32 w + 31 (fixed
-//     order) when their tickets are in; the master warp adds the ~33 group rows, pushes the 2D+3 doubles into every
-//     peer GPU's mailbox with plain stores over NVLink (peer memory mapped through CUDA IPC), waits for the peers'
-//     pushes, adds the world's vectors in rank order (every rank computes the same bits), updates log h and
-//     publishes h[it + 2]: the one-iteration-stale pipeline of HMC.run, so the reductions, the NVLink round trip
-//     (~184 B out and in per peer, a few microseconds) and the update all hide behind iteration it + 1.
-// Per-iteration cost on the compute CTAs' path: the block reduction of their own row.
+//   * the unit of work is a BATCH of 32 consecutive particles run by one warp.  The warps of the compute CTAs take
+//     (iteration, batch) pairs in order from one global cursor; when an iteration's batches are all taken the cursor
+//     simply runs on into the next iteration.  A warp runs k_small_body on its batch (q round-trips through HBM / L2)
+//     and writes the batch's row of 2D+3 sums in the state's precision.  Batches are tied into GROUPS of 2^k
+//     consecutive batches: the warp that arrives last in a group (one acq_rel atomic per batch) adds the group's
+//     batch rows in batch order into one float64 row, marks the group's iteration complete (the batches of the next
+//     iteration of that group wait for this mark: it orders iteration it + 1 of a particle behind iteration it,
+//     whoever ran it) and releases a ticket (fire and forget).  Nothing here waits for the statistics: iteration
+//     `it` only needs the step size h[it], published 1 + lag iterations earlier.
+//   * 8 SERVICE CTAs = 32 independent reducer warps: warp w adds the rows of 64 consecutive groups (fixed order)
+//     when their tickets are in; the master warp adds those, sends the 2D+3 doubles to every peer GPU's mailbox with
+//     8-byte stores over NVLink that carry their own flags (peer memory mapped through CUDA IPC), collects the peers'
+//     vectors, adds the world's vectors in rank order (every rank computes the same bits), updates log h and
+//     publishes h[it + 1 + lag]: with lag = 1 the one-iteration-stale pipeline of HMC.run, so the reductions, the
+//     NVLink round trip (368 B out and in per peer, a few microseconds) and the update hide behind iteration it + 1;
+//     lag = 2 gives them two iterations (at 2^19 particles per GPU an iteration is 30 us and the chain -- last
+//     batch, three reduction levels, the slowest of 8 GPUs, publish -- measured 20-30 us:
+//     profiles/r02_bench_n8_mid.json was taken with lag = 1 and waited for h in every iteration).
+// Why batches and a queue (measured at 2^19 particles per GPU, the 8-GPU shard of config 5, 28.8 us for the bare
+// per-launch kernel): a fixed share per CTA is 3.46 blocks of 128 that round up to 4, and the warp schedulers'
+// preference for the oldest warps let the oldest CTAs of every SM finish early and wait ahead of the others (39 us
+// per iteration); CTA-wide slices of 128 particles from a queue need three block barriers per slice and expose the
+// queue's L2 round trips to four warps at once (41 us); warp-wide slices of 128 particles make an iteration as long
+// as one warp needs for four batches in a row, because every slice of an iteration is in flight at once (72 us).
+// With single batches a warp has 3.5 of them per iteration and the order of the queue keeps every dependency
+// (previous iteration of the same group, step size) a full iteration behind the cursor.
+// The statistics are deterministic: rows belong to batches and groups, never to whichever warp ran them.
 #pragma once
 
 #include "k_small.cuh"
 
 namespace ehmc {
 
-constexpr int ENS_PUB_COPIES = 64; // replicas of the "step sizes published" counter, one 128-byte line each
+constexpr int ENS_PUB_COPIES = 32; // replicas of the "step sizes published" counter, one 128-byte line each (one per
+                                   // lane of the master warp: a single release store each)
 constexpr int ENS_SERVICE_CTAS = 8; // blocks of reducer warps (one of them also runs the all-reduce and the update)
-constexpr int ENS_GROUP = 32;      // compute CTAs per first-level reduction group
-constexpr int ENS_MB_STRIDE = 72;  // doubles per mailbox slot: up to 2 * 32 + 3 statistics, last one = sequence flag
+constexpr int ENS_GROUP = 64;      // group rows per first-level reduction of the service warps
+constexpr int ENS_MAX_GROUPS = 8192;  // groups per iteration at most (the launcher aims at 2048)
+constexpr int ENS_MB_STRIDE = 144;  // 8-byte words per mailbox slot: two per statistic (up to 2 * 32 + 3 statistics)
+constexpr int ENS_RING = 4;        // iterations in flight at most (lag <= 2): rows, tickets and step sizes are rings of 4
+constexpr int ENS_MAX_LAG = 2;
+constexpr size_t ENS_SERVICE_SMEM = 5632;  // master warp: two vectors of <= 72 doubles + [8 ranks][2 * 67] received halves
 
 template <typename T>
 struct EnsRunArgs {
   int nIter;
+  int lag;             // the statistics of iteration it set the step size of iteration it + 1 + lag (1 or 2)
   int adaptIters;      // Robbins-Monro updates during the first adaptIters iterations of this launch
   double target, maxMove, logLo, logHi;
   const double* gains;  // [adaptIters] Robbins-Monro gain of every update, gain0 / k^kappa (host-computed)
   double Ptot;         // particles of all ranks
-  double* hsched;      // [nIter + 2] step size of every iteration
-  long long* published;  // [ENS_PUB_COPIES][16] number of valid hsched entries (replicated, one line per copy)
-  unsigned long long* arrived;  // [ENS_PUB_COPIES][16] compute CTAs that finished an iteration, ever (soft grid barrier)
-  int lockstep;        // 1: iterations start in step (soft grid barrier)
-  unsigned* ticket;    // [2][32] (entry 0 of each 128-byte line) groups whose rows of the iteration of this parity are reduced
-  unsigned* gticket;   // [2][ngroups] compute CTAs of the group that finished the iteration
-  double* rows;        // [2][ncompute][2D+3] per-CTA partial sums
-  double* grows;       // [2][ngroups][2D+3] per-group sums
+  double* hsched;      // [nIter + 1 + lag] step size of every iteration (the master's own record)
+  long long* published;  // [ENS_PUB_COPIES][16] per replica line: [0] iterations whose step size is published,
+                         //   [1 + it % ENS_RING] the step size of iteration it (double bits)
+  unsigned long long* cursor;   // [1] next (iteration * nbatch + batch) to hand out
+  unsigned* done;      // [nvirt] iterations of every group that are complete AND reduced into the group's row
+  unsigned* arrived;   // [nvirt] batches of every group that have finished, ever
+  void* brows;         // [nbatch][2 DT + 3] per-batch sums in the state's precision (padded layout)
+  unsigned nvirt;      // groups per iteration
+  unsigned nbatch;     // batches (32 particles) per iteration
+  int bshift;          // log2(batches per group)
+  unsigned* ticket;    // [ENS_RING][32] (entry 0 of each 128-byte line) groups of iteration it % ENS_RING that are reduced
+  unsigned* gticket;   // [ENS_RING][ngroups] group rows of the reduction group that are written
+  double* rows;        // [ENS_RING][nvirt][2D+3] per-group partial sums
+  double* grows;       // [ENS_RING][ngroups][2D+3] per-group sums
   double* state;       // [4] in/out: step size, log step size, updates k, iterations run
   double* history;     // [nIter][4] {accept rate, mean acceptance probability, mean H, step size used} or null
   double* moments;     // [2D] += sum q_d, sum q_d^2 of every iteration, or null
@@ -82,98 +110,199 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
-// Step size of iteration `it`, waited for INSIDE the trajectory body, behind the momentum draw of the CTA's first
-// particles (~300 instructions of Philox work that do not depend on h): lane 0 of every warp polls its replica of the
-// "published" counter, the warp shares the value.
-template <typename T>
-struct EnsStepHook {
-  const long long* pub;
-  const double* hsched;
-  int it;
-  long long* dbg;  // stamp slot of this iteration (thread 0 of CTA 0) or null
-  __device__ __forceinline__ void operator()(T& h, T& h2) const {
-    if ((threadIdx.x & 31) == 0) {
-      unsigned long long t0 = 0, t1 = 0;
-      if (dbg != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      while (ld_acquire_gpu(pub) < it + 1) __nanosleep(250);
-      if (dbg != nullptr && threadIdx.x == 0) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        dbg[6] = (long long)(t1 - t0);  // time spent waiting for the step size
-      }
-    }
-    __syncwarp();
-    h = (T)__ldcg(&hsched[it]);
-    h2 = h * h;
-  }
-};
-
 template <typename T, int DT, class Pot, int INTEG, bool EXACT>
-__global__ void __launch_bounds__(K1_THREADS) k_small_ens(const IterArgs<T> Ain, const Pot pot, const EnsRunArgs<T> R) {
-  extern __shared__ double k1_smem[];
+__global__ void __launch_bounds__(K1_THREADS, 8) k_small_ens(const IterArgs<T> Ain, const Pot pot, const EnsRunArgs<T> R) {
+  extern __shared__ __align__(16) double k1_smem[];
   const int Dn = EXACT ? DT : Ain.D;
   const int NS = 2 * Dn + 3;
   const unsigned ncompute = gridDim.x - ENS_SERVICE_CTAS;
-  const unsigned ngroups = (ncompute + ENS_GROUP - 1) / ENS_GROUP;
+  const unsigned V = R.nvirt;  // slices of `chunk` consecutive particles, one statistics row each
+  const unsigned ngroups = (V + ENS_GROUP - 1) / ENS_GROUP;
   const int tid = threadIdx.x;
+  constexpr int NWARP = K1_THREADS / 32;
+  constexpr int NAP = 2 * DT + 3;  // padded row of a batch
+  // per compute warp, lane 0's view of the queue (shared memory rather than registers: it lives across the trajectories)
+  __shared__ long long s_pub_seen[NWARP];          // newest value of the published counter the warp has seen
+  __shared__ double s_hring[NWARP][ENS_RING];      // step sizes read behind s_pub_seen
+  __shared__ unsigned s_done_seen[NWARP];          // "done" counter of the next batch's group when last looked at
+  __shared__ unsigned long long s_base[NWARP];     // cursor value of batch 0 of iteration s_next_it
+  __shared__ int s_next_it[NWARP];                 // the pair after the current one (-1: the queue is empty)
+  __shared__ unsigned s_next_b[NWARP];
+  __shared__ int s_it[NWARP];                      // the current pair and its step size, lane 0 -> the warp
+  __shared__ unsigned s_b[NWARP];
+  __shared__ double s_hcur[NWARP];
 
   if (blockIdx.x < ncompute) {
-    // ===== compute CTAs =====
-    IterArgs<T> A = Ain;
-    EnsStepHook<T> hook;
-    // (64 replicas of the counter on separate 128-byte lines: a thousand waiting CTAs polling ONE line kept its L2
-    // slice busy enough to slow the ticket atomics in its neighbourhood)
-    hook.pub = R.published + (blockIdx.x % ENS_PUB_COPIES) * 16;
-    hook.hsched = R.hsched;
-    for (int it = 0; it < R.nIter; ++it) {
-      auto stamp = [&](int k) {
-        if (R.dbg != nullptr && blockIdx.x == 0 && tid == 0 && it < R.dbg_iters) {
-          unsigned long long t;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-          R.dbg[it * 8 + k] = (long long)t;
-        }
-      };
-      stamp(5);
-      if (R.lockstep && it > 0) {
-        // soft grid barrier: nobody starts iteration `it` before every CTA has finished iteration it - 1.  Without it
-        // the warp schedulers' preference for the oldest warps lets the oldest CTAs of every SM run up to two
-        // iterations ahead and then wait there, so that on average only about half of the resident warps are
-        // runnable: measured 39.8 us per iteration at 2^19 particles against 33 us for iterations that start in step.
-        if (tid == 0) {
-          const unsigned long long want = (unsigned long long)ncompute * (unsigned long long)it;
-          while (ld_acquire_gpu_u64(R.arrived + (blockIdx.x % ENS_PUB_COPIES) * 16) < want) __nanosleep(100);
-        }
-        __syncthreads();
+    // ===== compute CTAs: four independent warps, each a worker of ONE queue over (iteration, batch) =====
+    // Lane 0 owns the warp's queue state: while a batch runs it already holds the cursor value of the NEXT pair, and
+    // when the batch is done it looks at that pair's group mark and at the published step sizes, so the top of the
+    // loop normally finds both satisfied; it spins only when the warp really is ahead of the pipeline.
+    // (replicas of the "published" line: thousands of warps polling ONE line kept its L2 slice busy enough to slow
+    // the ticket atomics in its neighbourhood)
+    const int lane = tid & 31, w = tid >> 5;
+    const long long* pub = R.published + ((blockIdx.x * NWARP + w) % ENS_PUB_COPIES) * 16;
+    const unsigned NB = R.nbatch;
+    const unsigned long long total = (unsigned long long)NB * (unsigned long long)R.nIter;
+    unsigned long long g_next = 0ull;  // (lane 0) the cursor value taken while the current batch runs
+    auto take = [&](unsigned long long g) {  // lane 0: pair g, and a non-blocking look at what it will need
+      if (g >= total) {
+        s_next_it[w] = -1;
+        return;
       }
-      hook.it = it;
-      hook.dbg = (R.dbg != nullptr && blockIdx.x == 0 && it < R.dbg_iters) ? R.dbg + it * 8 : nullptr;
-      A.iter = Ain.iter + (u64)it;
-      A.partials = R.rows + ((size_t)(it & 1) * ncompute) * NS;
-      k_small_body<T, DT, Pot, INTEG, true, EXACT>(A, pot, k1_smem, blockIdx.x, ncompute, hook);
+      // (a warp's cursor values only grow: no 64-bit division)
+      unsigned long long base = s_base[w];
+      int it = s_next_it[w];
+      while (g >= base + NB) {
+        base += NB;
+        ++it;
+      }
+      s_base[w] = base;
+      const unsigned b = (unsigned)(g - base);
+      s_next_it[w] = it;
+      s_next_b[w] = b;
+      s_done_seen[w] = it > 0 ? ld_acquire_gpu_u32(&R.done[b >> R.bshift]) : 0u;
+      if (s_pub_seen[w] < it + 1) {
+        s_pub_seen[w] = ld_acquire_gpu(pub);
+#pragma unroll
+        for (int k = 0; k < ENS_RING; ++k) s_hring[w][k] = __longlong_as_double(__ldcg(pub + 1 + k));
+      }
+    };
+    if (lane == 0) {
+      s_pub_seen[w] = 0;
+      s_base[w] = 0ull;
+      s_next_it[w] = 0;
+      take(atomicAdd(R.cursor, 1ull));
+    }
+    for (;;) {
+      if (lane == 0) {
+        const int it = s_next_it[w];
+        s_it[w] = it;
+        if (it >= 0) {
+          const unsigned b = s_next_b[w];
+          s_b[w] = b;
+          unsigned long long t0 = 0, t1 = 0;
+          const bool dbg = R.dbg != nullptr && it < R.dbg_iters && b == 0;
+          if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+          // the batch's positions were written by whoever ran it in the previous iteration
+          unsigned dn = s_done_seen[w];
+          while (dn < (unsigned)it) {
+            __nanosleep(100);
+            dn = ld_acquire_gpu_u32(&R.done[b >> R.bshift]);
+          }
+          long long ps = s_pub_seen[w];
+          while (ps < it + 1) {
+            __nanosleep(200);
+            ps = ld_acquire_gpu(pub);
+            if (ps >= it + 1) {
+#pragma unroll
+              for (int k = 0; k < ENS_RING; ++k) s_hring[w][k] = __longlong_as_double(__ldcg(pub + 1 + k));
+              s_pub_seen[w] = ps;
+            }
+          }
+          // (a ring slot is rewritten only after the iteration it belonged to has completed everywhere, and the
+          // counter is re-read whenever a newer iteration is needed, so slot it % ENS_RING read behind a counter
+          // value >= it + 1 holds the step size of iteration it: a later one of the same slot is published only
+          // after iteration it + ENS_RING - 1 - lag >= it + 1 has been reduced, i.e. after every batch of `it` ran)
+          s_hcur[w] = s_hring[w][it % ENS_RING];
+          if (dbg) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            R.dbg[it * 8 + 5] = (long long)t0;
+            R.dbg[it * 8 + 6] = (long long)(t1 - t0);  // time spent waiting for the group and the step size
+          }
+        }
+      }
+      __syncwarp();  // (also orders the other lanes' loads behind lane 0's acquires)
+      if (s_it[w] < 0) break;
+      // the round trip of the next atomic hides behind this batch (its result is first used after the trajectories)
+      if (lane == 0) g_next = atomicAdd(R.cursor, 1ull);
+      {
+        // (everything about the pair lives in this scope and is re-read from shared memory afterwards: values kept
+        // in registers across the trajectory body cost the kernel its eighth resident CTA per SM)
+        const int it = s_it[w];
+        const unsigned b = s_b[w];
+        const long long lo = (long long)b * 32;
+        IterArgs<T> A = Ain;
+        A.h = (T)s_hcur[w];
+        A.h2 = A.h * A.h;
+        A.P = min(32LL, Ain.P - lo);
+        A.q = Ain.q + lo;
+        A.mass = Ain.mass + lo;
+        A.offset = Ain.offset + (u64)lo;
+        if (Ain.accept != nullptr) A.accept = Ain.accept + lo;
+        A.iter = Ain.iter + (u64)it;
+        A.partials = reinterpret_cast<double*>(static_cast<T*>(R.brows) + (size_t)b * NAP);
+        k_small_body<T, DT, Pot, INTEG, true, EXACT, NoStepHook, true>(A, pot, k1_smem, 0u, 1u);
+      }
+      const int it = *(volatile int*)&s_it[w];
+      const unsigned b = *(volatile unsigned*)&s_b[w];
       if (R.trace != nullptr) {
         // kept positions of the first ntrace local particles (each thread re-reads what it wrote itself)
-        const long long stride = (long long)ncompute * K1_THREADS;
-        for (long long i = (long long)blockIdx.x * K1_THREADS + tid; i < R.ntrace; i += stride)
-          for (int d = 0; d < Dn; ++d) R.trace[((long long)d * R.ntrace + i) * R.S + R.s0 + it] = A.q[d * A.q_ld + i];
+        const long long i = (long long)b * 32 + lane;
+        if (i < min(R.ntrace, Ain.P))
+          for (int d = 0; d < Dn; ++d) R.trace[((long long)d * R.ntrace + i) * R.S + R.s0 + it] = Ain.q[d * Ain.q_ld + i];
       }
-      __syncthreads();  // the row of partial sums is written (and the reduction scratch is free again)
-      // fire and forget: the row is released to the reducer warp of this CTA's group; nothing here waits
-      if (tid == 0)
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&R.gticket[(it & 1) * ngroups + blockIdx.x / ENS_GROUP])
-                     : "memory");
-      if (R.lockstep && tid < ENS_PUB_COPIES)  // arrival counters, replicated like `published` (all of them count every CTA)
-        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(R.arrived + tid * 16) : "memory");
-      stamp(7);
+      __syncwarp();  // positions and the batch row are written (memory ordering among the warp's lanes)
+      const unsigned grp = b >> R.bshift;
+      const unsigned b0 = grp << R.bshift;
+      const unsigned cnt = min(1u << R.bshift, NB - b0);  // batches of this group
+      int last = 0;
+      if (lane == 0) {
+        // release: what the whole warp wrote is visible to whoever acquires; acquire: the last arrival sees the
+        // rows of every batch of the group
+        unsigned old;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(&R.arrived[grp]) : "memory");
+        last = (old + 1u == ((unsigned)it + 1u) * cnt) ? 1 : 0;
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        // the group's row: its batch rows in batch order, float64; padded dimensions are dropped
+        const int ring = it % ENS_RING;
+        const T* br = static_cast<const T*>(R.brows) + (size_t)b0 * NAP;
+        double* out = R.rows + ((size_t)ring * V + grp) * NS;
+        for (int j = lane; j < NAP; j += 32) {
+          double sum = 0.0;
+#pragma unroll 8
+          for (unsigned r = 0; r < cnt; ++r) sum += (double)__ldcg(&br[(size_t)r * NAP + j]);
+          int o = j;
+          if (j >= 3 + DT) {
+            const int d = j - 3 - DT;
+            o = d < Dn ? 3 + Dn + d : -1;
+          } else if (j >= 3) {
+            o = (j - 3) < Dn ? j : -1;
+          }
+          if (o >= 0) out[o] = sum;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&R.done[grp]), "r"((unsigned)it + 1u) : "memory");
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&R.gticket[ring * ngroups + grp / ENS_GROUP])
+                       : "memory");
+        }
+      }
+      if (lane == 0) {
+        if (R.dbg != nullptr && it < R.dbg_iters && b == 0) {
+          unsigned long long t;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+          R.dbg[it * 8 + 7] = (long long)t;
+        }
+        take(g_next);
+      }
     }
     return;
   }
 
   // ===== service CTAs (the last ENS_SERVICE_CTAS blocks): 32 independent warps, no block-wide barrier =====
-  // Warp w reduces the rows of groups w, w + 32, ... (ENS_GROUP consecutive compute CTAs each; lane j adds column j over
-  // the group's 32 rows: independent loads, one L2 round trip, fixed order) as soon as the group's tickets are in.
+  // Warp w reduces the rows of groups w, w + 32, ... (ENS_GROUP consecutive slices each; lane j adds column j over
+  // the group's rows: independent loads, fixed order) as soon as the group's tickets are in.
   // Warp 0 is also the MASTER: group rows -> this GPU's vector, all-reduce over NVLink, step-size update, publish.
   // Everything that polls or waits for L2 / NVLink latency lives here, off the compute CTAs' path; 190 KB of rows
   // through ONE CTA took longer than an iteration of the 8-GPU shard and set the pace of the whole run.
@@ -190,12 +319,13 @@ __global__ void __launch_bounds__(K1_THREADS) k_small_ens(const IterArgs<T> Ain,
       s_h = R.state[0];
       s_logh = R.state[1];
       s_k = (unsigned long long)R.state[2];
-      R.hsched[0] = s_h;
-      R.hsched[1] = s_h;
-      __threadfence();
+      for (int k = 0; k <= R.lag; ++k) R.hsched[k] = s_h;  // the first 1 + lag iterations run with the incoming step size
     }
-    __syncwarp();
-    for (int c = lane; c < ENS_PUB_COPIES; c += 32) st_release_gpu(R.published + c * 16, 2);
+    s_h = __shfl_sync(0xffffffffu, s_h, 0);
+    for (int c = lane; c < ENS_PUB_COPIES; c += 32) {
+      for (int k = 0; k <= R.lag; ++k) R.published[c * 16 + 1 + k] = __double_as_longlong(s_h);
+      st_release_gpu(R.published + c * 16, (long long)R.lag + 1);
+    }
   }
   auto stamp = [&](int it, int k) {
     if (R.dbg != nullptr && master && lane == 0 && it < R.dbg_iters) {
@@ -205,35 +335,36 @@ __global__ void __launch_bounds__(K1_THREADS) k_small_ens(const IterArgs<T> Ain,
     }
   };
   for (int it = 0; it < R.nIter; ++it) {
-    const int par = it & 1;
+    const int par = it & 1;          // mailbox slot (the masters of all ranks advance in step)
+    const int ring = it % ENS_RING;  // rows and tickets of this iteration
     // ---- first level: my groups ----
     for (unsigned g = sw; g < ngroups; g += NSW) {
-      const unsigned gsize = min((unsigned)ENS_GROUP, ncompute - g * ENS_GROUP);
-      unsigned* gt = &R.gticket[par * ngroups + g];
+      const unsigned gsize = min((unsigned)ENS_GROUP, V - g * ENS_GROUP);
+      unsigned* gt = &R.gticket[ring * ngroups + g];
       if (lane == 0) {
         while (ld_acquire_gpu_u32(gt) < gsize) __nanosleep(100);
-        *gt = 0u;  // next used two iterations later, behind the published step size
+        *gt = 0u;  // next used ENS_RING iterations later, behind a step size published after this iteration's update
       }
       __syncwarp();
-      const double* rows = R.rows + ((size_t)par * ncompute + (size_t)g * ENS_GROUP) * NS;
+      const double* rows = R.rows + ((size_t)ring * V + (size_t)g * ENS_GROUP) * NS;
       for (int j = lane; j < NS; j += 32) {
         double sum = 0.0;
 #pragma unroll 8
         for (unsigned r = 0; r < gsize; ++r) sum += __ldcg(&rows[(size_t)r * NS + j]);
-        R.grows[((size_t)par * ngroups + g) * NS + j] = sum;
+        R.grows[((size_t)ring * ngroups + g) * NS + j] = sum;
       }
       __syncwarp();
-      if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&R.ticket[32 * par]) : "memory");
+      if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&R.ticket[32 * ring]) : "memory");
     }
     if (!master) continue;
     // ---- master: second level, all-reduce, update, publish ----
     if (lane == 0) {
-      while (ld_acquire_gpu_u32(&R.ticket[32 * par]) < ngroups) __nanosleep(100);
-      R.ticket[32 * par] = 0u;  // nobody touches this parity again before h[it + 2] is published below
+      while (ld_acquire_gpu_u32(&R.ticket[32 * ring]) < ngroups) __nanosleep(100);
+      R.ticket[32 * ring] = 0u;  // nobody touches this ring slot again before the step size below is published
     }
     __syncwarp();
     stamp(it, 0);
-    const double* grows = R.grows + ((size_t)par * ngroups) * NS;
+    const double* grows = R.grows + ((size_t)ring * ngroups) * NS;
     for (int j = lane; j < NS; j += 32) {
       double sum = 0.0;
 #pragma unroll 8
@@ -243,34 +374,43 @@ __global__ void __launch_bounds__(K1_THREADS) k_small_ens(const IterArgs<T> Ain,
     __syncwarp();
     stamp(it, 1);
     if (R.world > 1) {
-      const unsigned long long seq = R.seq0 + (unsigned long long)it + 1ull;
+      // All-reduce, "LL" style: every 8-byte word that crosses NVLink carries its own flag -- {half of a double,
+      // 32-bit sequence number} -- so there is no separate flag store and no system-scope fence (remote stores +
+      // __threadfence_system + flag took 8-10 us here; this takes one NVLink store latency).  8-byte stores are
+      // single transactions; the slot of this parity was last written two iterations ago with sequence - 2.
+      const unsigned flag = (unsigned)(R.seq0 + (unsigned long long)it + 1ull);
       const size_t slot = ((size_t)par * R.world + R.rank) * ENS_MB_STRIDE;
-      // push: payload to every peer, then the sequence flag (release at system scope, behind the payload)
+      const int NW = 2 * NS;  // words per vector
+      for (int w = lane; w < NW; w += 32) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(loc[w >> 1]);
+        const unsigned half = (w & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+        const unsigned long long word = ((unsigned long long)flag << 32) | half;
+        for (int r = 0; r < R.world; ++r)
+          if (r != R.rank) st_relaxed_sys(reinterpret_cast<unsigned long long*>(R.peers[r]) + slot + w, word);
+      }
+      stamp(it, 2);
+      // receive: poll every word of every peer's slot in MY mailbox; halves go to shared memory
+      unsigned* rx = reinterpret_cast<unsigned*>(k1_smem + 144);  // [world][NW]
       for (int r = 0; r < R.world; ++r) {
         if (r == R.rank) continue;
-        double* dst = R.peers[r] + slot;
-        for (int j = lane; j < NS; j += 32) dst[j] = loc[j];
-      }
-      __threadfence_system();
-      __syncwarp();
-      if (lane < R.world && lane != R.rank)
-        st_release_sys(reinterpret_cast<unsigned long long*>(R.peers[lane] + slot + ENS_MB_STRIDE - 1), seq);
-      stamp(it, 2);
-      // wait for every peer's push of this iteration
-      if (lane < R.world && lane != R.rank) {
-        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(
-            R.peers[R.rank] + ((size_t)par * R.world + lane) * ENS_MB_STRIDE + ENS_MB_STRIDE - 1);
-        while (ld_acquire_sys(f) < seq) {
+        const unsigned long long* src =
+            reinterpret_cast<const unsigned long long*>(R.peers[R.rank]) + ((size_t)par * R.world + r) * ENS_MB_STRIDE;
+        for (int w = lane; w < NW; w += 32) {
+          unsigned long long word;
+          do {
+            word = ld_relaxed_sys(src + w);
+          } while ((unsigned)(word >> 32) != flag);
+          rx[r * NW + w] = (unsigned)word;
         }
       }
       __syncwarp();
       stamp(it, 3);
       for (int j = lane; j < NS; j += 32) {
         double s = 0.0;
-        for (int r = 0; r < R.world; ++r)  // rank order: the same bits on every rank
-          s += r == R.rank ? loc[j]
-                           : *reinterpret_cast<volatile const double*>(
-                                 R.peers[R.rank] + ((size_t)par * R.world + r) * ENS_MB_STRIDE + j);
+        for (int r = 0; r < R.world; ++r) {  // rank order: the same bits on every rank
+          const unsigned long long bits = ((unsigned long long)rx[r * NW + 2 * j + 1] << 32) | rx[r * NW + 2 * j];
+          s += r == R.rank ? loc[j] : __longlong_as_double((long long)bits);
+        }
         tot[j] = s;
       }
     } else {
@@ -279,7 +419,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_small_ens(const IterArgs<T> Ain,
     __syncwarp();
     if (lane == 0) {
       // Robbins-Monro on log h (parallel.StepSizeAdapter / ehmc_adapt_step): the update computed from iteration
-      // `it` is first used by iteration it + 2.  gains[i] = gain0 / (k0 + 1 + i)^kappa comes from the host.
+      // `it` is first used by iteration it + 1 + lag.  gains[i] = gain0 / (k0 + 1 + i)^kappa comes from the host.
       const double meanAcc = tot[1] / R.Ptot;
       if (it < R.adaptIters) {
         s_k += 1ull;
@@ -289,11 +429,15 @@ __global__ void __launch_bounds__(K1_THREADS) k_small_ens(const IterArgs<T> Ain,
         s_logh = fmin(fmax(s_logh + move, R.logLo), R.logHi);
         s_h = exp(s_logh);
       }
-      R.hsched[it + 2] = s_h;
-      __threadfence();
+      R.hsched[it + 1 + R.lag] = s_h;
     }
-    __syncwarp();
-    for (int c = lane; c < ENS_PUB_COPIES; c += 32) st_release_gpu(R.published + c * 16, (long long)it + 3);
+    {
+      const double hn = __shfl_sync(0xffffffffu, s_h, 0);
+      for (int c = lane; c < ENS_PUB_COPIES; c += 32) {
+        R.published[c * 16 + 1 + (it + 1 + R.lag) % ENS_RING] = __double_as_longlong(hn);
+        st_release_gpu(R.published + c * 16, (long long)it + 2 + R.lag);  // release: behind the step size in the same line
+      }
+    }
     stamp(it, 4);
     if (lane == 0 && R.history != nullptr) {
       R.history[4 * it + 0] = tot[0] / R.Ptot;

@@ -121,6 +121,51 @@ class StepSizeAdapter:
         return self.stepSize
 
 
+class MassAdapter:
+    """Ensemble-based diagonal mass adaptation (build-defined; BASELINE.json north_star: "step-size/mass adaptation
+    moments").  Consumes the all-reduced moments sum q_d, sum q_d^2 of a window of iterations -- the same numbers on
+    every rank, so every rank derives the same masses without a broadcast -- and returns per-dimension scales
+    s_d = sqrt(var_d): the coordinates are rescaled to q / s (unit marginal variances), which is HMC with the diagonal
+    mass matrix M_d = mass / s_d^2 (Stan's "diag_e" metric, M^-1 = var).  Shrunk towards 1 like Stan's estimator,
+    var <- n / (n + 5) var + 1e-3 * 5 / (n + 5), n = particles * iterations of the window."""
+
+    def __init__(self, numDimensions, minScale=1e-8, maxScale=1e8):
+        self.numDimensions = int(numDimensions)
+        self.minScale, self.maxScale = float(minScale), float(maxScale)
+
+    def scales(self, mean, var, count):
+        """mean, var: per-dimension moments over `count` samples (particles x iterations, all ranks)."""
+        import numpy as np
+
+        var = np.asarray(var, dtype=np.float64)
+        n = float(count)
+        v = n / (n + 5.0) * var + 1e-3 * 5.0 / (n + 5.0)
+        s = np.sqrt(np.where(np.isfinite(v) & (v > 0), v, 1.0))
+        return np.clip(s, self.minScale, self.maxScale)
+
+
+def mass_windows(adaptIterations, numWindows=3, first=0.15, last=0.1):
+    """Schedule of a mass-adapting warm-up of adaptIterations iterations, Stan-like: an initial step-size-only stretch
+    (`first` of the phase), numWindows windows of doubling length whose moments each give a new mass at their end,
+    and a final stretch (`last`) that re-tunes the step size for the final mass.  Returns a list of
+    (iterations, updateMassAfter) with the iterations summing to adaptIterations; phases too short to split keep the
+    step-size adaptation only."""
+    n = int(adaptIterations)
+    if n <= 0:
+        return []
+    if n < 20 or numWindows < 1:
+        return [(n, False)]
+    n0 = max(1, int(round(first * n)))
+    n1 = max(1, int(round(last * n)))
+    rest = n - n0 - n1
+    unit = rest / float(2**numWindows - 1)
+    w = [max(1, int(round(unit * 2**k))) for k in range(numWindows)]
+    w[-1] += rest - sum(w)
+    if w[-1] < 1:
+        return [(n, False)]
+    return [(n0, False)] + [(k, True) for k in w] + [(n1, False)]
+
+
 def unpack_stats(stats, numDimensions, numParticles):
     """Named view of the 2D+3 statistics vector of ehmc_hmc_iter (summed over ranks) for an
     ensemble of numParticles particles in total."""

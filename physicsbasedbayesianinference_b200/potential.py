@@ -81,6 +81,18 @@ class Potential:
     def gradient(self, q):
         return self._eval(q, False, True)[1]
 
+    # -- mass adaptation (HMC.run(adaptMass=True)) --------------------------------------
+    def rescaled(self, scales):
+        """The same potential in the coordinates q' = q / scales, U'(q') = U(scales * q'), as a descriptor of the
+        SAME family (so the kernels are untouched).  HMC on U' with the particle's scalar mass is HMC on U with
+        the diagonal mass matrix M_d = mass / scales_d**2."""
+        raise NotImplementedError(f"{type(self).__name__} has no rescaled form: mass adaptation is not available "
+                                  "for this family")
+
+    def projectScales(self, scales):
+        """The per-dimension scales this family can absorb (identity unless dimensions are tied)."""
+        return np.asarray(scales, dtype=np.float64)
+
 
 class HarmonicPotential(Potential):
     """U = 0.5 * dot(k, q**2) -- harmonicPotentialND (src/potential.py:18-27)."""
@@ -93,6 +105,9 @@ class HarmonicPotential(Potential):
 
     def _params(self):
         return [self.springConsts]
+
+    def rescaled(self, scales):
+        return HarmonicPotential(self.springConsts * np.asarray(scales, dtype=np.float64) ** 2)
 
 
 class GaussianPotential(Potential):
@@ -119,18 +134,42 @@ class GaussianPotential(Potential):
     def _params(self):
         return [self.precision, self.mean]
 
+    def rescaled(self, scales):
+        s = np.asarray(scales, dtype=np.float64)
+        return GaussianPotential(precision=self.precision * s[:, None] * s[None, :], mean=self.mean / s)
+
 
 class FunnelPotential(Potential):
-    """Neal's funnel: v = q[0] ~ N(0, sigmaV^2), q[k] ~ N(0, e^v)."""
+    """Neal's funnel: v = q[0] ~ N(0, sigmaV^2), q[k] ~ N(0, e^v).
+
+    scaleV, scaleX: the funnel in rescaled coordinates, v = scaleV * q[0], x_k = scaleX * q[k] (one scale for all x:
+    they are exchangeable) -- what mass adaptation produces (Potential.rescaled)."""
 
     family = _lib.FAMILY_FUNNEL
 
-    def __init__(self, numDimensions, sigmaV=3.0):
+    def __init__(self, numDimensions, sigmaV=3.0, scaleV=1.0, scaleX=1.0):
         self.sigmaV = float(sigmaV)
+        self.scaleV = float(scaleV)
+        self.scaleX = float(scaleX)
+        if not (self.scaleV > 0 and self.scaleX > 0):
+            raise ValueError("scaleV and scaleX must be > 0")
         super().__init__(numDimensions)
 
     def _scalars(self):
-        return [self.numDimensions, self.sigmaV]
+        if self.scaleV == 1.0 and self.scaleX == 1.0:
+            return [self.numDimensions, self.sigmaV]
+        return [self.numDimensions, self.sigmaV, self.scaleV, self.scaleX]
+
+    def projectScales(self, scales):
+        s = np.array(scales, dtype=np.float64)
+        s[1:] = np.sqrt(np.mean(s[1:] ** 2))  # pooled variance of the exchangeable dimensions
+        return s
+
+    def rescaled(self, scales):
+        s = np.asarray(scales, dtype=np.float64)
+        if not np.allclose(s[1:], s[1], rtol=1e-12):
+            raise ValueError("the funnel family ties the scales of q[1:] (use projectScales)")
+        return FunnelPotential(self.numDimensions, self.sigmaV, self.scaleV * s[0], self.scaleX * s[1])
 
 
 class CoinTossPotential(Potential):

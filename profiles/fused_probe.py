@@ -16,9 +16,8 @@ import os
 ctx = E._lib.Context.get()
 if os.environ.get("EHMC_ENS_DEBUG"):
     ctx.set_option("ens_debug", float(os.environ["EHMC_ENS_DEBUG"]))
-if os.environ.get("EHMC_ENS_LOCKSTEP"):
-    ctx.set_option("ens_lockstep", float(os.environ["EHMC_ENS_LOCKSTEP"]))
-for logP in (19, 20, 22):
+LAG = int(os.environ.get("EHMC_ADAPT_LAG", "2"))
+for logP in (19, 22):
     P = 1 << logP
     ens = E.Ensemble(D, P, dtype=np.float32, device="cuda", seed=1)
     ens.setPosition(1.0)
@@ -28,7 +27,7 @@ for logP in (19, 20, 22):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    r = hmc.run(n, 1 / KB, adapt=False, keepNumSteps=True)
+    r = hmc.run(n, 1 / KB, adapt=False, keepNumSteps=True, adaptLag=LAG)
     e1.record()
     torch.cuda.synchronize()
     fused = e0.elapsed_time(e1) / n

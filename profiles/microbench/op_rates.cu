@@ -22,8 +22,18 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, float s
   unsigned long long w[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) w[i] = ((unsigned long long)__float_as_uint(a[i]) << 32) | __float_as_uint(a[i] + 0.5f);
+  double dd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dd[i] = (double)a[i];
+  const double dseed = (double)seed;
+  extern __shared__ double sm64[];  // [8][1025]
+  if (OP >= 30 && OP <= 31) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm64[i * 1025 + threadIdx.x] = dd[i];
+  }
   const unsigned long long wseed = ((unsigned long long)__float_as_uint(seed) << 32) | __float_as_uint(seed);
-  long long t0 = clock64();
+  long long t0, t1;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0)::"memory");
   for (int it = 0; it < ITER; ++it) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -53,22 +63,35 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, float s
       if (OP == 23) asm volatile("lg2.approx.f32 %0, %0;" : "+f"(a[i]));
       if (OP == 24) asm volatile("sin.approx.f32 %0, %0;" : "+f"(a[i]));
       if (OP == 25) asm volatile("cvt.rn.f32.u32 %0, %1;" : "=f"(a[i]) : "r"(u[i] + it));  // I2FP (+ IADD)
+      if (OP == 27) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(dd[i]) : "d"(dseed) : "memory");               // DADD
+      if (OP == 28) asm volatile("fma.rn.f64 %0, %0, %1, %0;" : "+d"(dd[i]) : "d"(dseed) : "memory");           // DFMA
+      if (OP == 29) asm volatile("{.reg .f64 t; cvt.f64.f32 t, %0; cvt.rn.f32.f64 %0, t;}" : "+f"(a[i]));  // F2F.F64.F32 + F2F.F32.F64
+      if (OP == 35) asm volatile("{.reg .f64 t; cvt.f64.f32 t, %1; add.rn.f64 %0, %0, t;}" : "+d"(dd[i]) : "f"(a[(i + it) & 7]));  // F2F.F64.F32 + DADD
+      if (OP == 36) asm volatile("redux.sync.add.s32 %0, %0, 0xffffffff;" : "+r"(u[i]));  // REDUX
+      if (OP == 37) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(u[i]));  // SHFL
+      if (OP == 30) asm volatile("{.reg .f64 t; ld.shared.f64 t, [%0]; add.rn.f64 t, t, %1; st.shared.f64 [%0], t;}" ::"r"((unsigned)__cvta_generic_to_shared(&sm64[i * 1025 + threadIdx.x])), "d"(dseed) : "memory");  // LDS.64 + DADD + STS.64
+      if (OP == 31) asm volatile("{.reg .f64 t, c; cvt.f64.f32 c, %2; ld.shared.f64 t, [%0]; add.rn.f64 t, t, c; st.shared.f64 [%0], t;}" ::"r"((unsigned)__cvta_generic_to_shared(&sm64[i * 1025 + threadIdx.x])), "d"(dseed), "f"(a[i]) : "memory");  // the statistics update: F2F + LDS.64 + DADD + STS.64
+      if (OP == 32) asm volatile("{add.u32 %0, %0, %1; shf.l.wrap.b32 %1, %1, %1, 13; xor.b32 %1, %1, %0;}" : "+r"(u[i]), "+r"(u[(i + 1) & 7]));  // Threefry mix: IADD + SHF + LOP
+      if (OP == 33) asm volatile("add.u32 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]));              // IADD (register operands)
+      if (OP == 34) asm volatile("{.reg .b32 e; shr.u32 e, %1, 3; add.u32 e, e, 0x38000000; mov.b64 %0, {%2, e};}" : "=d"(dd[i]) : "r"(u[i]), "r"(u[(i + 1) & 7]));  // float -> double bits by integer ops (2 ALU + move)
       if (OP == 26) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(u[i]) : "r"(0xD2511F53u));  // IMAD.HI.U32
     }
   }
-  long long t1 = clock64();
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1)::"memory");
   float s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s += a[i] + __uint_as_float(u[i]) + __uint_as_float((uint32_t)w[i]) + __uint_as_float((uint32_t)(w[i] >> 32));
+  for (int i = 0; i < 8; ++i) s += (float)dd[i] + a[i] + __uint_as_float(u[i]) + __uint_as_float((uint32_t)w[i]) + __uint_as_float((uint32_t)(w[i] >> 32));
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
 template <int OP>
 void run(const char* name, float* out, long long* cyc) {
-  k<OP><<<148, 1024>>>(out, cyc, 1.0f);
+  const size_t smb = 8 * 1025 * sizeof(double);
+  cudaFuncSetAttribute(k<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+  k<OP><<<148, 1024, smb>>>(out, cyc, 1.0f);
   cudaDeviceSynchronize();
-  k<OP><<<148, 1024>>>(out, cyc, 1.0f);
+  k<OP><<<148, 1024, smb>>>(out, cyc, 1.0f);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[148];
   cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
@@ -112,5 +135,16 @@ int main() {
   run<23>("MUFU.LG2", out, cyc);
   run<24>("MUFU.SIN", out, cyc);
   run<25>("I2FP.F32.U32 (+ IADD)", out, cyc);
+  run<27>("DADD", out, cyc);
+  run<28>("DFMA", out, cyc);
+  run<29>("F2F.F64.F32 + F2F.F32.F64 (per pair)", out, cyc);
+  run<35>("F2F.F64.F32 + DADD (per pair)", out, cyc);
+  run<36>("REDUX.SUM.S32", out, cyc);
+  run<37>("SHFL.BFLY", out, cyc);
+  run<30>("LDS.64 + DADD + STS.64 (per group)", out, cyc);
+  run<31>("F2F + LDS.64 + DADD + STS.64 (per group)", out, cyc);
+  run<32>("IADD + SHF + LOP3 (per group)", out, cyc);
+  run<33>("IADD (register operands)", out, cyc);
+  run<34>("f32->f64 bits, integer ops (per group)", out, cyc);
   return 0;
 }

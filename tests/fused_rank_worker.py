@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--P", type=int, default=8192)
     ap.add_argument("--S", type=int, default=24)
+    ap.add_argument("--lag", type=int, default=1)
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -37,7 +38,7 @@ def main():
     ens.q.copy_(torch.tensor(q0[:, lo:hi]))
     hmc = E.HMC(ens, L * 0.05 + 1e-9, 0.05, None, potential=E.FunnelPotential(D, 3.0), seed=9, bugCompat=False)
     r = hmc.run(a.S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=a.S - 4, keepNumSteps=True, fused=True,
-                group=dist.group.WORLD if a.world > 1 else None, traceParticles=8)
+                group=dist.group.WORLD if a.world > 1 else None, traceParticles=8, adaptLag=a.lag)
     torch.cuda.synchronize()
     np.savez(a.out, q=ens.q.cpu().numpy(), stepSize=np.array(r["stepSize"]), acceptRate=np.array(r["acceptRate"]),
              meanH=np.array(r["meanH"]), mean=r["mean"].numpy(), var=r["var"].numpy(), lo=lo, hi=hi,

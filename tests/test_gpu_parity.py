@@ -407,12 +407,15 @@ def test_shard_invariance_and_column_views(E, case):
     E._lib.hmc_iter(ctx, h, parts[:, a:], mass[a:], mk(a), stats=st[1])
     torch.cuda.synchronize()
     assert torch.equal(full, parts)
-    # the statistics are plain sums over particles -> shard sums add up (allreduce semantics)
-    assert torch.allclose(st_full, st[0] + st[1], rtol=1e-12, atol=1e-9)
+    # the statistics are plain sums over particles -> shard sums add up (allreduce semantics).  float32 state: the
+    # sums over each warp's 32 particles are float32 (k_small.cuh WarpStats; the dense kernels sum in float64), and a
+    # shard boundary that is not a multiple of 32 regroups them
+    assert torch.allclose(st_full, st[0] + st[1], rtol=2e-6, atol=1e-4)
+    assert st_full[0].item() == st[0][0].item() + st[1][0].item()
     qf = full.double().cpu().numpy()
     assert st_full[0].item() <= P
-    np.testing.assert_allclose(st_full[3:3 + D].cpu().numpy(), qf.sum(1), rtol=1e-9, atol=1e-9)
-    np.testing.assert_allclose(st_full[3 + D:].cpu().numpy(), (qf * qf).sum(1), rtol=1e-9)
+    np.testing.assert_allclose(st_full[3:3 + D].cpu().numpy(), qf.sum(1), rtol=2e-6, atol=1e-3)
+    np.testing.assert_allclose(st_full[3 + D:].cpu().numpy(), (qf * qf).sum(1), rtol=2e-6)
 
 
 @pytest.mark.parametrize("case", ["diag2", "dense100"])
@@ -1246,11 +1249,13 @@ def test_run_device_adaptation_matches_host_adaptation(E, case):
 
 @pytest.mark.parametrize("case", ["funnel10", "diag3", "dense8", "coin2"])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-def test_run_fused_matches_host_loop(E, case, dt):
+@pytest.mark.parametrize("lag", [1, 2])
+def test_run_fused_matches_host_loop(E, case, dt, lag):
     """HMC.run(fused=True): trajectory kernel, statistics, step-size update in ONE persistent cooperative launch
-    (ehmc_hmc_run_ensemble) against the iteration-by-iteration host loop: same Philox stream, same
-    one-iteration-stale Robbins-Monro schedule.  The statistics are float64 sums in a different (fixed) order, so the
-    step sizes agree to 1e-12 and the chains to the float rounding of h."""
+    (ehmc_hmc_run_ensemble) against the iteration-by-iteration host loop: same Philox stream, same Robbins-Monro
+    schedule (the statistics of iteration k set the step size of iteration k + 1 + adaptLag).  The statistics are
+    float64 sums in a different (fixed) order, so the step sizes agree to 1e-12 and the chains to the float rounding
+    of h."""
     import torch
 
     P, S, L = 5000, 31, 5
@@ -1277,21 +1282,25 @@ def test_run_fused_matches_host_loop(E, case, dt):
 
     ens_h, hmc_h = fresh()
     rh = hmc_h.run(S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=24, keepNumSteps=True, fused=False,
-                   traceParticles=7)
+                   traceParticles=7, adaptLag=lag)
     ens_f, hmc_f = fresh()
     n0 = ctx.launch_count()
-    rf = hmc_f.run(S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=24, keepNumSteps=True, traceParticles=7)
+    rf = hmc_f.run(S, 1 / KB, adapt=True, targetAccept=0.8, adaptIterations=24, keepNumSteps=True, traceParticles=7,
+                   adaptLag=lag)
     assert rf.get("fused") and ctx.launch_count() - n0 == 1  # the default picks the fused path: ONE launch
     assert hmc_f.iteration == S and hmc_f.integrator.numSteps == L
     np.testing.assert_allclose(rf["stepSize"], rh["stepSize"], rtol=1e-12)
-    assert rf["stepSize"][0] == h0 and rf["stepSize"][1] == h0 and rf["stepSize"][2] != h0  # one iteration stale
-    assert rf["stepSize"][26] == rf["stepSize"][30]  # adaptation stops after adaptIterations
+    assert all(rf["stepSize"][k] == h0 for k in range(lag + 1)) and rf["stepSize"][lag + 1] != h0  # `lag` iterations stale
+    assert rf["stepSize"][25 + lag] == rf["stepSize"][30]  # adaptation stops after adaptIterations
     assert abs(hmc_f.stepSize - hmc_h.stepSize) <= 1e-12 * hmc_h.stepSize
     np.testing.assert_array_equal(rf["acceptRate"], rh["acceptRate"])
     np.testing.assert_allclose(rf["meanAcceptProb"], rh["meanAcceptProb"], rtol=1e-12)
     np.testing.assert_allclose(rf["meanH"], rh["meanH"], rtol=1e-12, atol=1e-12)
-    np.testing.assert_allclose(rf["mean"].numpy(), rh["mean"].numpy(), rtol=1e-11, atol=1e-13)
-    np.testing.assert_allclose(rf["var"].numpy(), rh["var"].numpy(), rtol=1e-10)
+    # (the float64 coin-toss chain is chaotic near the 1 / q poles: the last-bit difference between the device's and
+    # libm's exp(log h) reaches the moments of later iterations)
+    loose = case == "coin2" and dt == np.float64
+    np.testing.assert_allclose(rf["mean"].numpy(), rh["mean"].numpy(), rtol=1e-6 if loose else 1e-11, atol=1e-13)
+    np.testing.assert_allclose(rf["var"].numpy(), rh["var"].numpy(), rtol=1e-6 if loose else 1e-10)
     def same_chain(a, b):
         if dt == np.float32:
             return torch.equal(a, b)  # (float) h is the same number: identical bits
@@ -1309,7 +1318,8 @@ def test_run_fused_matches_host_loop(E, case, dt):
     np.testing.assert_allclose(r2f["stepSize"], r2h["stepSize"], rtol=1e-12)  # device exp() vs libm: 1 ulp
 
 
-def test_run_fused_two_ranks(E, tmp_path):
+@pytest.mark.parametrize("lag", [1, 2])
+def test_run_fused_two_ranks(E, tmp_path, lag):
     """The in-kernel all-reduce of the fused ensemble run: two processes (sharing this GPU: CUDA IPC mailboxes work
     within one device and the time-sliced persistent kernels still make progress), each with half of the ensemble,
     against one process with all of it.  Philox ids are global, so the ensemble statistics -- and with them the
@@ -1327,7 +1337,8 @@ def test_run_fused_two_ranks(E, tmp_path):
 
     def launch(rank, world, out):
         return subprocess.Popen([sys.executable, worker, "--rank", str(rank), "--world", str(world), "--port", str(port),
-                                 "--out", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                                 "--out", out, "--lag", str(lag)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                text=True)
 
     single = str(tmp_path / "single.npz")
     p = launch(0, 1, single)
@@ -1357,6 +1368,106 @@ def test_run_fused_two_ranks(E, tmp_path):
     np.testing.assert_array_equal(shards[0]["stepSize"], shards[1]["stepSize"])
     np.testing.assert_array_equal(shards[0]["meanH"], shards[1]["meanH"])
     np.testing.assert_array_equal(shards[0]["trace"], ref["trace"])
+
+
+# ---------------------------------------------------------------------------
+# mass adaptation (HMC.run(adaptMass=True)): rescaled coordinates == diagonal mass matrix
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["diag3", "dense8", "funnel5"])
+def test_rescaled_potential_is_hmc_with_diagonal_mass(E, case):
+    """One HMC iteration on Potential.rescaled(s) in the coordinates q / s (what run(adaptMass=True) launches) against
+    the oracle's leapfrog with the diagonal mass matrix M_d = mass / s_d^2 written out in the ORIGINAL coordinates:
+    same fed z and u, float64, 1e-11."""
+    rng = np.random.RandomState(31)
+    P, L, h = 257, 7, 0.11
+    if case == "diag3":
+        D, pe, po = 3, E.HarmonicPotential([4.0, 0.25, 1.0]), O.DiagGaussian(np.array([4.0, 0.25, 1.0]))
+        s = np.array([0.5, 2.0, 3.0])
+    elif case == "dense8":
+        D = 8
+        A = rng.standard_normal((D, D))
+        prec, mu = A @ A.T / D + np.eye(D), rng.standard_normal(D)
+        pe, po = E.GaussianPotential(precision=prec, mean=mu), O.DenseGaussian(prec, mu)
+        s = rng.uniform(0.3, 3.0, D)
+    else:
+        D, pe, po = 5, E.FunnelPotential(5, 3.0), O.Funnel(5, 3.0)
+        s = np.array([2.5, 0.7, 0.7, 0.7, 0.7])
+        assert np.array_equal(pe.projectScales([2.5, 0.5, 0.7, 0.9, 0.7])[1:], np.full(4, np.sqrt(np.mean(np.array([0.5, 0.7, 0.9, 0.7]) ** 2))))
+    q0 = rng.standard_normal((D, P))
+    z = rng.standard_normal((D, P))
+    u = rng.uniform(size=P)
+    mass = rng.uniform(0.5, 2.0, P)
+    qr, accr, oh, nh = O.hmc_iter_diag_mass(q0, z, u, mass, 1.0 / s**2, 1 / KB, h, L, po)
+    ps = pe.rescaled(s)
+    assert type(ps) is type(pe) and ps.family == pe.family
+    # the rescaled descriptor evaluates U(s * q') on the GPU
+    np.testing.assert_allclose(ps(q0 / s[:, None]), po.energy(q0), rtol=1e-12, atol=1e-12)
+    ens = E.Ensemble(D, P)
+    ens.q[:] = q0 / s[:, None]
+    ens.mass[:] = mass
+    hmc = E.HMC(ens, L * h + 1e-9, h, None, potential=ps, bugCompat=False)
+    acc = np.empty(P, dtype=np.uint8)
+    hmc.step(1 / KB, accept=acc, z=z, u=u)
+    clear = np.abs(u - np.minimum(1, np.exp(oh - nh))) > 1e-9
+    assert np.array_equal(acc.astype(bool)[clear], accr[clear])
+    same = acc.astype(bool) == accr
+    assert rel_err((ens.q * s[:, None])[:, same], qr[:, same]) < 1e-11
+
+
+@pytest.mark.parametrize("case", ["diag10", "dense20", "funnel10"])
+def test_run_adapt_mass(E, case):
+    """HMC.run(adaptMass=True): the all-reduced moments become per-dimension masses (coordinate scales) during the
+    warm-up; ensemble.q, mean, var and trace come back in the original coordinates; ESS per iteration of the worst
+    dimension rises against step-size adaptation alone (same seeds, same number of iterations)."""
+    import torch
+
+    from physicsbasedbayesianinference_b200 import diagnostics
+
+    rng = np.random.RandomState(41)
+    P, L, warm, S = 8192, 16, 200, 300
+    if case == "diag10":
+        D = 10
+        sd = np.logspace(-1.5, 1.0, D)
+        pot, h0, q_sd = E.HarmonicPotential(1.0 / sd**2), 0.01, sd
+    elif case == "dense20":
+        D = 20
+        A = rng.standard_normal((D, D))
+        corr = A @ A.T / D + 2.0 * np.eye(D)
+        dd = np.sqrt(np.diag(corr))
+        corr = corr / dd[:, None] / dd[None, :]
+        sd = np.logspace(-1.0, 1.0, D)
+        cov = corr * sd[:, None] * sd[None, :]
+        pot, h0, q_sd = E.GaussianPotential(cov=cov), 0.01, sd
+    else:
+        D = 10
+        pot, h0, q_sd = E.FunnelPotential(D, 3.0), 0.05, np.ones(D)
+    res = {}
+    for am in (False, True):
+        ens = E.Ensemble(D, P, dtype=np.float32, device="cuda", seed=3)
+        ens.q.copy_(torch.tensor(rng.standard_normal((D, P)) * q_sd[:, None] * 0.5, dtype=torch.float32))
+        hmc = E.HMC(ens, L * h0 + 1e-9, h0, None, potential=pot, seed=3, bugCompat=False)
+        rw = hmc.run(warm, 1 / KB, adapt=True, adaptMass=am, keepNumSteps=True)
+        r = hmc.run(S, 1 / KB, traceParticles=128)
+        torch.cuda.synchronize()
+        assert torch.isfinite(ens.q).all() and hmc.potential is pot
+        ess, _ = diagnostics.ess_min_over_dims(r["trace"].double().cpu())
+        res[am] = dict(ess=ess / S, scale=hmc.massScale, var=r["var"].numpy(), q=ens.q, acc=float(np.mean(r["acceptRate"])),
+                       h=hmc.stepSize, warm=rw)
+    assert res[False]["scale"] is None and res[True]["scale"] is not None
+    assert len(res[True]["warm"]["massScale"]) == warm and len(res[True]["warm"]["stepSize"]) == warm
+    if case != "funnel10":
+        # the adapted scales are the target's marginal standard deviations, and the moments come back in the
+        # original coordinates
+        np.testing.assert_allclose(res[True]["scale"], sd, rtol=0.15)
+        np.testing.assert_allclose(res[True]["var"], sd**2, rtol=0.15)
+        np.testing.assert_allclose(res[True]["q"].double().std(dim=1).cpu().numpy(), sd, rtol=0.1)
+        assert res[True]["ess"] > 3.0 * res[False]["ess"], (res[True]["ess"], res[False]["ess"])
+    else:
+        sc = res[True]["scale"]
+        assert np.all(sc[1:] == sc[1]) and sc[0] > 1.5  # x dimensions pooled; v has sd 3
+        assert res[True]["ess"] > 1.0 * res[False]["ess"], (res[True]["ess"], res[False]["ess"])
+    print(f"adaptMass {case}: ESS/iteration (worst dimension) {res[False]['ess']:.4f} -> {res[True]['ess']:.4f}; "
+          f"step {res[False]['h']:.4g} -> {res[True]['h']:.4g}; acceptance {res[False]['acc']:.3f} -> {res[True]['acc']:.3f}")
 
 
 # ---------------------------------------------------------------------------

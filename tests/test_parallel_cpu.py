@@ -42,7 +42,9 @@ def _worker(rank, world, port, D, P, q):
     u = parallel.unpack_stats(stats, D, P)
     ad = parallel.StepSizeAdapter(0.1, target=0.8)
     hs = [ad.update(u["meanAcceptProb"]) for _ in range(3)]
-    torch.save(dict(stats=stats, hs=hs, mean=u["mean"], var=u["var"], acc=u["acceptRate"]), f"/tmp/ehmc_par_{port}_{rank}.pt")
+    scales = torch.from_numpy(parallel.MassAdapter(D).scales(u["mean"].numpy(), u["var"].numpy(), P))
+    torch.save(dict(stats=stats, hs=hs, mean=u["mean"], var=u["var"], acc=u["acceptRate"], scales=scales),
+               f"/tmp/ehmc_par_{port}_{rank}.pt")
     dist.destroy_process_group()
 
 
@@ -58,6 +60,23 @@ def test_stats_allreduce_and_adaptation_gloo_world2():
     np.testing.assert_allclose(r[0]["mean"].numpy(), q.mean(1), rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(r[0]["var"].numpy(), q.var(1), rtol=1e-10)
     assert r[0]["acc"] == pytest.approx((q[0] > 0).mean())
+    # mass adaptation consumes the same all-reduced moments: identical masses on every rank, = the ensemble's std
+    assert torch.equal(r[0]["scales"], r[1]["scales"])
+    np.testing.assert_allclose(r[0]["scales"].numpy(), q.std(1), rtol=1e-2)
+
+
+def test_mass_adapter_and_windows():
+    ad = parallel.MassAdapter(3)
+    s = ad.scales(np.zeros(3), np.array([4.0, 0.25, np.nan]), 1e6)
+    np.testing.assert_allclose(s, [2.0, 0.5, 1.0], rtol=1e-5)  # non-finite moments leave the scale at 1
+    assert ad.scales(np.zeros(1), np.array([0.0]), 10)[0] == pytest.approx(np.sqrt(1e-3 * 5 / 15))  # Stan's shrinkage
+    for n in (0, 5, 19, 20, 100, 1000, 1237):
+        w = parallel.mass_windows(n, 3)
+        assert sum(k for k, _ in w) == n and all(k > 0 for k, _ in w)
+        if n >= 100:
+            upd = [k for k, u in w if u]
+            assert len(upd) == 3 and upd[0] < upd[1] < upd[2]  # doubling windows
+            assert not w[0][1] and not w[-1][1]  # step-size-only stretches at both ends
 
 
 def test_step_size_adapter_moves_towards_target():
