@@ -41,9 +41,12 @@
  *  where "particle id" is the GLOBAL index (particleOffset + column), so results
  *  do not depend on how the ensemble is sharded over GPUs.  float32: block b
  *  gives the standard normals of dimensions 4b..4b+3 (two Box-Muller pairs);
- *  float64: block b gives dimensions 2b, 2b+1 from 53-bit uniforms.  The
- *  Metropolis uniform uses block 0xFFFFFFFF.  oracle/hmc_oracle.py::philox_stream
- *  is the bit-level specification used by the tests.
+ *  float64: block b gives dimensions 2b, 2b+1 from 53-bit uniforms.
+ *  Metropolis uniform, stream version EHMC_RNG_STREAM_VERSION = 2: float32 state with D mod 4 in {1, 2} (the last
+ *  normal block, D / 4, leaves its words z and w unused): (z >> 8) 2^-24 of that block, so that a kernel which has
+ *  just drawn the momentum needs no further Philox block (D = 10: 3 blocks instead of 4); every other case: word x
+ *  (float64: x, y) of block 0xFFFFFFFF.  Version 1 (library versions < 110) always used block 0xFFFFFFFF.
+ *  oracle/hmc_oracle.py::philox_stream is the bit-level specification used by the tests.
  */
 #ifndef EHMC_H_
 #define EHMC_H_
@@ -56,7 +59,8 @@
 extern "C" {
 #endif
 
-#define EHMC_VERSION 100 /* 0.1.0 */
+#define EHMC_VERSION 110 /* 0.1.1 */
+#define EHMC_RNG_STREAM_VERSION 2 /* see "RNG stream" above */
 
 #if defined(__GNUC__)
 #define EHMC_API __attribute__((visibility("default")))
@@ -179,6 +183,8 @@ EHMC_API int ehmc_ctx_device_info(const ehmc_ctx* ctx, double out[4]);
  *   "dense_occupancy" 1|2: CTAs/SM variant of the float32 CUDA-core dense kernel
  *   "small_waves"     resident waves of CTAs of the persistent small-D kernel (default 8)
  *   "nbody_ti"        bodies per thread of the N-body kernel (0 auto, 4, 8)
+ *   "ens_sshift"      fused ensemble run: log2 of the 32-particle sub-batches a warp takes from the work queue at
+ *                     once (-1 auto: 0 below 2^21 particles per GPU, above that 1, or 2 for trajectories of <= 8 steps)
  *   "host_chunk_mb"   bytes of state per staged chunk on the host path
  *   "tc_debug", "tc_prof", "tc_prof_dump"  profiling aids of the tensor-core dense kernels */
 EHMC_API int ehmc_ctx_set_option(ehmc_ctx* ctx, const char* name, double value);
@@ -210,7 +216,8 @@ EHMC_API int ehmc_set_momentum(ehmc_ctx* ctx, DLTensor* p, const DLTensor* mass,
                       double temperature, uint64_t seed, uint64_t iteration,
                       uint64_t particleOffset, void* stream);
 /* Raw stream: z[D,P] standard normals and/or u[P] uniforms in [0,1) (either may be NULL)
- * exactly as ehmc_hmc_iter would draw them for (seed, iteration). */
+ * exactly as ehmc_hmc_iter would draw them for (seed, iteration) on a D-dimensional state; u without z is the
+ * uniform of block 0xFFFFFFFF (a state whose D is a multiple of 4). */
 EHMC_API int ehmc_philox_fill(ehmc_ctx* ctx, DLTensor* z, DLTensor* u, uint64_t seed, uint64_t iteration,
                      uint64_t particleOffset, void* stream);
 

@@ -403,6 +403,7 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 PHILOX_UNIFORM_BLOCK = 0xFFFFFFFF
+PHILOX_STREAM_VERSION = 2  # == EHMC_RNG_STREAM_VERSION (include/ehmc.h)
 
 
 def philox_stream(seed, iteration, particle_ids, num_dims, dtype=np.float32):
@@ -415,7 +416,9 @@ def philox_stream(seed, iteration, particle_ids, num_dims, dtype=np.float32):
           u1 = ((x>>8)+1) 2^-24 in (0,1], u2 = (y>>8) 2^-24 in [0,1).
     fp64: block b yields dimensions 2b, 2b+1 from one pair built out of 53-bit
           uniforms: u1 = (((x>>6)<<27 | (y>>5)) + 1) 2^-53,  u2 = ((z>>6)<<27 | (w>>5)) 2^-53.
-    Metropolis uniform: block 0xFFFFFFFF; fp32 (x>>8) 2^-24, fp64 ((x>>6)<<27 | y>>5) 2^-53.
+    Metropolis uniform (stream version 2, PHILOX_STREAM_VERSION): fp32 with D mod 4 in {1, 2} -- the last normal
+          block D // 4 leaves its words z, w unused -- (z>>8) 2^-24 of THAT block; otherwise block 0xFFFFFFFF:
+          fp32 (x>>8) 2^-24, fp64 ((x>>6)<<27 | y>>5) 2^-53.  (Version 1 always used block 0xFFFFFFFF.)
     Returns (z[D,P], u[P]) in float64 evaluated from the exact integer stream.
     """
     pid = np.asarray(particle_ids, dtype=np.uint64)
@@ -436,7 +439,10 @@ def philox_stream(seed, iteration, particle_ids, num_dims, dtype=np.float32):
                     d = 4 * b + 2 * j + t
                     if d < D:
                         z[d] = val
-        x, _, _, _ = philox4x32_10(lo, hi, PHILOX_UNIFORM_BLOCK, it, k0, k1)
+        if D % 4 in (1, 2):
+            _, _, x, _ = philox4x32_10(lo, hi, D // 4, it, k0, k1)
+        else:
+            x, _, _, _ = philox4x32_10(lo, hi, PHILOX_UNIFORM_BLOCK, it, k0, k1)
         u = (x >> np.uint32(8)).astype(np.float64) * 2.0**-24
     else:
         def u53(a, c):
@@ -460,11 +466,11 @@ def philox_stream(seed, iteration, particle_ids, num_dims, dtype=np.float32):
 # --------------------------------------------------------------------------
 def ess_geyer(x):
     """ESS of chains x[S, C] (S draws, C independent chains of one coordinate):
-    FFT autocovariance averaged over chains, Geyer initial-positive-sequence
+    centred on the grand mean, FFT autocovariance averaged over chains, Geyer initial-positive-sequence
     truncation.  Returns total ESS over all chains."""
     x = np.asarray(x, dtype=np.float64)
     S, C = x.shape
-    xc = x - x.mean(axis=0, keepdims=True)
+    xc = x - x.mean()  # grand mean: the chains are exchangeable
     n = 1 << (2 * S - 1).bit_length()
     f = np.fft.rfft(xc, n=n, axis=0)
     acov = np.fft.irfft(f * np.conj(f), n=n, axis=0)[:S] / S

@@ -32,7 +32,7 @@ class HMC:
     """Class with getSamples method (src/HMC.py:20-71)."""
 
     def __init__(self, ensemble, simulTime, stepSize, density, potential=None, gradient=None, method="Leapfrog",
-                 rng=None, seed=None, bugCompat=True, rejectNonFinite=False):
+                 rng=None, seed=None, bugCompat=True, rejectNonFinite=None):
         """
         ensemble (Ensemble)
         simulTime (float): duration of the Hamiltonian simulation
@@ -77,7 +77,11 @@ class HMC:
         self.rng = rng
         self.seed = ensemble.seed if seed is None else int(seed)
         self.bugCompat = bool(bugCompat)
-        self.rejectNonFinite = bool(rejectNonFinite)
+        # None: the reference's rule (a NaN ratio is ACCEPTED, src/HMC.py:168-173) for getSamples() / step(), rejection
+        # for run() -- an adaptive ensemble run must survive the divergent trajectories its own step-size search causes
+        # (funnel neck: inf - inf energies), one accepted NaN particle poisons the all-reduced moments for good
+        self.rejectNonFinite = None if rejectNonFinite is None else bool(rejectNonFinite)
+        self._inRun = False
         self.iteration = 0  # Philox iteration counter (persists across getSamples calls)
         self.massScale = None  # per-dimension coordinate scales of run(adaptMass=True): M_d = mass / massScale_d^2
         self.lastAccept = None
@@ -111,7 +115,7 @@ class HMC:
     # ------------------------------------------------------------------------------------
     def _flags(self):
         return (_lib.FLAG_BUGCOMPAT_MOMENTUM if self.bugCompat else 0) | (
-            _lib.FLAG_REJECT_NONFINITE if self.rejectNonFinite else 0)
+            _lib.FLAG_REJECT_NONFINITE if (self._inRun if self.rejectNonFinite is None else self.rejectNonFinite) else 0)
 
     def _args(self, temperature, dynamic=None, reuseEndpoint=False):
         integ = _lib.LEAPFROG if self.method == "Leapfrog" else _lib.STORMER_VERLET
@@ -270,6 +274,18 @@ class HMC:
         """
         if adaptLag not in (1, 2):
             raise ValueError("adaptLag must be 1 or 2")
+        if not self._inRun:
+            # everything below runs with _inRun set: non-finite acceptance ratios are rejected unless the driver was
+            # built with an explicit rejectNonFinite=False (see __init__)
+            self._inRun = True
+            try:
+                return self.run(numIterations, temperature, adapt=adapt, targetAccept=targetAccept,
+                                adaptIterations=adaptIterations, traceParticles=traceParticles, group=group,
+                                collectStats=collectStats, keepNumSteps=keepNumSteps, deviceAdapt=deviceAdapt,
+                                graph=graph, fused=fused, adaptLag=adaptLag, adaptMass=adaptMass,
+                                massWindows=massWindows)
+            finally:
+                self._inRun = False
         if adaptMass or getattr(self, "massScale", None) is not None:
             if adaptMass and not adapt:
                 raise ValueError("adaptMass=True needs adapt=True (the step size must follow the mass)")

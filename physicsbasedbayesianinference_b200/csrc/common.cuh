@@ -103,6 +103,33 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return r;
 }
 
+// bare MUFU forms (flush-to-zero: no denormal rescue code around the instruction)
+__device__ __forceinline__ float sqrt_ftz(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sin_ftz(float x) {
+  float r;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float cos_ftz(float x) {
+  float r;
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // Standard normals of one Philox block.
 // float : 4 normals (dims 4b .. 4b+3);  double: 2 normals (dims 2b, 2b+1).
 template <typename T>
@@ -126,24 +153,34 @@ struct NormalBlock<float> {
   }
   static __device__ __forceinline__ void transform(const uint4 r, float* z) {
     const float s = 5.9604644775390625e-8f;  // 2^-24
-    const float u1a = (float)((r.x >> 8) + 1u) * s, u2a = (float)(r.y >> 8) * s;
-    const float u1b = (float)((r.z >> 8) + 1u) * s, u2b = (float)(r.w >> 8) * s;
+    const float u1a = (float)((r.x >> 8) + 1u) * s, u1b = (float)((r.z >> 8) + 1u) * s;
     // Box-Muller on the SFU: r = sqrt(-2 ln u1) via lg2.approx (clamped: u1 -> 1 may give a tiny
     // positive lg2 error), angle via sin/cos.approx on [-pi, pi).  Absolute error ~5e-7, far below
     // the sampling noise; the integer stream (and therefore u) stays exact.
+    // The .ftz forms are bare MUFU instructions: u1 >= 2^-24 and -2 ln u1 is 0 or >= 1.19e-7, never denormal, and
+    // the plain forms wrap each MUFU.LG2 / MUFU.SQRT in a denormal rescue (FSETP + 2 predicated FMUL / FADD each:
+    // 30 of the ~110 instructions of five pairs).  The angle 2 pi (u2 - 1/2) is ONE FFMA on the integer.
     const float c = -1.3862943611198906f;  // -2 ln 2
-    const float ra = sqrt_approx(fmaxf(c * __log2f(u1a), 0.0f)), rb = sqrt_approx(fmaxf(c * __log2f(u1b), 0.0f));
-    const float ta = 6.283185307179586f * (u2a - 0.5f), tb = 6.283185307179586f * (u2b - 0.5f);
+    const float ra = sqrt_ftz(fmaxf(c * lg2_ftz(u1a), 0.0f)), rb = sqrt_ftz(fmaxf(c * lg2_ftz(u1b), 0.0f));
+    const float k2pi = 3.7450702829317378e-7f;  // 2 pi 2^-24
+    const float ta = fmaf((float)(r.y >> 8), k2pi, -3.14159265358979f), tb = fmaf((float)(r.w >> 8), k2pi, -3.14159265358979f);
     // cos(2 pi u) = -cos(2 pi (u - 1/2)), sin likewise
-    const float sa = -__sinf(ta), ca = -__cosf(ta), sb = -__sinf(tb), cb = -__cosf(tb);
+    const float sa = -sin_ftz(ta), ca = -cos_ftz(ta), sb = -sin_ftz(tb), cb = -cos_ftz(tb);
     z[0] = ra * ca;
     z[1] = ra * sa;
     z[2] = rb * cb;
     z[3] = rb * sb;
   }
-  static __device__ __forceinline__ float uniform(const PhiloxKey& K, u64 pid) {
-    const uint4 r = K.block(pid, EHMC_UNIFORM_BLOCK);
-    return (float)(r.x >> 8) * 5.9604644775390625e-8f;
+  // Metropolis uniform of a D-dimensional state (stream version 2): for D mod 4 in {1, 2} the last normal block
+  // (block D / 4) leaves its words z, w unused and the uniform is (z >> 8) 2^-24 of THAT block -- the kernels that
+  // have just drawn it keep the word instead of running a fourth Philox block (D = 10: 3 blocks instead of 4, D = 2:
+  // 1 instead of 2); otherwise word x of the dedicated block 0xFFFFFFFF as before.
+  static __host__ __device__ __forceinline__ bool uniform_in_normal_block(int D) { return ((D - 1) & 3) < 2; }
+  static __device__ __forceinline__ float uniform_from_word(uint32_t w) { return (float)(w >> 8) * 5.9604644775390625e-8f; }
+  static __device__ __forceinline__ float uniform(const PhiloxKey& K, u64 pid, int D) {
+    const bool spare = uniform_in_normal_block(D);
+    const uint4 r = K.block(pid, spare ? (uint32_t)(D >> 2) : EHMC_UNIFORM_BLOCK);
+    return uniform_from_word(spare ? r.z : r.x);
   }
 };
 
@@ -163,7 +200,10 @@ struct NormalBlock<double> {
     z[0] = rr * cs;
     z[1] = rr * sn;
   }
-  static __device__ __forceinline__ double uniform(const PhiloxKey& K, u64 pid) {
+  // (float64 normal blocks use all four words: the uniform always has its own block)
+  static __host__ __device__ __forceinline__ bool uniform_in_normal_block(int) { return false; }
+  static __device__ __forceinline__ double uniform_from_word(uint32_t) { return 0.0; }
+  static __device__ __forceinline__ double uniform(const PhiloxKey& K, u64 pid, int /*D*/) {
     const uint4 r = K.block(pid, EHMC_UNIFORM_BLOCK);
     return (double)u53(r.x, r.y) * 1.1102230246251565e-16;
   }

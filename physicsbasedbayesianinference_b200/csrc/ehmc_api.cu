@@ -28,11 +28,17 @@ using namespace ehmc;
 // errors
 // ---------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+// CUDA device of the device tensors parsed since the last entry point bound its context (-1: none yet), and whether
+// two of them disagreed; checked and cleared by enter_device(), cleared by every failure
+static thread_local int g_dev_seen = -1;
+static thread_local bool g_dev_mixed = false;
 
 int ehmc_fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  g_dev_seen = -1;
+  g_dev_mixed = false;
   va_end(ap);
   return code;
 }
@@ -81,6 +87,8 @@ static int parse(const DLTensor* t, const char* name, int ndim, View* v) {
     case kDLCUDA:
     case kDLCUDAManaged:
       v->host = false;
+      if (g_dev_seen >= 0 && g_dev_seen != t->device.device_id) g_dev_mixed = true;
+      g_dev_seen = t->device.device_id;
       break;
     case kDLCPU:
     case kDLCUDAHost:
@@ -113,6 +121,21 @@ static int parse_float(const DLTensor* t, const char* name, int ndim, int bits, 
     return fail(EHMC_ERR_INVALID, "%s: dtype must be float32 or float64", name);
   if (bits && v->bits != bits)
     return fail(EHMC_ERR_INVALID, "%s: dtype float%d does not match float%d of the call", name, v->bits, bits);
+  return EHMC_OK;
+}
+
+// Binds the calling thread to the context's device -- after checking that every device tensor parsed for this call
+// lives there: a kernel launched on the context's device with another device's pointers is an illegal address at
+// best and silent peer access at worst.
+static int enter_device(const ehmc_ctx* ctx) {
+  const int seen = g_dev_seen;
+  const bool mixed = g_dev_mixed;
+  g_dev_seen = -1;
+  g_dev_mixed = false;
+  if (mixed) return fail(EHMC_ERR_INVALID, "the device tensors of the call live on different CUDA devices");
+  if (seen >= 0 && seen != ctx->device)
+    return fail(EHMC_ERR_INVALID, "tensor on cuda:%d handed to a context bound to cuda:%d", seen, ctx->device);
+  CUDA_TRY(cudaSetDevice(ctx->device));
   return EHMC_OK;
 }
 
@@ -236,6 +259,9 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
   } else if (!strcmp(name, "nbody_ti")) {
     if (value != 0 && value != 4 && value != 8) return fail(EHMC_ERR_INVALID, "nbody_ti must be 0, 4 or 8");
     c->nbody_ti = (int)value;
+  } else if (!strcmp(name, "ens_sshift")) {
+    if (!(value >= -1 && value <= 4)) return fail(EHMC_ERR_INVALID, "ens_sshift must be in [-1, 4]");
+    c->ens_sshift = (int)value;
   } else if (!strcmp(name, "ens_debug")) {
     if (!(value >= 0 && value <= 65536)) return fail(EHMC_ERR_INVALID, "ens_debug must be in [0, 65536]");
     c->ens_debug = (int)value;
@@ -343,7 +369,7 @@ extern "C" int ehmc_potential_create(ehmc_ctx* ctx, int family, const DLTensor* 
   if (dtype_bits != 32 && dtype_bits != 64) return fail(EHMC_ERR_INVALID, "dtype_bits must be 32 or 64");
   if (nparams < 0 || nscalars < 0 || (nparams > 0 && !params) || (nscalars > 0 && !scalars))
     return fail(EHMC_ERR_INVALID, "ehmc_potential_create: bad params/scalars");
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   ehmc_potential* p = new (std::nothrow) ehmc_potential();
   if (!p) return fail(EHMC_ERR_NOMEM, "out of host memory");
   p->ctx = ctx;
@@ -876,7 +902,7 @@ static int integrate_entry(ehmc_ctx* ctx, const ehmc_potential* pot, int integ, 
   v.has_p = true;
   if (v.p.shape[0] != v.D || v.p.shape[1] != v.P) return fail(EHMC_ERR_INVALID, "%s: p must have q's shape", fn);
   TRY(check_same_place(v));
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (v.bits == 32) {
     IterArgs<float> A = base_args<float>(v, h, h2, L);
@@ -942,7 +968,7 @@ extern "C" int ehmc_hmc_iter(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor*
     if (v.stats.shape[0] != 2 * v.D + 3) return fail(EHMC_ERR_INVALID, "%s: stats_out must be float64[2D+3]", fn);
   }
   TRY(check_same_place(v));
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto fill = [&](auto& A) {
     A.flags = a->flags;
@@ -1040,7 +1066,7 @@ extern "C" int ehmc_hmc_run(ehmc_ctx* ctx, const ehmc_potential* pot, DLTensor* 
     if (va.host || va.bits != 32 || va.shape[0] != v.P) return fail(EHMC_ERR_INVALID, "%s: accepted_out must be device int32[P]", fn);
     accepted = reinterpret_cast<int*>(va.data);
   }
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (v.bits == 32)
     return hmc_run_typed<float>(ctx, pot, v, a, numIterations, samples_out ? &vs : nullptr, momenta_out ? &vm : nullptr,
@@ -1096,8 +1122,8 @@ extern "C" int ehmc_hmc_run_ensemble(ehmc_ctx* ctx, const ehmc_potential* pot, D
       return fail(EHMC_ERR_INVALID, "%s: trace must be a contiguous device [D*traceParticles, S] view with room for the iterations", fn);
     S = vt.shape[1];
   }
+  TRY(enter_device(ctx));
   if (numIterations == 0 || v.P == 0) return EHMC_OK;
-  CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // Robbins-Monro gains of this call's updates, k continuing from state[2] (read back: one small synchronous copy)
   double st_host[4];
@@ -1207,7 +1233,7 @@ extern "C" int ehmc_adapt_step(ehmc_ctx* ctx, const DLTensor* stats, double numP
     if (vm.host || vm.shape[0] != 2 * D) return fail(EHMC_ERR_INVALID, "%s: moments must be a device float64[2D]", fn);
     mom = reinterpret_cast<double*>(vm.data);
   }
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   k_adapt_step<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const double*>(vs.data), D, numParticlesTotal,
                                                                 targetAccept, gain0, kappa, maxMove, std::log(minStep),
                                                                 std::log(maxStep), adaptRows, static_cast<DynArgs*>(dynamic),
@@ -1275,7 +1301,7 @@ extern "C" int ehmc_potential_eval(ehmc_ctx* ctx, const ehmc_potential* pot, con
     if (vg.shape[0] != vq.shape[0] || vg.shape[1] != vq.shape[1] || vg.host != vq.host)
       return fail(EHMC_ERR_INVALID, "%s: grad_out must be [D,P] beside q", fn);
   }
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pot->bits == 32) return eval_any<float>(ctx, pot, vq, energy_out ? &ve : nullptr, grad_out ? &vg : nullptr, st);
   return eval_any<double>(ctx, pot, vq, energy_out ? &ve : nullptr, grad_out ? &vg : nullptr, st);
@@ -1332,7 +1358,7 @@ extern "C" int ehmc_philox_fill(ehmc_ctx* ctx, DLTensor* z, DLTensor* u, uint64_
     if (z && (vu.shape[0] != vz.shape[1] || vu.host != vz.host))
       return fail(EHMC_ERR_INVALID, "ehmc_philox_fill: u must be [P] beside z");
   }
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (bits == 32)
     return fill_any<float>(ctx, z ? &vz : nullptr, u ? &vu : nullptr, nullptr, 0, 1.0, 0, 0, seed, iteration, particleOffset, st);
@@ -1345,7 +1371,7 @@ extern "C" int ehmc_set_position(ehmc_ctx* ctx, DLTensor* q, double qStd, uint64
   if (!ctx) return fail(EHMC_ERR_INVALID, "ehmc_set_position: NULL context");
   View vq;
   TRY(parse_float(q, "q", 2, 0, &vq));
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint64_t it = ~0ULL;
   if (vq.bits == 32) return fill_any<float>(ctx, &vq, nullptr, nullptr, 0, qStd, 0, 0, seed, it, particleOffset, st);
@@ -1360,7 +1386,7 @@ extern "C" int ehmc_set_momentum(ehmc_ctx* ctx, DLTensor* p, const DLTensor* mas
   TRY(parse_float(mass, "mass", 1, vp.bits, &vm));
   if (vm.shape[0] != vp.shape[1] || vm.host != vp.host)
     return fail(EHMC_ERR_INVALID, "ehmc_set_momentum: mass must be [P] beside p");
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (vp.bits == 32)
     return fill_any<float>(ctx, &vp, nullptr, &vm, 1, 1.0, boltzmann, temperature, seed, iteration, particleOffset, st);
@@ -1415,7 +1441,7 @@ extern "C" int ehmc_integrate_nbody_mode(ehmc_ctx* ctx, int integrator, DLTensor
   if (vp.shape[0] != vq.shape[0] || vp.shape[1] != vq.shape[1] || vm.shape[0] != vq.shape[1])
     return fail(EHMC_ERR_INVALID, "%s: shape mismatch", fn);
   if (vp.host != vq.host || vm.host != vq.host) return fail(EHMC_ERR_INVALID, "%s: tensors on different sides", fn);
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  TRY(enter_device(ctx));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (vq.bits == 32) return nbody_mode_any<float>(ctx, integrator, vq, vp, vm, gravConst, stepSize, stepSizeSq, numSteps, st);
   return nbody_mode_any<double>(ctx, integrator, vq, vp, vm, gravConst, stepSize, stepSizeSq, numSteps, st);

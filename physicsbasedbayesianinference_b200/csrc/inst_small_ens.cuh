@@ -25,14 +25,23 @@ static int ens_launch(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, EnsRunA
   const int NS = 2 * A.D + 3;
   // batches of 32 particles, tied into groups of 2^bshift consecutive batches (one float64 row each): about 2048
   // groups per iteration, at most ENS_MAX_GROUPS
-  const long long nbatch = (A.P + 31) / 32;
+  const long long nrows = (A.P + 31) / 32;  // sub-batches = rows of per-batch statistics
+  // queue items of 1 / 2 / 4 sub-batches.  Measured on B200 (profiles/r02_fused_probe_sshift.txt, us per iteration of
+  // the funnel, items of 32 | 64 | 128 | 256 particles):   2^19, L = 20: 32 | 44 | 60 | 70     2^19, L = 4: 22 | 25 | 38 | 44
+  //   2^20, L = 20: 56 | 69 | 86 | 116    2^20, L = 4: 39 | 35 | 48 | 71    2^22, L = 20: 222 | 207 | 233 | 277
+  //   2^22, L = 4: 160 | 135 | 127 | 139.  Small shards need the fine grain (a warp has 3.5 items per iteration at 2^19),
+  // large ones gain from paying the queue round per 64 (long trajectories) or 128 (short ones) particles.
+  int sshift = c->ens_sshift >= 0 ? c->ens_sshift : (nrows >= (1 << 16) ? (A.L <= 8 ? 2 : 1) : 0);
+  const long long nbatch = (nrows + (1LL << sshift) - 1) >> sshift;
   int bshift = 0;
   while ((nbatch >> bshift) > 2048) ++bshift;
   R.bshift = bshift;
+  R.sshift = sshift;
+  R.nrows = (unsigned)nrows;
   R.nbatch = (unsigned)nbatch;
   R.nvirt = (unsigned)((nbatch + (1LL << bshift) - 1) >> bshift);
   static_assert(ENS_MAX_GROUPS >= 4096, "group count");
-  if (nbatch > 0x3FFFFFFFLL || ((long long)R.nIter << bshift) > 0x7FFFFFFFLL)
+  if (nrows > 0x3FFFFFFFLL || ((long long)R.nIter << bshift) > 0x7FFFFFFFLL)
     return fail(EHMC_ERR_UNSUPPORTED, "fused ensemble run: too many particles or iterations for one launch");
   const unsigned V = R.nvirt, ngroups = (V + ENS_GROUP - 1) / ENS_GROUP;
   // control block (every section on a 128-byte line): hsched [nIter + 1 + lag] | published replicas | ticket [ENS_RING]
@@ -47,7 +56,7 @@ static int ens_launch(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, EnsRunA
   const size_t n_rows = up((size_t)ENS_RING * V * NS);
   const size_t n_grows = up((size_t)ENS_RING * ngroups * NS);
   const size_t n_gains = up((size_t)std::max(1, R.adaptIters));
-  const size_t n_brows = up(((size_t)nbatch * (2 * DT + 3) * sizeof(T) + 7) / 8);
+  const size_t n_brows = up(((size_t)nrows * (2 * DT + 3) * sizeof(T) + 7) / 8);
   const size_t bytes = sizeof(double) * (n_h + n_pub + n_tk + n_gt + n_done + n_rows + n_grows + n_gains + n_brows) + 128;
   TRY(c->ens_ctl.ensure(bytes));
   double* base = reinterpret_cast<double*>(((uintptr_t)c->ens_ctl.ptr + 127) & ~(uintptr_t)127);

@@ -401,7 +401,7 @@ k_dense(const IterArgs<T> A, const DenseArgs<T> pa, const int integ, const int h
 #pragma unroll
     for (int t = 0; t < TM; ++t) {
       T u = T(0);
-      if (valid[t]) u = A.u != nullptr ? A.u[pbase + t] : NormalBlock<T>::uniform(K, A.offset + (u64)(pbase + t));
+      if (valid[t]) u = A.u != nullptr ? A.u[pbase + t] : NormalBlock<T>::uniform(K, A.offset + (u64)(pbase + t), A.D);
       rej[t] = metropolis_reject<T>(oldH[t], newH[t], u, A.flags, &accp[t]);
     }
   }

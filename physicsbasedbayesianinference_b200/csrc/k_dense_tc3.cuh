@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) k_dense_tc3(const IterArgs<flo
       newH = 0.5f * K1 * inv_m + U1;
       float u = 0.f;
       if (valid)
-        u = A.u != nullptr ? A.u[pc] : NormalBlock<float>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)pc);
+        u = A.u != nullptr ? A.u[pc] : NormalBlock<float>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)pc, A.D);
       rej = metropolis_reject<float>(oldH, newH, u, A.flags, &accp);
       // A row whose position ran more than 256x past its prologue scale saturates its fp16 operands (finite, but no
       // longer the trajectory).  The exact kernels carry such a divergent trajectory to |q| ~ 1e38 and reject it

@@ -262,7 +262,7 @@ __global__ void k_uf_final(const IterArgs<T> A, const T* w, const T* v, const T*
   if (A.u != nullptr)
     u = A.u[i];
   else
-    u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)i);
+    u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)i, A.D);
   T accp;
   const bool rej = metropolis_reject<T>((T)(oldH - newH), T(0), u, A.flags, &accp);
   const T pstd = momentum_std<T>(m, A.kB, A.temp, A.pscale);

@@ -130,7 +130,8 @@ __global__ void k_philox_fill(T* out, long long ld, long long P, int D, T* u, co
         if (b * NB + t < D) out[(long long)(b * NB + t) * ld + i] = Ar<T>::mul(zz[t], s);
     }
   }
-  if (u != nullptr) u[i] = NormalBlock<T>::uniform(K, offset + (u64)i);
+  // (u without z: D = 0, the dedicated uniform block)
+  if (u != nullptr) u[i] = NormalBlock<T>::uniform(K, offset + (u64)i, out != nullptr ? D : 0);
 }
 
 // Register-only FFMA chain: 8 independent accumulators x ITER FMAs per thread.

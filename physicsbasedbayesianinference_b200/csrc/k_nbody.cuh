@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(NTMAX) k_nbody(const IterArgs<T> A, const NBod
     if (A.u != nullptr)
       u = A.u[part];
     else
-      u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)part);
+      u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)part, A.D);
     rej = metropolis_reject<T>(oldH, newH, u, A.flags, &accp);  // identical in every thread
   }
 

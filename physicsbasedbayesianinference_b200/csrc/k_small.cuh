@@ -103,10 +103,16 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL), optionally
     return T(0.5) * v * v * inv_s2 + hs + half_dm1 * v;
   }
   static constexpr bool kPacked = true;
+  // float32 packed forms: e^{lnb - a v} is ONE FFMA + MUFU.EX2 (ex2.approx.ftz, relative error 2^-22, on the argument
+  // scaled by log2 e) instead of expf's 9 instructions (range reduction by FFMA.SAT / FFMA.RM, two-term log2 e, scale
+  // by shift): the trajectory loop is issue / FMA-pipe bound and this was a quarter of a leapfrog step.
+  __device__ __forceinline__ float expo(float v) const {
+    return ex2_ftz(fmaf(-(float)a * 1.4426950408889634f, v, (float)lnb * 1.4426950408889634f));
+  }
   // pair 0 = (v, q_1); padded dims hold q = 0 and contribute nothing
   __device__ __forceinline__ float grad2(const f32x2 (&Q)[(DT + 1) / 2], f32x2 (&G)[(DT + 1) / 2], bool) const {
     const float v = pk_lo(Q[0]), q1 = pk_hi(Q[0]);
-    const float ev = expf((float)lnb - (float)a * v);
+    const float ev = expo(v);
     const f32x2 ev2 = pk2(ev, ev);
     f32x2 S = 0ull;
 #pragma unroll
@@ -121,12 +127,14 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL), optionally
     return 0.5f * v * v * (float)inv_s2 + hs + (float)half_dm1 * v;
   }
   // Gradient and kick in one: V += c * grad U(Q).  For the pairs above the first, grad = e^{-v} q, so the kick is
-  // ONE FFMA2 with the scalar c e^{-v} instead of FMUL2 (gradient) + FFMA2 (kick): the trajectory loop is bound by
-  // the FMA pipe (ncu: math_pipe_throttle is its top stall) and this is 4 of its 18 packed instructions at D = 10.
+  // ONE FFMA2 with the scalar c e^{-v} instead of FMUL2 (gradient) + FFMA2 (kick); the first pair's
+  // c (v / s^2 - a e^{-v} s2 / 2 + (D-1) a / 2) and c e^{-v} q_1 are formed with c folded into the coefficients
+  // (c / s^2, c (D-1) a / 2: loop invariants), 6 scalar instructions.  Returns U(Q) when wantE.
   static constexpr bool kFusedKick = true;
-  __device__ __forceinline__ float kick2(const f32x2 (&Q)[(DT + 1) / 2], f32x2 (&V)[(DT + 1) / 2], float c) const {
+  __device__ __forceinline__ float kick2(const f32x2 (&Q)[(DT + 1) / 2], f32x2 (&V)[(DT + 1) / 2], float c,
+                                         bool wantE) const {
     const float v = pk_lo(Q[0]), q1 = pk_hi(Q[0]);
-    const float ev = expf((float)lnb - (float)a * v);
+    const float ev = expo(v);
     const float cev = c * ev;
     const f32x2 cev2 = pk2(cev, cev);
     f32x2 S = 0ull;
@@ -136,10 +144,10 @@ struct FunnelPot {  // Neal's funnel (see ehmc.h EHMC_FAMILY_FUNNEL), optionally
       V[i] = fma2(Q[i], cev2, V[i]);
     }
     const float s2 = fmaf(q1, q1, pk_lo(S) + pk_hi(S));
-    const float hs = 0.5f * ev * s2;
-    const float ahs = (float)a * hs;
-    V[0] = fma2(pk2(v * (float)inv_s2 - ahs + (float)half_dm1, ev * q1), pk2(c, c), V[0]);
-    return 0.5f * v * v * (float)inv_s2 + hs + (float)half_dm1 * v;
+    const float w = (0.5f * (float)a) * cev;                             // c a e^{-v} / 2
+    const float t = fmaf(c * (float)inv_s2, v, c * (float)half_dm1);     // c (v / s^2 + (D-1) a / 2)
+    V[0] = pk2(pk_lo(V[0]) + fmaf(-w, s2, t), fmaf(cev, q1, pk_hi(V[0])));
+    return wantE ? fmaf(0.5f * ev, s2, fmaf(0.5f * v * (float)inv_s2, v, (float)half_dm1 * v)) : 0.f;
   }
 };
 
@@ -163,8 +171,11 @@ struct CoinPot {  // EHMC_FAMILY_COIN_TOSS: U = -sum k ln q + (n - k) ln(1 - q)
 // ---------------------------------------------------------------------------
 // momentum draw: p = z * pstd, z fed or from Philox
 // ---------------------------------------------------------------------------
+// uword (optional, float32 Philox draws only): receives word z of normal block Dn / 4 -- the Metropolis uniform's
+// word when NormalBlock<float>::uniform_in_normal_block(Dn) (stream version 2, common.cuh)
 template <typename T, int DT>
-__device__ __forceinline__ void draw_momentum(const IterArgs<T>& A, int Dn, long long i, T pstd, T (&p)[DT]) {
+__device__ __forceinline__ void draw_momentum(const IterArgs<T>& A, int Dn, long long i, T pstd, T (&p)[DT],
+                                              uint32_t* uword = nullptr) {
   if (A.z != nullptr) {
 #pragma unroll
     for (int d = 0; d < DT; ++d) p[d] = d < Dn ? Ar<T>::mul(A.z[d * A.z_ld + i], pstd) : T(0);
@@ -174,7 +185,13 @@ __device__ __forceinline__ void draw_momentum(const IterArgs<T>& A, int Dn, long
 #pragma unroll
     for (int b = 0; b < (DT + NB - 1) / NB; ++b) {
       T zz[NB];
-      NormalBlock<T>::draw(K, A.offset + (u64)i, (uint32_t)b, zz);
+      if constexpr (sizeof(T) == 4) {
+        const uint4 r = K.block(A.offset + (u64)i, (uint32_t)b);
+        NormalBlock<float>::transform(r, zz);
+        if (uword != nullptr && b == (Dn >> 2)) *uword = r.z;
+      } else {
+        NormalBlock<T>::draw(K, A.offset + (u64)i, (uint32_t)b, zz);
+      }
 #pragma unroll
       for (int t = 0; t < NB; ++t) {
         const int d = b * NB + t;
@@ -184,55 +201,124 @@ __device__ __forceinline__ void draw_momentum(const IterArgs<T>& A, int Dn, long
   }
 }
 
+// Metropolis uniform of particle i: fed, or the word kept from the momentum draw, or its own Philox block
+template <typename T>
+__device__ __forceinline__ T metropolis_uniform(const IterArgs<T>& A, int Dn, long long i, uint32_t uword) {
+  if (A.u != nullptr) return A.u[i];
+  if (A.z == nullptr && NormalBlock<T>::uniform_in_normal_block(Dn)) return NormalBlock<T>::uniform_from_word(uword);
+  return NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)i, Dn);
+}
+
 // ---------------------------------------------------------------------------
 // The integrators on register state.  On entry p holds the momentum; on exit q, p
 // hold the integrated state.  Returns U(q_final) when wantE.  U0 (energy at the
 // start) is returned through *U0 when wantE.
 // ---------------------------------------------------------------------------
+// float32 leapfrog on PACKED state (pairs of dimensions: FFMA2 / FMUL2 do two lanes of work per issue slot and this
+// loop is issue bound): kick-drift-kick, Q positions, V velocities, hm = h / m.  The last step is peeled so that the
+// loop body carries no select of the kick coefficient and no energy.
+template <int DT, class Pot>
+__device__ __forceinline__ float integrate_packed(const Pot& pot, f32x2 (&Q)[(DT + 1) / 2], f32x2 (&V)[(DT + 1) / 2],
+                                                  float hm, float h, int L, bool wantE, float* U0) {
+  constexpr int NP2 = (DT + 1) / 2;
+  const float hmh = 0.5f * hm;
+  const f32x2 h2p = pk2(h, h);
+  f32x2 G[NP2];
+  if (L <= 0) {  // L = 0: nothing moves
+    *U0 = pot.grad2(Q, G, wantE);
+    return *U0;
+  }
+  if constexpr (HasFusedKick<Pot>::value) {
+    *U0 = pot.kick2(Q, V, -hmh, wantE);
+    for (int j = 1; j < L; ++j) {
+#pragma unroll
+      for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
+      pot.kick2(Q, V, -hm, false);
+    }
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
+    return pot.kick2(Q, V, -hmh, wantE);
+  } else {
+    const f32x2 nhm = pk2(-hm, -hm), nhmh = pk2(-hmh, -hmh);
+    *U0 = pot.grad2(Q, G, wantE);
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], nhmh, V[i]);
+    for (int j = 1; j < L; ++j) {
+#pragma unroll
+      for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
+      pot.grad2(Q, G, false);
+#pragma unroll
+      for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], nhm, V[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
+    const float Uend = pot.grad2(Q, G, wantE);
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], nhmh, V[i]);
+    return Uend;
+  }
+}
+
+// One HMC trajectory of the float32 packed path from UNIT normals z (fed or drawn): velocities V = z pstd / m directly
+// (no momentum in between), kinetic energies from sum z^2 and sum V^2 with packed FFMA2.  On exit q holds the end
+// position, K0 / K1 / U0 / U1 the energies; the momentum p = V m is formed by the caller only when it is stored.
+// Shared by k_small (all its grids) and k_small_run, whose results must agree bit for bit.
+template <int DT, class Pot>
+struct PackedHmc {
+  static constexpr int NP2 = (DT + 1) / 2;
+  f32x2 Q[NP2], V[NP2];
+  float K0, K1, U0, U1;
+  __device__ __forceinline__ void start(const float (&q)[DT], const float (&z)[DT], float m, float inv_m, float pstd) {
+    const float sv = pstd * inv_m;
+    const f32x2 sv2 = pk2(sv, sv);
+    f32x2 S = 0ull;
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) {
+      Q[i] = pk2(q[2 * i], 2 * i + 1 < DT ? q[2 * i + 1] : 0.f);
+      const f32x2 Z = pk2(z[2 * i], 2 * i + 1 < DT ? z[2 * i + 1] : 0.f);
+      S = fma2(Z, Z, S);
+      V[i] = mul2(Z, sv2);
+    }
+    // 0.5 dot(p, p) / m with p = z pstd                       HMC.py:109
+    K0 = (0.5f * pstd) * sv * (pk_lo(S) + pk_hi(S));
+  }
+  __device__ __forceinline__ void run(const Pot& pot, float m, float inv_m, float h, int L) {
+    U1 = integrate_packed<DT, Pot>(pot, Q, V, h * inv_m, h, L, true, &U0);
+    f32x2 S = 0ull;
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) S = fma2(V[i], V[i], S);
+    K1 = (0.5f * m) * (pk_lo(S) + pk_hi(S));  // dot(-p,-p) == dot(p,p), HMC.py:164
+  }
+  __device__ __forceinline__ void position(float (&q)[DT]) const {
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) {
+      q[2 * i] = pk_lo(Q[i]);
+      if (2 * i + 1 < DT) q[2 * i + 1] = pk_hi(Q[i]);
+    }
+  }
+  __device__ __forceinline__ void momentum(float (&p)[DT], float m) const {
+#pragma unroll
+    for (int i = 0; i < NP2; ++i) {
+      p[2 * i] = pk_lo(V[i]) * m;
+      if (2 * i + 1 < DT) p[2 * i + 1] = pk_hi(V[i]) * m;
+    }
+  }
+};
+
 template <typename T, int DT, class Pot, int INTEG>
 __device__ __forceinline__ T integrate_regs(const Pot& pot, T (&q)[DT], T (&p)[DT], T m, T h, T h2, int L,
                                             bool wantE, T* U0) {
   typedef Ar<T> R;
   const T inv_m = R::rcp_(m);
   if constexpr (sizeof(T) == 4 && INTEG == INTEG_LEAPFROG && HasPacked<Pot>::value) {
-    // float32, packed: the kick-drift-kick recurrence below on pairs of dimensions -- FFMA2 / FMUL2 do two
-    // lanes of work per issue slot and this loop is issue bound (ncu: 78 % issue active, FMA pipe 53 %)
     constexpr int NP2 = (DT + 1) / 2;
-    f32x2 Q[NP2], V[NP2], G[NP2];
+    f32x2 Q[NP2], V[NP2];
 #pragma unroll
     for (int i = 0; i < NP2; ++i) {
       Q[i] = pk2(q[2 * i], 2 * i + 1 < DT ? q[2 * i + 1] : 0.f);
       V[i] = pk2(p[2 * i] * inv_m, 2 * i + 1 < DT ? p[2 * i + 1] * inv_m : 0.f);
     }
-    const float hm = h * inv_m, hmh = 0.5f * hm;
-    const f32x2 h2p = pk2(h, h), nhm = pk2(-hm, -hm), nhmh = pk2(-hmh, -hmh);
-    T Uend;
-    if constexpr (HasFusedKick<Pot>::value) {
-      // L = 0: c = 0 leaves V untouched (V + 0 * g; a non-finite gradient there is a non-finite U0 as well)
-      *U0 = L > 0 ? pot.kick2(Q, V, -hmh) : pot.grad2(Q, G, wantE);
-      Uend = *U0;
-      for (int j = 0; j < L; ++j) {
-#pragma unroll
-        for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
-        Uend = pot.kick2(Q, V, j == L - 1 ? -hmh : -hm);
-      }
-    } else {
-      *U0 = pot.grad2(Q, G, wantE);
-      Uend = *U0;
-      if (L > 0) {
-#pragma unroll
-        for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], nhmh, V[i]);
-      }
-      for (int j = 0; j < L; ++j) {
-#pragma unroll
-        for (int i = 0; i < NP2; ++i) Q[i] = fma2(V[i], h2p, Q[i]);
-        const bool last = j == L - 1;
-        Uend = pot.grad2(Q, G, wantE && last);
-        const f32x2 ck = last ? nhmh : nhm;
-#pragma unroll
-        for (int i = 0; i < NP2; ++i) V[i] = fma2(G[i], ck, V[i]);
-      }
-    }
+    const T Uend = integrate_packed<DT, Pot>(pot, Q, V, h * inv_m, h, L, wantE, U0);
 #pragma unroll
     for (int i = 0; i < NP2; ++i) {
       q[2 * i] = pk_lo(Q[i]);
@@ -391,14 +477,30 @@ struct WarpStats {
         for (int t = 0; t < PER16; ++t) ps[t] = pr[t] = T(0);
         // (not unrolled further: with all 32 values of the row in registers at once the trajectory kernel loses
         // resident CTAs)
+        if constexpr (PER16 == 4) {
+          // float32: the four partial sums as two packed pairs (FADD2 / FFMA2: the same sums for half the issue slots)
+          f32x2 s01 = 0ull, s23 = 0ull, r01 = 0ull, r23 = 0ull;
 #pragma unroll 2
-        for (int k = 0; k < 32; k += PER16) {
-          alignas(16) T x[PER16];
-          *reinterpret_cast<uint4*>(x) = *reinterpret_cast<const uint4*>(row + k);
+          for (int k = 0; k < 32; k += 4) {
+            const uint4 x = *reinterpret_cast<const uint4*>(row + k);
+            const f32x2 x01 = ((f32x2)x.y << 32) | x.x, x23 = ((f32x2)x.w << 32) | x.z;
+            s01 = add2(s01, x01);
+            s23 = add2(s23, x23);
+            r01 = fma2(x01, x01, r01);
+            r23 = fma2(x23, x23, r23);
+          }
+          ps[0] = pk_lo(s01), ps[1] = pk_hi(s01), ps[2] = pk_lo(s23), ps[3] = pk_hi(s23);
+          pr[0] = pk_lo(r01), pr[1] = pk_hi(r01), pr[2] = pk_lo(r23), pr[3] = pk_hi(r23);
+        } else {
+#pragma unroll 2
+          for (int k = 0; k < 32; k += PER16) {
+            alignas(16) T x[PER16];
+            *reinterpret_cast<uint4*>(x) = *reinterpret_cast<const uint4*>(row + k);
 #pragma unroll
-          for (int t = 0; t < PER16; ++t) {
-            ps[t] += x[t];
-            pr[t] = x[t] * x[t] + pr[t];
+            for (int t = 0; t < PER16; ++t) {
+              ps[t] += x[t];
+              pr[t] = x[t] * x[t] + pr[t];
+            }
           }
         }
         if constexpr (PER16 == 4) {
@@ -481,8 +583,9 @@ struct WarpStats {
 // instead of behind them (profiles/r01_k1_dbg_probe.txt, r01_ncu_full_k1l4_before.txt).
 struct NoStepHook {};  // k_small_body: the step size is A.h
 
-// WARP: the calling WARP runs particles 0 .. A.P - 1 (A.P <= 32: one batch) on its own -- no block-wide barrier
-// anywhere, A.partials is the batch's row of statistics in the state's precision (WarpStats::batch_row); otherwise the
+// WARP: the calling WARP runs particles 0 .. A.P - 1 (one batch of the fused ensemble run, 32 at a time) on its own --
+// no block-wide barrier anywhere, A.partials holds one row of statistics per 32 particles in the state's precision
+// (WarpStats::batch_row); otherwise the
 // CTA is number blk of nblk CTAs walking the particles, 128 at a time, and A.partials holds one float64 row per CTA.
 template <typename T, int DT, class Pot, int INTEG, bool HMC, bool EXACT, class StepHook = NoStepHook, bool WARP = false>
 __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& pot, double* k1_smem, unsigned blk,
@@ -509,50 +612,61 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
 #pragma unroll
     for (int d = 0; d < DT; ++d) q[d] = EXACT ? A.q[d * A.q_ld + ic] : ld_if(A.q + (d * A.q_ld + ic), d < Dn);
 
+    // float32 leapfrog with a packed potential: the trajectory runs on pairs of dimensions straight from the unit
+    // normals (PackedHmc); every other combination goes through integrate_regs on (q, p)
+    constexpr bool FAST = HMC && sizeof(T) == 4 && INTEG == INTEG_LEAPFROG && HasPacked<Pot>::value;
     T pstd = T(0);
+    uint32_t uword = 0u;
     if (HMC) {
       // the unit normals first: ~300 instructions that depend on nothing in flight; the mass is first touched
       // after them (z * 1 is exact, so p = z * pstd below is the product the one-step form gave)
-      draw_momentum<T, DT>(A, Dn, ic, T(1), p);
+      draw_momentum<T, DT>(A, Dn, ic, T(1), p, &uword);
       pstd = momentum_std<T>(m, A.kB, A.temp, A.pscale);
+      if constexpr (!FAST) {
 #pragma unroll
-      for (int d = 0; d < DT; ++d) p[d] = Ar<T>::mul(p[d], pstd);
+        for (int d = 0; d < DT; ++d) p[d] = Ar<T>::mul(p[d], pstd);
+      }
     } else {
 #pragma unroll
       for (int d = 0; d < DT; ++d) p[d] = EXACT ? A.p[d * A.p_ld + ic] : ld_if(A.p + (d * A.p_ld + ic), d < Dn);
     }
 
-    T K0 = T(0);
     const T inv_m = Ar<T>::rcp_(m);
-    if (HMC) K0 = kinetic<T, DT>(p, m, inv_m);
-    T U0;
     if constexpr (!std::is_same<StepHook, NoStepHook>::value) {
       if (!h_known) {
         hook(h, h2);
         h_known = true;
       }
     }
-    const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, h, h2, A.L, HMC, &U0);
+    T oldH, newH;
+    [[maybe_unused]] PackedHmc<DT, Pot> traj;
+    if constexpr (FAST) {
+      traj.start(q, p, m, inv_m, pstd);
+      traj.run(pot, m, inv_m, h, A.L);
+      traj.position(q);
+      oldH = traj.K0 + traj.U0;
+      newH = traj.K1 + traj.U1;
+    } else {
+      T K0 = T(0);
+      if (HMC) K0 = kinetic<T, DT>(p, m, inv_m);
+      T U0;
+      const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, h, h2, A.L, HMC, &U0);
 
-    if (!HMC) {
-      if (active) {
+      if (!HMC) {
+        if (active) {
 #pragma unroll
-        for (int d = 0; d < DT; ++d)
-          if (d < Dn) {
-            A.q[d * A.q_ld + i] = q[d];
-            A.p[d * A.p_ld + i] = p[d];
-          }
+          for (int d = 0; d < DT; ++d)
+            if (d < Dn) {
+              A.q[d * A.q_ld + i] = q[d];
+              A.p[d * A.p_ld + i] = p[d];
+            }
+        }
+        continue;
       }
-      continue;
+      oldH = Ar<T>::add(K0, U0);
+      newH = Ar<T>::add(kinetic<T, DT>(p, m, inv_m), U1);  // dot(-p,-p) == dot(p,p), HMC.py:164
     }
-
-    const T oldH = Ar<T>::add(K0, U0);
-    const T newH = Ar<T>::add(kinetic<T, DT>(p, m, inv_m), U1);  // dot(-p,-p) == dot(p,p), HMC.py:164
-    T u;
-    if (A.u != nullptr)
-      u = A.u[ic];
-    else
-      u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)ic);
+    const T u = metropolis_uniform<T>(A, Dn, ic, uword);
     T accp;
     const bool rej = metropolis_reject<T>(oldH, newH, u, A.flags, &accp);
 
@@ -563,6 +677,7 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
           if (d < Dn) A.q[d * A.q_ld + i] = q[d];  // HMC.py:175 (rejected: q in HBM is still oldQ)
       }
       if (A.p != nullptr) {
+        if constexpr (FAST) traj.momentum(p, m);
         if (rej) {
           if (A.flags & FLAG_BUGCOMPAT) {
 #pragma unroll
@@ -584,9 +699,9 @@ __device__ __forceinline__ void k_small_body(const IterArgs<T>& A, const Pot& po
 #pragma unroll
         for (int d = 0; d < DT; ++d) q[d] = d < Dn ? A.q[d * A.q_ld + i] : T(0);
       }
-      if constexpr (WARP)
-        WarpStats<T, DT>::batch_row(stats_smem, reinterpret_cast<T*>(A.partials), active, rej ? T(0) : T(1), accp,
-                                    rej ? oldH : newH, q);
+      if constexpr (WARP)  // one row per 32 particles (sub-batch), consecutive
+        WarpStats<T, DT>::batch_row(stats_smem, reinterpret_cast<T*>(A.partials) + (base >> 5) * (2 * DT + 3), active,
+                                    rej ? T(0) : T(1), accp, rej ? oldH : newH, q);
       else
         ws.add(stats_smem, active, rej ? T(0) : T(1), accp, rej ? oldH : newH, q);
     }
@@ -624,20 +739,33 @@ __global__ void __launch_bounds__(K1_THREADS) k_small_run(const IterArgs<T> Ain,
 #pragma unroll
     for (int d = 0; d < DT; ++d) q[d] = d < A.D ? A.q[d * A.q_ld + i] : T(0);
     int nacc = 0;
+    constexpr bool FAST = sizeof(T) == 4 && INTEG == INTEG_LEAPFROG && HasPacked<Pot>::value;  // as in k_small_body
     for (int it = 0; it < R.nIter; ++it) {
       A.iter = Ain.iter + (u64)it;
-      draw_momentum<T, DT>(A, A.D, i, pstd, p);
+      uint32_t uword = 0u;
+      draw_momentum<T, DT>(A, A.D, i, FAST ? T(1) : pstd, p, &uword);
 #pragma unroll
       for (int d = 0; d < DT; ++d) {
         qold[d] = q[d];
-        p0[d] = p[d];
+        p0[d] = FAST ? p[d] * pstd : p[d];
       }
-      const T K0 = kinetic<T, DT>(p, m, inv_m);
-      T U0;
-      const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, A.h, A.h2, A.L, true, &U0);
-      const T oldH = Ar<T>::add(K0, U0);
-      const T newH = Ar<T>::add(kinetic<T, DT>(p, m, inv_m), U1);
-      const T u = NormalBlock<T>::uniform(PhiloxKey(A.seed, A.iter), A.offset + (u64)i);
+      T oldH, newH;
+      if constexpr (FAST) {
+        PackedHmc<DT, Pot> traj;
+        traj.start(q, p, m, inv_m, pstd);
+        traj.run(pot, m, inv_m, A.h, A.L);
+        traj.position(q);
+        traj.momentum(p, m);
+        oldH = traj.K0 + traj.U0;
+        newH = traj.K1 + traj.U1;
+      } else {
+        const T K0 = kinetic<T, DT>(p, m, inv_m);
+        T U0;
+        const T U1 = integrate_regs<T, DT, Pot, INTEG>(pot, q, p, m, A.h, A.h2, A.L, true, &U0);
+        oldH = Ar<T>::add(K0, U0);
+        newH = Ar<T>::add(kinetic<T, DT>(p, m, inv_m), U1);
+      }
+      const T u = metropolis_uniform<T>(A, A.D, i, uword);
       T accp;
       const bool rej = metropolis_reject<T>(oldH, newH, u, A.flags, &accp);
       nacc += rej ? 0 : 1;

@@ -9,7 +9,8 @@
 // particles) against 33 us of kernel (profiles/r01_adapt_probe.txt).
 //
 // Structure (grid = one resident wave, cooperative launch so that every CTA is co-resident):
-//   * the unit of work is a BATCH of 32 consecutive particles run by one warp.  The warps of the compute CTAs take
+//   * the unit of work is a BATCH of 32 consecutive particles run by one warp (of 64 / 128 particles, as two / four
+//     sub-batches in a row, when the shard has >= 2^21 particles: EnsRunArgs::sshift).  The warps of the compute CTAs take
 //     (iteration, batch) pairs in order from one global cursor; when an iteration's batches are all taken the cursor
 //     simply runs on into the next iteration.  A warp runs k_small_body on its batch (q round-trips through HBM / L2)
 //     and writes the batch's row of 2D+3 sums in the state's precision.  Batches are tied into GROUPS of 2^k
@@ -68,8 +69,13 @@ struct EnsRunArgs {
   unsigned* arrived;   // [nvirt] batches of every group that have finished, ever
   void* brows;         // [nbatch][2 DT + 3] per-batch sums in the state's precision (padded layout)
   unsigned nvirt;      // groups per iteration
-  unsigned nbatch;     // batches (32 particles) per iteration
+  unsigned nbatch;     // batches (32 << sshift particles: the queue's unit of work) per iteration
   int bshift;          // log2(batches per group)
+  int sshift;          // log2(sub-batches of 32 particles per batch): 0 for small shards (the 8-GPU shard of config 5
+                       // has 3.5 batches per warp and iteration and needs the fine grain), 1 (L > 8) or 2 when an
+                       // iteration has >= 2^16 sub-batches, so that the queue round (cursor, group mark, step size,
+                       // arrival atomic: ~170 instructions and four L2 round trips) is paid once per 64 / 128 particles
+  unsigned nrows;      // sub-batches (rows of brows) per iteration = ceil(P / 32)
   unsigned* ticket;    // [ENS_RING][32] (entry 0 of each 128-byte line) groups of iteration it % ENS_RING that are reduced
   unsigned* gticket;   // [ENS_RING][ngroups] group rows of the reduction group that are written
   double* rows;        // [ENS_RING][nvirt][2D+3] per-group partial sums
@@ -229,26 +235,28 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_small_ens(const IterArgs<T> A
         // in registers across the trajectory body cost the kernel its eighth resident CTA per SM)
         const int it = s_it[w];
         const unsigned b = s_b[w];
-        const long long lo = (long long)b * 32;
+        const long long lo = ((long long)b * 32) << R.sshift;
         IterArgs<T> A = Ain;
         A.h = (T)s_hcur[w];
         A.h2 = A.h * A.h;
-        A.P = min(32LL, Ain.P - lo);
+        A.P = min(32LL << R.sshift, Ain.P - lo);
         A.q = Ain.q + lo;
         A.mass = Ain.mass + lo;
         A.offset = Ain.offset + (u64)lo;
         if (Ain.accept != nullptr) A.accept = Ain.accept + lo;
         A.iter = Ain.iter + (u64)it;
-        A.partials = reinterpret_cast<double*>(static_cast<T*>(R.brows) + (size_t)b * NAP);
+        A.partials = reinterpret_cast<double*>(static_cast<T*>(R.brows) + ((size_t)b << R.sshift) * NAP);
         k_small_body<T, DT, Pot, INTEG, true, EXACT, NoStepHook, true>(A, pot, k1_smem, 0u, 1u);
       }
       const int it = *(volatile int*)&s_it[w];
       const unsigned b = *(volatile unsigned*)&s_b[w];
       if (R.trace != nullptr) {
         // kept positions of the first ntrace local particles (each thread re-reads what it wrote itself)
-        const long long i = (long long)b * 32 + lane;
-        if (i < min(R.ntrace, Ain.P))
-          for (int d = 0; d < Dn; ++d) R.trace[((long long)d * R.ntrace + i) * R.S + R.s0 + it] = Ain.q[d * Ain.q_ld + i];
+        for (int sb = 0; sb < (1 << R.sshift); ++sb) {
+          const long long i = ((((long long)b << R.sshift) + sb) * 32) + lane;
+          if (i < min(R.ntrace, Ain.P))
+            for (int d = 0; d < Dn; ++d) R.trace[((long long)d * R.ntrace + i) * R.S + R.s0 + it] = Ain.q[d * Ain.q_ld + i];
+        }
       }
       __syncwarp();  // positions and the batch row are written (memory ordering among the warp's lanes)
       const unsigned grp = b >> R.bshift;
@@ -266,12 +274,14 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_small_ens(const IterArgs<T> A
       if (last) {
         // the group's row: its batch rows in batch order, float64; padded dimensions are dropped
         const int ring = it % ENS_RING;
-        const T* br = static_cast<const T*>(R.brows) + (size_t)b0 * NAP;
+        const unsigned r0 = b0 << R.sshift;                           // first sub-batch row of the group
+        const unsigned nr = min(cnt << R.sshift, R.nrows - r0);       // (the last batch may be short of sub-batches)
+        const T* br = static_cast<const T*>(R.brows) + (size_t)r0 * NAP;
         double* out = R.rows + ((size_t)ring * V + grp) * NS;
         for (int j = lane; j < NAP; j += 32) {
           double sum = 0.0;
 #pragma unroll 8
-          for (unsigned r = 0; r < cnt; ++r) sum += (double)__ldcg(&br[(size_t)r * NAP + j]);
+          for (unsigned r = 0; r < nr; ++r) sum += (double)__ldcg(&br[(size_t)r * NAP + j]);
           int o = j;
           if (j >= 3 + DT) {
             const int d = j - 3 - DT;

@@ -1,7 +1,9 @@
 """Effective sample size of ensemble chains (build-defined: the reference has no ESS).
 
-Estimator: for one coordinate, the autocovariance is computed by FFT per chain and AVERAGED
-over the traced chains (they are exchangeable: same target, independent particles), then
+Estimator: for one coordinate, the chains are centred on the GRAND mean over chains and draws (they
+are exchangeable: same target, independent particles -- centring every chain on its own mean would
+hide exactly the slow component a poorly mixing chain has not traversed yet), the autocovariance is
+computed by FFT per chain and AVERAGED over the traced chains, then
 Geyer's initial-positive-sequence truncation gives the integrated autocorrelation time tau;
 ESS = (number of draws) x (number of chains) / tau.  Runs on the tensors' device (torch.fft)."""
 from __future__ import annotations
@@ -15,7 +17,7 @@ def ess(trace):
 
     x = trace.to(torch.float64)
     S, C = x.shape
-    xc = x - x.mean(dim=0, keepdim=True)
+    xc = x - x.mean()
     n = 1 << (2 * S - 1).bit_length()
     f = torch.fft.rfft(xc, n=n, dim=0)
     acov = torch.fft.irfft(f * f.conj(), n=n, dim=0)[:S] / S

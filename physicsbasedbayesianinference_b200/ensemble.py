@@ -34,6 +34,7 @@ class Ensemble:
         self.seed = int(seed)
         self.particleOffset = int(particleOffset)  # global index of particle 0 (multi-GPU shards)
         self._drawCount = 0
+        self._posCount = 0
         if device is None:
             self.device = None
             dt = np.dtype(np.float64 if dtype is None else dtype)
@@ -84,7 +85,11 @@ class Ensemble:
         import torch
 
         self.q = torch.empty((self.numDimensions, self.numParticles), dtype=self.dtype, device=self.device)
-        _lib.set_position(self._ctx(), self.q, qStd, self.seed, self.particleOffset,
+        # fresh positions on every call, like the reference's norm.rvs: call k > 0 draws from the Philox key
+        # seed XOR k * 0x9E3779B97F4A7C15 (call 0: the seed itself, the stream documented in ehmc.h)
+        seed = (self.seed ^ ((self._posCount * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+        self._posCount += 1
+        _lib.set_position(self._ctx(), self.q, qStd, seed, self.particleOffset,
                           _lib.current_stream_ptr(self.q))
         return self.q
 

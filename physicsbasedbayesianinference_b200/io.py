@@ -3,8 +3,11 @@
 * N-body input files of the reference's sample lab (samples/NBody/pl2.txt, pl3.txt, pl100.txt,
   pl1k.txt; reader samples/NBody/MiscFunctions.py:8-43): header "N tmax dt", then N masses, N
   positions, N velocities.
-* A resumable checkpoint of an HMC run: positions, masses, Philox (seed, iteration), step size.
-  Because the RNG is counter based, resuming reproduces the uninterrupted run bit for bit.
+* A resumable checkpoint of an HMC run: positions, masses, Philox (seed, iteration), step size,
+  trajectory length (simulTime, numSteps), flags and mass scales.  Because the RNG is counter based, a
+  driver restored between two run() / step() / getSamples() calls continues exactly like the one that
+  was never interrupted (bit for bit, adaptive runs included: the Robbins-Monro gain restarts with every
+  run() call, interrupted or not, so there is no adapter state to carry).
 """
 from __future__ import annotations
 
@@ -43,8 +46,11 @@ def saveCheckpoint(path, hmc):
     to_np = (lambda a: a) if not ens.onDevice else (lambda a: a.detach().cpu().numpy())
     np.savez_compressed(path, q=to_np(hmc.integrator.q), mass=to_np(ens.mass), seed=np.uint64(hmc.seed),
                         iteration=np.uint64(hmc.iteration), stepSize=np.float64(hmc.stepSize),
-                        simulTime=np.float64(hmc.simulTime), particleOffset=np.int64(ens.particleOffset),
-                        method=np.array(hmc.method))
+                        simulTime=np.float64(hmc.simulTime), numSteps=np.int64(hmc.integrator.numSteps),
+                        particleOffset=np.int64(ens.particleOffset), method=np.array(hmc.method),
+                        bugCompat=np.int8(hmc.bugCompat),
+                        rejectNonFinite=np.int8(-1 if hmc.rejectNonFinite is None else int(hmc.rejectNonFinite)),
+                        massScale=np.zeros(0) if getattr(hmc, "massScale", None) is None else np.asarray(hmc.massScale))
 
 
 def loadCheckpoint(path, hmc):
@@ -68,5 +74,17 @@ def loadCheckpoint(path, hmc):
         hmc.iteration = int(f["iteration"])
         hmc.stepSize = float(f["stepSize"])
         hmc.integrator.stepSize = hmc.stepSize
-        hmc.integrator.numSteps = int(hmc.simulTime / hmc.stepSize)
+        if "numSteps" in f:
+            # the trajectory length the saved driver had (run(keepNumSteps=True) lets simulTime = numSteps * stepSize
+            # drift away from the constructor's value)
+            hmc.simulTime = float(f["simulTime"])
+            hmc.integrator.finalTime = hmc.simulTime
+            hmc.integrator.numSteps = int(f["numSteps"])
+            hmc.bugCompat = bool(f["bugCompat"])
+            rnf = int(f["rejectNonFinite"])
+            hmc.rejectNonFinite = None if rnf < 0 else bool(rnf)
+            ms = f["massScale"]
+            hmc.massScale = None if ms.size == 0 else np.array(ms, dtype=np.float64)
+        else:  # checkpoints written before these fields existed
+            hmc.integrator.numSteps = int(hmc.simulTime / hmc.stepSize)
     return hmc

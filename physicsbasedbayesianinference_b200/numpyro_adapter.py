@@ -41,10 +41,42 @@ def potentialFromSpec(spec):
         f"model family {fam!r} has no fused CUDA kernel; supported: normal_iid, mvn, funnel, coin_toss, logistic_regression")
 
 
+def logisticSpecFromLinearLogits(logits_of, numDimensions, y, priorScale, rtol=1e-6):
+    """Recognises ``obs ~ Bernoulli(logits = X @ theta)`` from the logits alone and returns the
+    ``logistic_regression`` spec (the design matrix is not visible in a model trace, only the logits are).
+
+    logits_of(theta) -> logits (N,) of the observed site with the latent vector fixed to theta.  X is recovered by
+    probing the unit vectors, column k = logits_of(e_k) - logits_of(0); the model is accepted only if it has no
+    intercept (logits_of(0) == 0: the family has none) and is linear (checked on a random theta).  Raises
+    NotImplementedError otherwise."""
+    D = int(numDimensions)
+    base = np.asarray(logits_of(np.zeros(D)), dtype=np.float64).reshape(-1)
+    if not np.allclose(base, 0.0, atol=1e-12):
+        raise NotImplementedError("Bernoulli-logit model with an intercept / offset: the logistic family is X @ theta only")
+    X = np.empty((base.shape[0], D))
+    for k in range(D):
+        e = np.zeros(D)
+        e[k] = 1.0
+        X[:, k] = np.asarray(logits_of(e), dtype=np.float64).reshape(-1)
+    th = np.random.RandomState(0).standard_normal(D)
+    got = np.asarray(logits_of(th), dtype=np.float64).reshape(-1)
+    want = X @ th
+    if not np.allclose(got, want, rtol=rtol, atol=rtol * max(1.0, float(np.max(np.abs(want))))):
+        raise NotImplementedError("the logits of the observed Bernoulli site are not linear in the latent vector")
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    if y.shape[0] != X.shape[0] or not np.all((y == 0) | (y == 1)):
+        raise NotImplementedError("observations must be one 0/1 value per row of the design matrix")
+    return dict(family="logistic_regression", X=X, y=y, priorScale=float(priorScale))
+
+
 def potentialFromNumpyroModel(model, model_args=(), model_kwargs=None):
     """Traces a NumPyro model once and maps it to a family (needs numpyro + jax).  Recognised:
     a single MultivariateNormal / Normal latent site without observations, and a Bernoulli-logit
-    likelihood ``obs ~ Bernoulli(logits = X @ theta)`` with a Normal(0, s) prior on theta."""
+    likelihood ``obs ~ Bernoulli(logits = X @ theta)`` with a Normal(0, s) prior on theta
+    (logisticSpecFromLinearLogits), and the coin-toss sample of the reference.
+
+    NumPyro and JAX are absent from the build image, so this function itself has never run there: the
+    recognisers it delegates to (potentialFromSpec, logisticSpecFromLinearLogits) are what the tests cover."""
     try:
         import numpyro  # noqa: F401
         from numpyro import handlers
@@ -60,6 +92,22 @@ def potentialFromNumpyroModel(model, model_args=(), model_kwargs=None):
             isinstance(getattr(s["fn"], "base_dist", s["fn"]), (dist.BernoulliProbs,)) for s in observed):
         # the coin-toss sample: site k observes Bernoulli(latent k)
         return potentialFromSpec(dict(family="coin_toss", observations=[np.asarray(s["value"]) for s in observed]))
+    if len(latent) == 1 and len(observed) == 1:
+        # Bayesian logistic regression: theta ~ Normal(0, s) iid, obs ~ Bernoulli(logits = X @ theta)
+        prior = getattr(latent[0]["fn"], "base_dist", latent[0]["fn"])
+        like = getattr(observed[0]["fn"], "base_dist", observed[0]["fn"])
+        scale = np.unique(np.asarray(getattr(prior, "scale", np.nan), dtype=np.float64))
+        if (isinstance(prior, dist.Normal) and np.allclose(np.asarray(prior.loc), 0.0) and scale.size == 1
+                and isinstance(like, dist.BernoulliLogits) and np.ndim(latent[0]["value"]) == 1):
+            name, obs_name = latent[0]["name"], observed[0]["name"]
+
+            def logits_of(theta):
+                t = handlers.trace(handlers.substitute(handlers.seed(model, jax.random.PRNGKey(0)), {name: jax.numpy.asarray(theta)}))
+                site = t.get_trace(*model_args, **(model_kwargs or {}))[obs_name]
+                return np.asarray(getattr(site["fn"], "base_dist", site["fn"]).logits)
+
+            return potentialFromSpec(logisticSpecFromLinearLogits(logits_of, latent[0]["value"].shape[0],
+                                                                  np.asarray(observed[0]["value"]), float(scale[0])))
     if len(latent) == 1 and not observed:
         d = latent[0]["fn"]
         if isinstance(d, dist.MultivariateNormal):

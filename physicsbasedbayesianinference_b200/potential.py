@@ -52,7 +52,8 @@ class Potential:
 
     # -- evaluation (always on the GPU) ------------------------------------------------
     def _eval(self, q, want_energy, want_grad):
-        ctx = _lib.Context.get()
+        # the context of the device the tensor LIVES on (not the current device): the kernel is launched there
+        ctx = _lib.Context.get(q.device.index if getattr(q, "is_cuda", False) else None)
         if isinstance(q, np.ndarray) or not hasattr(q, "is_cuda"):
             qa = np.asarray(q)
             one = qa.ndim == 1

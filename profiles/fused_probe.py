@@ -16,8 +16,10 @@ import os
 ctx = E._lib.Context.get()
 if os.environ.get("EHMC_ENS_DEBUG"):
     ctx.set_option("ens_debug", float(os.environ["EHMC_ENS_DEBUG"]))
+if os.environ.get("EHMC_ENS_SSHIFT"):
+    ctx.set_option("ens_sshift", float(os.environ["EHMC_ENS_SSHIFT"]))  # sub-batches per queue item = 2^value
 LAG = int(os.environ.get("EHMC_ADAPT_LAG", "2"))
-for logP in (19, 22):
+for logP in (19, 20, 22):
     P = 1 << logP
     ens = E.Ensemble(D, P, dtype=np.float32, device="cuda", seed=1)
     ens.setPosition(1.0)

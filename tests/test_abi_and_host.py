@@ -34,7 +34,7 @@ def test_header_symbols_all_exported():
 
 
 def test_version_and_struct_layout():
-    assert _lib.load().ehmc_version() == 100
+    assert _lib.load().ehmc_version() == 110
     # struct ehmc_hmc_args: 4 x 32-bit, 4 doubles, 3 x u64, 1 pointer; struct ehmc_dynamic: 2 doubles, 3 x u64
     assert ctypes.sizeof(_lib.HmcArgs) == 16 + 32 + 24 + 8
     assert ctypes.sizeof(_lib.Dynamic) == 40
@@ -205,3 +205,24 @@ def test_model_spec_adapter():
         A.potentialFromSpec(dict(family="eight_schools"))
     with pytest.raises((ImportError, NotImplementedError)):
         A.potentialFromNumpyroModel(lambda: None)
+
+
+def test_logistic_recognition_from_logits():
+    """The Bernoulli-logit recogniser of the NumPyro adapter (the part that needs no NumPyro): X is recovered from
+    the logits of the observed site, models with an intercept or a non-linear predictor are refused."""
+    from physicsbasedbayesianinference_b200 import numpyro_adapter as A
+
+    rng = np.random.RandomState(5)
+    X = rng.standard_normal((50, 4))
+    y = (rng.uniform(size=50) < 0.5).astype(np.float64)
+    spec = A.logisticSpecFromLinearLogits(lambda th: X @ th, 4, y, 2.0)
+    assert spec["family"] == "logistic_regression" and spec["priorScale"] == 2.0
+    np.testing.assert_allclose(spec["X"], X, rtol=0, atol=1e-15)
+    pot = A.potentialFromSpec(spec)
+    assert pot.numDimensions == 4
+    with pytest.raises(NotImplementedError):
+        A.logisticSpecFromLinearLogits(lambda th: X @ th + 0.3, 4, y, 1.0)  # intercept
+    with pytest.raises(NotImplementedError):
+        A.logisticSpecFromLinearLogits(lambda th: np.tanh(X @ th), 4, y, 1.0)  # not linear
+    with pytest.raises(NotImplementedError):
+        A.logisticSpecFromLinearLogits(lambda th: X @ th, 4, y + 0.5, 1.0)  # not 0/1 observations

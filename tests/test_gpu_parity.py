@@ -1556,6 +1556,38 @@ def test_logistic_precision_auto_guard(E):
         assert np.max(np.abs(ga - ref) / scale) < 1e-5
 
 
+def test_config4_full_size(E):
+    """BASELINE config 4 at FULL size (4096 bodies x 3-D, ensemble of 1024, L = 10): one HMC iteration of the whole
+    ensemble with fed momenta and uniforms; 8 of the 1024 particles against the float64 oracle, whose results are the
+    committed fixture tests/golden/c4_full_8.npz (tests/golden/make_golden_c4.py: the oracle needs 13 s per particle)."""
+    import torch
+
+    from tests.golden.make_golden_c4 import B, EPS, H, L, P, config4_inputs
+
+    g = np.load(os.path.join(GOLDEN, "c4_full_8.npz"))
+    sel = g["sel"]
+    q0, z, u = config4_inputs()
+    m = np.ones(B) / B
+    ens = E.Ensemble(3 * B, P, dtype=np.float32, device="cuda")
+    ens.q.copy_(torch.tensor(q0, dtype=torch.float32))
+    hmc = E.HMC(ens, L * H + 1e-9, H, None, potential=E.NBodyPotential(m, G=1.0, eps=EPS))
+    assert hmc.integrator.numSteps == L
+    acc = torch.empty(P, dtype=torch.uint8, device="cuda")
+    hmc.step(1 / KB, accept=acc, z=torch.tensor(z, dtype=torch.float32, device="cuda"),
+             u=torch.tensor(u, dtype=torch.float32, device="cuda"))
+    torch.cuda.synchronize()
+    a = acc.cpu().numpy().astype(bool)[sel]
+    with np.errstate(over="ignore"):
+        clear = np.abs(u[sel] - np.minimum(1, np.exp(g["oldH"] - g["newH"]))) > TIE[np.float32]
+    assert np.array_equal(a[clear], g["accept"][clear])
+    same = a == g["accept"]
+    assert same.sum() >= 6
+    qg = ens.q.cpu().numpy()[:, sel]
+    err = float(np.max(np.abs(qg[:, same] - g["q1"][:, same])) / float(g["q1_absmax"]))
+    print("config 4 full size: rel err q", err, "accepted", int(a.sum()), "of", len(sel))
+    assert err < 1e-5
+
+
 def test_config3_full_size(E):
     """BASELINE config 3 at FULL size on the tensor-core path: X 100 000 x 256, 65 536 particles, L = 10, float32
     state, fed momenta and uniforms; 128 random particles against the float64 oracle at the north_star's 1e-5.
