@@ -125,7 +125,9 @@ class ClockSampler:
     """Samples SM clock, power and throttle reasons of one GPU through NVML (nvidia_ml_py) every
     few ms in a thread while the timed region runs; falls back to one nvidia-smi query."""
 
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x2: "applications_clocks_setting", 0x10: "sync_boost", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}  # (0x1 gpu_idle is not a slowdown)
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -183,6 +185,7 @@ class ClockSampler:
                 "sm_max_mhz": float(mx) if mx else None,
                 "power_w_max": max(x[1] for x in self.samples) if self.samples else None,
                 "samples": len(sm), "reasons": sorted(reasons),
+                "reason_bits_or": hex(int(np.bitwise_or.reduce([int(x[2]) for x in self.samples]))) if self.samples else None,
                 "source": "nvml, 4 ms sleep between queries, during the timed region"}
 
     def _smi_once(self):
@@ -408,7 +411,7 @@ def fused_get_samples(E, leg, dev):
     ens_f = E.Ensemble(D, P, dtype=np.float32, device=dev, seed=SEED)
     hmc_f = E.HMC(ens_f, L * h + 1e-9, h, None, potential=leg.pot, seed=SEED)
     with contextlib.redirect_stdout(io.StringIO()):
-        hmc_f.getSamples(10, 1 / KB, 1.0)
+        hmc_f.getSamples(1000, 1 / KB, 1.0)  # warm-up of the same size: first-use cudaMalloc of the (D, P, S) arrays
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         hmc_f.getSamples(1000, 1 / KB, 1.0)

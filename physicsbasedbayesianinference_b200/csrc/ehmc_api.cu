@@ -268,9 +268,15 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
   } else if (!strcmp(name, "ens_debug_dump")) {
     // debugging aid: phase stamps of the last fused ensemble run (ns relative to the first), to stderr
     if (c->ens_dbg_buf.ptr && c->ens_debug > 0) {
-      std::vector<long long> hbuf((size_t)8 * c->ens_debug);
+      std::vector<long long> hbuf((size_t)8 * (c->ens_debug + 1));
       CUDA_TRY(cudaMemcpy(hbuf.data(), c->ens_dbg_buf.ptr, sizeof(long long) * hbuf.size(), cudaMemcpyDeviceToHost));
       const int first = (int)value;
+      {
+        const long long* t = &hbuf[(size_t)8 * c->ens_debug];  // totals over the compute warps of the launch
+        fprintf(stderr, "ens_debug totals: %lld compute warps; mean wait per warp: %.1f us for the group mark, %.1f us "
+                "for the step size\n", t[2], t[2] ? 1e-3 * (double)t[0] / (double)t[2] : 0.0,
+                t[2] ? 1e-3 * (double)t[1] / (double)t[2] : 0.0);
+      }
       for (int it = first; it < c->ens_debug && hbuf[(size_t)8 * it]; ++it) {
         const long long* r = &hbuf[(size_t)8 * it];
         fprintf(stderr, "ens_debug it %d: master: tickets of it at %lld, +reduce %lld +push %lld +peers %lld +publish %lld | "

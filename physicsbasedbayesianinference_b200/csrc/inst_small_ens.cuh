@@ -79,8 +79,8 @@ static int ens_launch(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, EnsRunA
   R.dbg = nullptr;
   R.dbg_iters = 0;
   if (c->ens_debug > 0) {
-    TRY(c->ens_dbg_buf.ensure(sizeof(long long) * 8 * (size_t)c->ens_debug));
-    CUDA_TRY(cudaMemsetAsync(c->ens_dbg_buf.ptr, 0, sizeof(long long) * 8 * (size_t)c->ens_debug, st));
+    TRY(c->ens_dbg_buf.ensure(sizeof(long long) * 8 * ((size_t)c->ens_debug + 1)));  // + one row of totals
+    CUDA_TRY(cudaMemsetAsync(c->ens_dbg_buf.ptr, 0, sizeof(long long) * 8 * ((size_t)c->ens_debug + 1), st));
     R.dbg = static_cast<long long*>(c->ens_dbg_buf.ptr);
     R.dbg_iters = c->ens_debug;
   }

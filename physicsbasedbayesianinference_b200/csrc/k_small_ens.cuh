@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_small_ens(const IterArgs<T> A
   __shared__ int s_it[NWARP];                      // the current pair and its step size, lane 0 -> the warp
   __shared__ unsigned s_b[NWARP];
   __shared__ double s_hcur[NWARP];
+  __shared__ unsigned long long s_wait[NWARP][2];  // (debug) ns this warp spun for its group's mark / for the step size
 
   if (blockIdx.x < ncompute) {
     // ===== compute CTAs: four independent warps, each a worker of ONE queue over (iteration, batch) =====
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_small_ens(const IterArgs<T> A
       s_pub_seen[w] = 0;
       s_base[w] = 0ull;
       s_next_it[w] = 0;
+      s_wait[w][0] = s_wait[w][1] = 0ull;
       take(atomicAdd(R.cursor, 1ull));
     }
     for (;;) {
@@ -200,18 +202,34 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_small_ens(const IterArgs<T> A
           if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
           // the batch's positions were written by whoever ran it in the previous iteration
           unsigned dn = s_done_seen[w];
-          while (dn < (unsigned)it) {
-            __nanosleep(100);
-            dn = ld_acquire_gpu_u32(&R.done[b >> R.bshift]);
+          if (dn < (unsigned)it) {
+            unsigned long long ta = 0, tb = 0;
+            if (R.dbg != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ta));
+            while (dn < (unsigned)it) {
+              __nanosleep(100);
+              dn = ld_acquire_gpu_u32(&R.done[b >> R.bshift]);
+            }
+            if (R.dbg != nullptr) {
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb));
+              s_wait[w][0] += tb - ta;
+            }
           }
           long long ps = s_pub_seen[w];
-          while (ps < it + 1) {
-            __nanosleep(200);
-            ps = ld_acquire_gpu(pub);
-            if (ps >= it + 1) {
+          if (ps < it + 1) {
+            unsigned long long ta = 0, tb = 0;
+            if (R.dbg != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ta));
+            while (ps < it + 1) {
+              __nanosleep(200);
+              ps = ld_acquire_gpu(pub);
+              if (ps >= it + 1) {
 #pragma unroll
-              for (int k = 0; k < ENS_RING; ++k) s_hring[w][k] = __longlong_as_double(__ldcg(pub + 1 + k));
-              s_pub_seen[w] = ps;
+                for (int k = 0; k < ENS_RING; ++k) s_hring[w][k] = __longlong_as_double(__ldcg(pub + 1 + k));
+                s_pub_seen[w] = ps;
+              }
+            }
+            if (R.dbg != nullptr) {
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb));
+              s_wait[w][1] += tb - ta;
             }
           }
           // (a ring slot is rewritten only after the iteration it belonged to has completed everywhere, and the
@@ -227,7 +245,14 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_small_ens(const IterArgs<T> A
         }
       }
       __syncwarp();  // (also orders the other lanes' loads behind lane 0's acquires)
-      if (s_it[w] < 0) break;
+      if (s_it[w] < 0) {
+        if (lane == 0 && R.dbg != nullptr) {  // totals over all compute warps, behind the per-iteration stamps
+          atomicAdd(reinterpret_cast<unsigned long long*>(R.dbg) + 8 * R.dbg_iters + 0, s_wait[w][0]);
+          atomicAdd(reinterpret_cast<unsigned long long*>(R.dbg) + 8 * R.dbg_iters + 1, s_wait[w][1]);
+          atomicAdd(reinterpret_cast<unsigned long long*>(R.dbg) + 8 * R.dbg_iters + 2, 1ull);
+        }
+        break;
+      }
       // the round trip of the next atomic hides behind this batch (its result is first used after the trajectories)
       if (lane == 0) g_next = atomicAdd(R.cursor, 1ull);
       {
