@@ -11,7 +11,9 @@ namespace ehmc {
 template <typename T, int DT, class Pot, bool EXACT>
 static int ens_launch(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, EnsRunArgs<T> R, cudaStream_t st) {
   auto kernel = k_small_ens<T, DT, Pot, INTEG_LEAPFROG, EXACT>;
-  const size_t sm = std::max(WarpStats<T, DT>::kSmemBytes, ENS_SERVICE_SMEM);
+  // service CTAs: two vectors of <= 72 doubles + the received halves [world][2 (2D + 3)]
+  const size_t svc = std::max(ENS_SERVICE_SMEM, (size_t)1152 + sizeof(unsigned) * (size_t)std::max(1, R.world) * 2 * (2 * A.D + 3));
+  const size_t sm = std::max(WarpStats<T, DT>::kSmemBytes, svc);
   if (sm > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   int occ = 0, coop = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, K1_THREADS, sm));

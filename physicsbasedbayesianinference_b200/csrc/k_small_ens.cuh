@@ -424,19 +424,46 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_small_ens(const IterArgs<T> A
           if (r != R.rank) st_relaxed_sys(reinterpret_cast<unsigned long long*>(R.peers[r]) + slot + w, word);
       }
       stamp(it, 2);
-      // receive: poll every word of every peer's slot in MY mailbox; halves go to shared memory
+      // receive: poll every word of every peer's slot in MY mailbox; halves go to shared memory.  The (world - 1) NW
+      // words are dealt to the lanes and up to eight are in flight per lane: polled one after the other (a system-
+      // scope load is a 1-2 us round trip under load) the 7 x 46 words of an 8-GPU run made the master's period --
+      // and with it every iteration of the run -- 10 us longer than the trajectories (profiles/r02_bench_n8.json:
+      // 41.8 us per iteration at 8 GPUs against 32.4 us for the same shard without peers).
       unsigned* rx = reinterpret_cast<unsigned*>(k1_smem + 144);  // [world][NW]
-      for (int r = 0; r < R.world; ++r) {
-        if (r == R.rank) continue;
-        const unsigned long long* src =
-            reinterpret_cast<const unsigned long long*>(R.peers[R.rank]) + ((size_t)par * R.world + r) * ENS_MB_STRIDE;
-        for (int w = lane; w < NW; w += 32) {
-          unsigned long long word;
-          do {
-            word = ld_relaxed_sys(src + w);
-          } while ((unsigned)(word >> 32) != flag);
-          rx[r * NW + w] = (unsigned)word;
+      const unsigned long long* mine =
+          reinterpret_cast<const unsigned long long*>(R.peers[R.rank]) + (size_t)par * R.world * ENS_MB_STRIDE;
+      const int total = (R.world - 1) * NW;
+      for (int k0 = lane; k0 < total; k0 += 32 * 8) {
+        const unsigned long long* src[8];
+        unsigned long long word[8];
+        int dst[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k0 + 32 * j;
+          dst[j] = -1;
+          src[j] = mine;
+          if (k < total) {
+            const int pi = k / NW, w = k - pi * NW;
+            const int r = pi + (pi >= R.rank ? 1 : 0);
+            src[j] = mine + (size_t)r * ENS_MB_STRIDE + w;
+            dst[j] = r * NW + w;
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) word[j] = dst[j] >= 0 ? ld_relaxed_sys(src[j]) : 0ull;  // independent loads
+        bool pending;
+        do {
+          pending = false;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (dst[j] >= 0 && (unsigned)(word[j] >> 32) != flag) {
+              word[j] = ld_relaxed_sys(src[j]);
+              pending = pending || (unsigned)(word[j] >> 32) != flag;
+            }
+        } while (pending);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (dst[j] >= 0) rx[dst[j]] = (unsigned)word[j];
       }
       __syncwarp();
       stamp(it, 3);

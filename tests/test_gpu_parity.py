@@ -1737,3 +1737,82 @@ def test_checkpoint_resume_is_bit_exact(E, tmp_path):
     hmc_b.run(5, 1 / KB, collectStats=False)
     torch.cuda.synchronize()
     assert torch.equal(ens_a.q, ens_b.q)
+
+
+def test_checkpoint_resume_of_an_adaptive_run(E, tmp_path):
+    """A checkpoint taken between two run() calls of an ADAPTIVE driver (step size adapted at fixed numSteps, so
+    simulTime = numSteps * stepSize has drifted from the constructor's value; mass scales set) restores the trajectory
+    length, the flags and the scales: the resumed driver continues exactly like the uninterrupted one."""
+    import torch
+
+    D, P = 10, 4096
+
+    def make(bugCompat=False):
+        ens = E.Ensemble(D, P, dtype=np.float32, device="cuda", seed=5)
+        ens.setPosition(1.0)
+        return ens, E.HMC(ens, 0.81, 0.05, None, potential=E.HarmonicPotential(np.logspace(-1, 1, D)), seed=5,
+                          bugCompat=bugCompat, rejectNonFinite=True)
+
+    ens_a, hmc_a = make()
+    hmc_a.run(60, 1 / KB, adapt=True, adaptMass=True, keepNumSteps=True)
+    assert hmc_a.massScale is not None and hmc_a.integrator.numSteps == 16
+    assert abs(hmc_a.simulTime - 0.81) > 1e-3  # drifted with the step size
+    E.io.saveCheckpoint(str(tmp_path / "ck"), hmc_a)
+    ra = hmc_a.run(5, 1 / KB)
+    ens_b, hmc_b = make(bugCompat=True)  # flags differ on purpose: the checkpoint's win
+    hmc_b.rejectNonFinite = None
+    E.io.loadCheckpoint(str(tmp_path / "ck"), hmc_b)
+    assert hmc_b.integrator.numSteps == 16 and hmc_b.simulTime == hmc_a.integrator.numSteps * hmc_b.stepSize
+    assert hmc_b.bugCompat is False and hmc_b.rejectNonFinite is True
+    np.testing.assert_array_equal(hmc_b.massScale, hmc_a.massScale)
+    rb = hmc_b.run(5, 1 / KB)
+    torch.cuda.synchronize()
+    assert torch.equal(ens_a.q, ens_b.q)
+    assert ra["acceptRate"] == rb["acceptRate"]
+
+
+def test_set_position_draws_fresh_positions_each_call(E):
+    """Device-backed Ensemble.setPosition draws NEW positions on every call, like the reference's norm.rvs
+    (src/ensemble.py:72-74); the first call is the documented stream of (seed, iteration word ~0)."""
+    import torch
+
+    ens = E.Ensemble(3, 1000, dtype=np.float32, device="cuda", seed=9)
+    q1 = ens.setPosition(2.0).clone()
+    q2 = ens.setPosition(2.0).clone()
+    assert not torch.equal(q1, q2)
+    assert abs(float(q2.std()) - 2.0) < 0.1 and abs(float(torch.corrcoef(torch.stack([q1.flatten(), q2.flatten()]))[0, 1])) < 0.1
+    ref = torch.empty_like(q1)
+    E._lib.set_position(E._lib.Context.get(), ref, 2.0, 9, 0)
+    assert torch.equal(q1, ref)
+
+
+def test_run_rejects_non_finite_ratios_by_default(E):
+    """HMC.run must survive divergent trajectories: particles deep in the funnel's neck (v = -60: e^{60} x^2 overflows,
+    the energy difference is inf - inf = NaN) are REJECTED by run() and stay where they were, while step() keeps the
+    reference's rule -- u > NaN is False, the NaN proposal is accepted (src/HMC.py:168-173)."""
+    import torch
+
+    D, P = 10, 2048
+    q0 = torch.randn((D, P), dtype=torch.float32, device="cuda")
+    q0[0, :64] = -60.0
+    q0[1:, :64] = 1.0e10
+
+    def make(**kw):
+        ens = E.Ensemble(D, P, dtype=np.float32, device="cuda", seed=2)
+        ens.q.copy_(q0)
+        return ens, E.HMC(ens, 0.5, 0.05, None, potential=E.FunnelPotential(D, 3.0), seed=2, bugCompat=False, **kw)
+
+    ens, hmc = make()
+    r = hmc.run(3, 1 / KB)
+    torch.cuda.synchronize()
+    assert torch.isfinite(ens.q).all()
+    assert torch.equal(ens.q[:, :64], q0[:, :64])  # never moved
+    assert np.isfinite(r["mean"].numpy()).all()
+    ens2, hmc2 = make()  # reference semantics outside run()
+    hmc2.step(1 / KB)
+    torch.cuda.synchronize()
+    assert not torch.isfinite(ens2.q[:, :64]).all()
+    ens3, hmc3 = make(rejectNonFinite=False)  # explicit opt-out applies to run() too
+    hmc3.run(1, 1 / KB)
+    torch.cuda.synchronize()
+    assert not torch.isfinite(ens3.q[:, :64]).all()
