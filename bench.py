@@ -55,7 +55,7 @@ OTHER_STEPS = {"c1": 50, "c3": 3, "c4": 4, "c5": 1000, "c5l4": 1000}  # (config 
 LOGI_PREC = os.environ.get("EHMC_LOGISTIC_PRECISION", "fp16x3")
 
 
-ADAPT_LAG = int(os.environ.get("EHMC_ADAPT_LAG", "2"))
+ADAPT_LAG = int(os.environ.get("EHMC_ADAPT_LAG", "3"))
 
 
 def flops_per_unit(name, D):
@@ -367,8 +367,8 @@ class Leg:
         if n <= 0:
             return
         if self.adaptive:
-            # adaptLag = 2 at every N (results must not depend on the GPU count): the reductions and the all-reduce get
-            # two iterations, see HMC.run
+            # the same adaptLag (3) at every N (results must not depend on the GPU count): the reductions and the all-reduce get
+            # three iterations, see HMC.run
             self.run_out = self.hmc.run(n, 1 / KB, adapt=True, group=group, keepNumSteps=True, adaptLag=ADAPT_LAG)
         else:
             for _ in range(n):

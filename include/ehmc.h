@@ -293,8 +293,9 @@ typedef struct {
   double targetAccept, gain0, kappa, maxMove, minStep, maxStep; /* parallel.StepSizeAdapter */
   double numParticlesTotal;  /* particles of ALL ranks */
   int32_t lag;               /* the statistics of iteration k set the step size of iteration k + 1 + lag: 1 (0 means 1:
-                              * the one-iteration-stale pipeline of HMC.run) or 2 (two iterations for the reduction
-                              * and the all-reduce; what the 8-GPU runs of small shards need) */
+                              * the one-iteration-stale pipeline of HMC.run) up to 4.  The lag has to cover the span of an
+                              * iteration (hand-out of its batches, the last trajectory, the reductions, the all-reduce)
+                              * in units of the time per iteration: 3 for shards of ~2^19 particles on 8 GPUs */
   int32_t reserved;
 } ehmc_adapt_args;
 

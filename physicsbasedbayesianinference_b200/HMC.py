@@ -254,10 +254,11 @@ class HMC:
         or keepNumSteps=True); it needs CUDA IPC / peer access between the GPUs of `group`.
 
         adaptLag: the statistics of iteration k set the step size of iteration k + 1 + adaptLag.  1 (default) is the
-        one-iteration-stale pipeline described above; 2 leaves two iterations for the reductions and the all-reduce,
-        which is what small shards on many GPUs need (at 2^19 particles per GPU an iteration is 30 us and the chain
-        last slice -> reductions -> slowest of 8 GPUs -> publish measured 20-30 us).  The host loop and the fused
-        launch implement the same schedule for either value; results do not depend on the number of GPUs.
+        one-iteration-stale pipeline described above; 2 .. 4 leave that many iterations for the hand-out of an
+        iteration's batches, its last trajectories, the reductions and the all-reduce, which is what small shards on
+        many GPUs need (at 2^19 particles per GPU an iteration is 30 us and that span measured 90-100 us: 3).  The
+        host loop and the fused launch implement the same schedule for every value; results do not depend on the
+        number of GPUs.
 
         adaptMass=True adds ensemble-based diagonal MASS adaptation to the warm-up (the first adaptIterations
         iterations; needs adapt=True): at the end of each of `massWindows` windows of doubling length the all-reduced
@@ -272,8 +273,8 @@ class HMC:
         Returns dict(acceptRate[S], meanAcceptProb[S], meanH[S], stepSize[S], mean[D], var[D],
         trace (D, traceParticles, S) or None).
         """
-        if adaptLag not in (1, 2):
-            raise ValueError("adaptLag must be 1 or 2")
+        if adaptLag not in (1, 2, 3, 4):
+            raise ValueError("adaptLag must be 1, 2, 3 or 4")
         if not self._inRun:
             # everything below runs with _inRun set: non-finite acceptance ratios are rejected unless the driver was
             # built with an explicit rejectNonFinite=False (see __init__)

@@ -259,6 +259,9 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
   } else if (!strcmp(name, "nbody_ti")) {
     if (value != 0 && value != 4 && value != 8) return fail(EHMC_ERR_INVALID, "nbody_ti must be 0, 4 or 8");
     c->nbody_ti = (int)value;
+  } else if (!strcmp(name, "ens_groups")) {
+    if (!(value >= 1 && value <= 8192)) return fail(EHMC_ERR_INVALID, "ens_groups must be in [1, 8192]");
+    c->ens_groups = (int)value;
   } else if (!strcmp(name, "ens_sshift")) {
     if (!(value >= -1 && value <= 4)) return fail(EHMC_ERR_INVALID, "ens_sshift must be in [-1, 4]");
     c->ens_sshift = (int)value;
@@ -1107,7 +1110,7 @@ extern "C" int ehmc_hmc_run_ensemble(ehmc_ctx* ctx, const ehmc_potential* pot, D
   if (!(ad->numParticlesTotal > 0) || !(ad->minStep > 0) || !(ad->maxStep >= ad->minStep))
     return fail(EHMC_ERR_INVALID, "%s: bad adaptation scalars", fn);
   if (comm && (comm->ctx != ctx || !comm->connected)) return fail(EHMC_ERR_INVALID, "%s: communicator not connected on this context", fn);
-  if (ad->lag < 0 || ad->lag > ENS_MAX_LAG) return fail(EHMC_ERR_INVALID, "%s: adapt.lag must be 0 (= 1), 1 or %d", fn, ENS_MAX_LAG);
+  if (ad->lag < 0 || ad->lag > ENS_MAX_LAG) return fail(EHMC_ERR_INVALID, "%s: adapt.lag must be 0 (= 1) or 1 .. %d", fn, ENS_MAX_LAG);
   View vs, vh, vm, vt;
   TRY(parse_float(state, "state", 1, 64, &vs));
   if (vs.host || vs.shape[0] != 4) return fail(EHMC_ERR_INVALID, "%s: state must be a device float64[4]", fn);

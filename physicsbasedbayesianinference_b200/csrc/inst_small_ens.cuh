@@ -36,7 +36,7 @@ static int ens_launch(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, EnsRunA
   int sshift = c->ens_sshift >= 0 ? c->ens_sshift : (nrows >= (1 << 16) ? (A.L <= 8 ? 2 : 1) : 0);
   const long long nbatch = (nrows + (1LL << sshift) - 1) >> sshift;
   int bshift = 0;
-  while ((nbatch >> bshift) > 2048) ++bshift;
+  while ((nbatch >> bshift) > c->ens_groups) ++bshift;
   R.bshift = bshift;
   R.sshift = sshift;
   R.nrows = (unsigned)nrows;

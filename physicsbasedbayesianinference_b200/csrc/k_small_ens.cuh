@@ -25,9 +25,12 @@
 //     vectors, adds the world's vectors in rank order (every rank computes the same bits), updates log h and
 //     publishes h[it + 1 + lag]: with lag = 1 the one-iteration-stale pipeline of HMC.run, so the reductions, the
 //     NVLink round trip (368 B out and in per peer, a few microseconds) and the update hide behind iteration it + 1;
-//     lag = 2 gives them two iterations (at 2^19 particles per GPU an iteration is 30 us and the chain -- last
-//     batch, three reduction levels, the slowest of 8 GPUs, publish -- measured 20-30 us:
-//     profiles/r02_bench_n8_mid.json was taken with lag = 1 and waited for h in every iteration).
+//     lag = 2 gives them two iterations, lag = 3 three.  What the lag has to cover is the whole span of an
+//     iteration -- its first batch starts, a period later its last ticket is taken, that batch runs, three
+//     reduction levels, the slowest of N GPUs, publish -- measured 90-100 us at 2^19 particles per GPU, where a
+//     period is ~30 us: with lag = 2 every iteration's first batches waited 5-10 us for their step size and the run
+//     advanced at (span + chain) / 3 per iteration (profiles/r02_ens_wait_ranks2_L20.txt: 34.7 us at 2 GPUs, 37.3 us
+//     at 8, against 32.4 us without peers); profiles/r02_bench_n8_mid.json was taken with lag = 1.
 // Why batches and a queue (measured at 2^19 particles per GPU, the 8-GPU shard of config 5, 28.8 us for the bare
 // per-launch kernel): a fixed share per CTA is 3.46 blocks of 128 that round up to 4, and the warp schedulers'
 // preference for the oldest warps let the oldest CTAs of every SM finish early and wait ahead of the others (39 us
@@ -49,14 +52,14 @@ constexpr int ENS_SERVICE_CTAS = 8; // blocks of reducer warps (one of them also
 constexpr int ENS_GROUP = 64;      // group rows per first-level reduction of the service warps
 constexpr int ENS_MAX_GROUPS = 8192;  // groups per iteration at most (the launcher aims at 2048)
 constexpr int ENS_MB_STRIDE = 144;  // 8-byte words per mailbox slot: two per statistic (up to 2 * 32 + 3 statistics)
-constexpr int ENS_RING = 4;        // iterations in flight at most (lag <= 2): rows, tickets and step sizes are rings of 4
-constexpr int ENS_MAX_LAG = 2;
+constexpr int ENS_RING = 8;        // iterations in flight at most (>= lag + 2): rows, tickets and step sizes are rings of 8
+constexpr int ENS_MAX_LAG = 4;
 constexpr size_t ENS_SERVICE_SMEM = 5632;  // master warp: two vectors of <= 72 doubles + [8 ranks][2 * 67] received halves
 
 template <typename T>
 struct EnsRunArgs {
   int nIter;
-  int lag;             // the statistics of iteration it set the step size of iteration it + 1 + lag (1 or 2)
+  int lag;             // the statistics of iteration it set the step size of iteration it + 1 + lag (1 .. ENS_MAX_LAG)
   int adaptIters;      // Robbins-Monro updates during the first adaptIters iterations of this launch
   double target, maxMove, logLo, logHi;
   const double* gains;  // [adaptIters] Robbins-Monro gain of every update, gain0 / k^kappa (host-computed)

@@ -18,6 +18,8 @@ if os.environ.get("EHMC_ENS_DEBUG"):
     ctx.set_option("ens_debug", float(os.environ["EHMC_ENS_DEBUG"]))
 if os.environ.get("EHMC_ENS_SSHIFT"):
     ctx.set_option("ens_sshift", float(os.environ["EHMC_ENS_SSHIFT"]))  # sub-batches per queue item = 2^value
+if os.environ.get("EHMC_ENS_GROUPS"):
+    ctx.set_option("ens_groups", float(os.environ["EHMC_ENS_GROUPS"]))  # groups of batches per iteration at most
 LAG = int(os.environ.get("EHMC_ADAPT_LAG", "2"))
 for logP in (19, 20, 22):
     P = 1 << logP

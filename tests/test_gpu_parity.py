@@ -1318,7 +1318,7 @@ def test_run_fused_matches_host_loop(E, case, dt, lag):
     np.testing.assert_allclose(r2f["stepSize"], r2h["stepSize"], rtol=1e-12)  # device exp() vs libm: 1 ulp
 
 
-@pytest.mark.parametrize("lag", [1, 2])
+@pytest.mark.parametrize("lag", [1, 2, 3])
 def test_run_fused_two_ranks(E, tmp_path, lag):
     """The in-kernel all-reduce of the fused ensemble run: two processes (sharing this GPU: CUDA IPC mailboxes work
     within one device and the time-sliced persistent kernels still make progress), each with half of the ensemble,
