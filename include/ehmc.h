@@ -185,6 +185,8 @@ EHMC_API int ehmc_ctx_device_info(const ehmc_ctx* ctx, double out[4]);
  *   "nbody_ti"        bodies per thread of the N-body kernel (0 auto, 4, 8)
  *   "ens_sshift"      fused ensemble run: log2 of the 32-particle sub-batches a warp takes from the work queue at
  *                     once (-1 auto: 0 below 2^21 particles per GPU, above that 1, or 2 for trajectories of <= 8 steps)
+ *   "ens_groups"      fused ensemble run: groups of batches (one float64 statistics row each) per iteration at most
+ *                     (0 auto: 4096 for trajectories of more than 8 steps, else 2048)
  *   "host_chunk_mb"   bytes of state per staged chunk on the host path
  *   "tc_debug", "tc_prof", "tc_prof_dump"  profiling aids of the tensor-core dense kernels */
 EHMC_API int ehmc_ctx_set_option(ehmc_ctx* ctx, const char* name, double value);

@@ -260,7 +260,7 @@ extern "C" int ehmc_ctx_set_option(ehmc_ctx* c, const char* name, double value) 
     if (value != 0 && value != 4 && value != 8) return fail(EHMC_ERR_INVALID, "nbody_ti must be 0, 4 or 8");
     c->nbody_ti = (int)value;
   } else if (!strcmp(name, "ens_groups")) {
-    if (!(value >= 1 && value <= 8192)) return fail(EHMC_ERR_INVALID, "ens_groups must be in [1, 8192]");
+    if (!(value >= 0 && value <= 8192)) return fail(EHMC_ERR_INVALID, "ens_groups must be in [0, 8192] (0 = auto)");
     c->ens_groups = (int)value;
   } else if (!strcmp(name, "ens_sshift")) {
     if (!(value >= -1 && value <= 4)) return fail(EHMC_ERR_INVALID, "ens_sshift must be in [-1, 4]");

@@ -68,7 +68,7 @@ struct ehmc_ctx {
   long long host_chunk_bytes = 32LL << 20;
   int tc_prof = 0;                // 1: record a clock64 trace of CTA 0 into tc_prof_buf (64 x int64)
   DevBuf tc_prof_buf;
-  int ens_groups = 2048;          // fused ensemble run: groups of batches per iteration at most (one float64 row each)
+  int ens_groups = 0;             // fused ensemble run: groups of batches per iteration at most (one float64 row each); 0 = auto
   int ens_sshift = -1;            // fused ensemble run: log2(sub-batches per queue item), -1 = by shard size
   int ens_debug = 0;              // iterations of the fused ensemble run whose phase stamps are recorded
   DevBuf ens_dbg_buf;
