@@ -19,8 +19,9 @@ other_configs : short legs of the other BASELINE configs on the same ranks (c1 a
             ms_per_step, roofline and clocks; c5 / c5l4 run the fused adaptive ensemble run whose statistics
             all-reduce happens inside the kernel over NVLink.
 cpu_baseline     : the NumPy float64 oracle port on the host cores (bounded sample), timed in this run.
-cpu_baseline_ref : the UNMODIFIED reference under the jax.numpy stand-in at config 1, timed in the build container
-            (it is Python and cannot travel to the GPU box; profiles/r02_ref_standin_c1.json).
+cpu_baseline_ref : the UNMODIFIED reference under the jax.numpy stand-in at config 1 (and at configs 2 and 5 with a
+            reduced ensemble), timed in the build container (it is Python and cannot travel to the GPU box;
+            profiles/r02_ref_standin_c1.json, r02_ref_standin_reduced.json).
 """
 from __future__ import annotations
 
@@ -604,7 +605,11 @@ def main():
         cpu_ref = None
         try:
             cpu_ref = json.load(open(os.path.join(ROOT, "profiles", "r02_ref_standin_c1.json")))
-        except (OSError, ValueError):
+            # the same unmodified reference loop on configs 2 and 5 at reduced ensemble size (its rate per
+            # particle-leapfrog-step does not depend on P: a serial Python loop over particles)
+            red = json.load(open(os.path.join(ROOT, "profiles", "r02_ref_standin_reduced.json")))
+            cpu_ref["reduced_configs"] = {k: red[k] for k in ("c2", "c5")}
+        except (OSError, ValueError, KeyError):
             pass
         line = {
             "metric": "particle-leapfrog-steps/sec", "value": value, "unit": "particle-leapfrog-steps/s",
