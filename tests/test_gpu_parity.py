@@ -1816,3 +1816,32 @@ def test_run_rejects_non_finite_ratios_by_default(E):
     hmc3.run(1, 1 / KB)
     torch.cuda.synchronize()
     assert not torch.isfinite(ens3.q[:, :64]).all()
+
+
+def test_tensor_of_another_device_is_refused(E):
+    """The C-ABI checks DLTensor.device.device_id against the context's device (and the device tensors of one call
+    against each other): a tensor that claims to live on another GPU is refused with EHMC_ERR_INVALID instead of
+    being dereferenced on the wrong device, and the refusal leaves no state behind."""
+    import ctypes
+
+    import torch
+
+    q = torch.ones((2, 8), dtype=torch.float64, device="cuda")
+    e = torch.empty(8, dtype=torch.float64, device="cuda")
+    pot = E.HarmonicPotential([1.0, 2.0])
+    ctx = E._lib.Context.get()
+    view = E._lib.DL(q)
+    dev_id = ctypes.c_int32.from_address(view.ptr + 12)  # DLTensor: void* data; int32 device_type; int32 device_id
+    assert dev_id.value == q.device.index
+    dev_id.value = q.device.index + 1
+    try:
+        with pytest.raises(E._lib.EhmcError) as ei:
+            E._lib.potential_eval(ctx, pot.handle(64, ctx), view, e, None)
+        assert "device" in str(ei.value).lower()
+        with pytest.raises(E._lib.EhmcError):
+            E._lib.potential_eval(ctx, pot.handle(64, ctx), view, None, None)  # alone: wrong device for the context
+    finally:
+        dev_id.value = q.device.index
+    E._lib.potential_eval(ctx, pot.handle(64, ctx), view, e, None)
+    torch.cuda.synchronize()
+    assert torch.allclose(e, torch.full_like(e, 1.5))
