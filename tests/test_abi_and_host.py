@@ -226,3 +226,46 @@ def test_logistic_recognition_from_logits():
         A.logisticSpecFromLinearLogits(lambda th: np.tanh(X @ th), 4, y, 1.0)  # not linear
     with pytest.raises(NotImplementedError):
         A.logisticSpecFromLinearLogits(lambda th: X @ th, 4, y + 0.5, 1.0)  # not 0/1 observations
+
+
+def test_checkpoint_round_trip_of_driver_state_on_host(tmp_path):
+    """saveCheckpoint / loadCheckpoint carry everything the next call depends on: positions, masses, Philox (seed,
+    iteration), step size, the trajectory length actually in use (numSteps and the simulTime that drifted with it),
+    the flags and the mass scales (no GPU needed: nothing is launched)."""
+    ens = E.Ensemble(3, 16)
+    ens.q[:] = np.arange(48.0).reshape(3, 16)
+    ens.mass[:] = 2.0
+    hmc = E.HMC(ens, 1.0, 0.1, None, potential=E.HarmonicPotential(np.ones(3)), bugCompat=False, rejectNonFinite=True)
+    hmc.iteration, hmc.stepSize = 77, 0.25
+    hmc.integrator.stepSize, hmc.integrator.numSteps = 0.25, 10
+    hmc.simulTime = hmc.integrator.finalTime = 2.5
+    hmc.massScale = np.array([1.0, 2.0, 4.0])
+    E.io.saveCheckpoint(str(tmp_path / "ck"), hmc)
+    ens2 = E.Ensemble(3, 16)
+    hmc2 = E.HMC(ens2, 1.0, 0.1, None, potential=E.HarmonicPotential(np.ones(3)))
+    E.io.loadCheckpoint(str(tmp_path / "ck"), hmc2)
+    assert np.array_equal(ens2.q, ens.q) and np.array_equal(ens2.mass, ens.mass)
+    assert hmc2.integrator.q is ens2.q and hmc2.iteration == 77 and hmc2.seed == hmc.seed
+    assert hmc2.stepSize == 0.25 and hmc2.integrator.stepSize == 0.25
+    assert hmc2.integrator.numSteps == 10 and hmc2.simulTime == 2.5 and hmc2.integrator.finalTime == 2.5
+    assert hmc2.bugCompat is False and hmc2.rejectNonFinite is True
+    np.testing.assert_array_equal(hmc2.massScale, [1.0, 2.0, 4.0])
+    hmc.rejectNonFinite, hmc.massScale = None, None
+    E.io.saveCheckpoint(str(tmp_path / "ck2"), hmc)
+    E.io.loadCheckpoint(str(tmp_path / "ck2"), hmc2)
+    assert hmc2.rejectNonFinite is None and hmc2.massScale is None
+    with pytest.raises(ValueError):
+        E.io.loadCheckpoint(str(tmp_path / "ck2"), E.HMC(E.Ensemble(3, 8), 1.0, 0.1, None, potential=E.HarmonicPotential(np.ones(3))))
+
+
+def test_run_argument_validation_without_a_gpu():
+    """HMC.run refuses inconsistent requests before anything is launched."""
+    ens = E.Ensemble(2, 8)
+    hmc = E.HMC(ens, 1.0, 0.1, None, potential=E.HarmonicPotential(np.ones(2)))
+    with pytest.raises(ValueError):
+        hmc.run(1, 1.0, adaptLag=5)
+    with pytest.raises(ValueError):
+        hmc.run(1, 1.0, adaptMass=True)  # needs adapt=True
+    with pytest.raises(ValueError):
+        hmc.run(1, 1.0, adapt=True, deviceAdapt=True, adaptLag=2)
+    assert hmc._inRun is False  # the guard of run() is released on every exit path
