@@ -189,6 +189,33 @@ def test_philox_stream_moments():
         assert abs(u.mean() - 0.5) < 0.01 and u.min() >= 0 and u.max() < 1
 
 
+def test_philox_stream_version_2_uniform_rule():
+    """Stream version 2 (include/ehmc.h, EHMC_RNG_STREAM_VERSION): float32 states with D mod 4 in {1, 2} take the
+    Metropolis uniform from word z of the last normal block (block D // 4), every other case from word x (float64:
+    x, y) of block 0xFFFFFFFF; the normals do not depend on the rule, and the uniform is independent of them."""
+    seed, it = 0x0123456789ABCDEF, (3 << 32) | 17
+    pid = np.arange(5000, dtype=np.uint64) + (1 << 33)
+    lo, hi = pid & np.uint64(0xFFFFFFFF), pid >> np.uint64(32)
+    k0, k1, itw = seed & 0xFFFFFFFF, ((seed >> 32) ^ (it >> 32)) & 0xFFFFFFFF, it & 0xFFFFFFFF
+    assert O.PHILOX_STREAM_VERSION == 2
+    for D in range(1, 13):
+        z, u = O.philox_stream(seed, it, pid, D, np.float32)
+        if D % 4 in (1, 2):
+            _, _, w, _ = O.philox4x32_10(lo, hi, D // 4, itw, k0, k1)
+        else:
+            w, _, _, _ = O.philox4x32_10(lo, hi, O.PHILOX_UNIFORM_BLOCK, itw, k0, k1)
+        assert np.array_equal(u, (w >> np.uint32(8)).astype(np.float64) * 2.0**-24)
+        # the same dimensions of a wider state are the same normals (blocks are per 4 dimensions)
+        z12, _ = O.philox_stream(seed, it, pid, 12, np.float32)
+        assert np.array_equal(z, z12[:D])
+        assert abs(np.corrcoef(u, z[D - 1])[0, 1]) < 0.05
+    for D in (1, 2, 5):  # float64: all four words of a normal block are used, the uniform keeps its own block
+        _, u = O.philox_stream(seed, it, pid, D, np.float64)
+        x, y, _, _ = O.philox4x32_10(lo, hi, O.PHILOX_UNIFORM_BLOCK, itw, k0, k1)
+        u53 = ((x >> np.uint32(6)).astype(np.uint64) << np.uint64(27)) | (y >> np.uint32(5)).astype(np.uint64)
+        assert np.array_equal(u, u53.astype(np.float64) * 2.0**-53)
+
+
 def test_ess_iid_and_correlated():
     rng = np.random.RandomState(5)
     x = rng.standard_normal((400, 64))
