@@ -38,7 +38,7 @@ static int ens_launch(ehmc_ctx* c, const IterArgs<T>& A, const Pot& pot, EnsRunA
   int bshift = 0;
   // (sweep in profiles/r02_fused_probe_groups.txt: fewer, larger groups make the next iteration's batches wait for
   // their group's mark -- 256 groups: 42 us per iteration at 2^19 x L = 20, 2048: 32.3, 4096: 31.1; short trajectories
-  // prefer 2048: 21.4 against 22.3 us at L = 4)
+  // prefer 2048: 21.4 against 22.3 us at L = 4; 8192 groups cost the reducers more than they save: 35.9 us)
   const long long gmax = c->ens_groups > 0 ? c->ens_groups : (A.L > 8 ? 4096 : 2048);
   while ((nbatch >> bshift) > gmax) ++bshift;
   R.bshift = bshift;
